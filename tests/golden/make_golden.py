@@ -1,0 +1,116 @@
+"""Generate tests/golden/*.npz by running the REAL reference package (imported from /root/reference through a
+throw-away `boxx` shim: boxx is a hard import of the reference, requirements.txt:1, and is not installable
+offline) on seeded synthetic inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+/root/reference does not exist on the GPU box; the tests read only the committed .npz files.
+"""
+import os
+import sys
+import tempfile
+import textwrap
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+SHIM = textwrap.dedent('''
+    """Minimal stand-in for the `boxx` names the reference's hot path touches (throw-away, never shipped)."""
+    import contextlib, glob as _glob
+    import numpy as np
+    import cv2
+    from numpy import pi, arctan, tan
+    glob = _glob.glob
+    @contextlib.contextmanager
+    def inpkg():
+        yield
+    def npa(x):
+        return np.array(x)
+    def imread(p):
+        return cv2.imread(p)[..., ::-1]
+    def imsave(p, a):
+        cv2.imwrite(p, a[..., ::-1])
+    def resize(img, arg2, interpolation=None):
+        # boxx.resize semantics are not available offline; the golden vectors only use ratio == 1 paths
+        hw = img.shape[:2]
+        if isinstance(arg2, (int, float)):
+            if arg2 == 1:
+                return img
+            new = (int(round(hw[0] * arg2)), int(round(hw[1] * arg2)))
+        else:
+            new = tuple(arg2)
+        if new == tuple(hw):
+            return img
+        raise NotImplementedError("boxx.resize with a real size change is unpinned offline")
+    def increase(*a, **k): return 0
+    def strnum(x, *a, **k): return str(x)
+    def _noop(*a, **k): return None
+    shows = show = showb = tree = loga = mg = timeit = _noop
+''')
+
+
+def import_reference():
+    d = tempfile.mkdtemp(prefix="boxx_shim_")
+    os.makedirs(os.path.join(d, "boxx"))
+    with open(os.path.join(d, "boxx", "__init__.py"), "w") as f:
+        f.write(SHIM)
+    sys.path.insert(0, d)
+    sys.path.insert(0, "/root/reference")
+    import calibrating  # noqa
+    return calibrating
+
+
+def main():
+    import cv2
+    from calibrating_b200 import synth
+    calibrating = import_reference()
+
+    class Param64(calibrating.MetaStereoMatching):
+        """BASELINE config 1 matcher: the reference's parameters with numDisparities=64."""
+        def __init__(self):
+            self.sgbm = cv2.StereoSGBM_create(minDisparity=2, numDisparities=64, blockSize=11, uniquenessRatio=5,
+                                              speckleWindowSize=200, speckleRange=2, disp12MaxDiff=0, P1=968, P2=3872)
+        def __call__(self, a, b):
+            d = self.sgbm.compute(a, b).astype(np.float32).clip(0)
+            d[d < 2 * 16] = 0
+            return d / 16.0
+
+    out = {}
+    # --- case A: 320x240 rig, reference default SemiGlobalBlockMatching (D=218, minD=2, block 11, 5-path)
+    rig = synth.rig_dict((320, 240))
+    img1, img2 = synth.render_rig(rig, seed=0)
+    st = calibrating.Stereo.load(rig)
+    st.set_stereo_matching(calibrating.SemiGlobalBlockMatching({"max_size": 4000}), max_depth=3.5)
+    with np.errstate(all="ignore"):
+        res = st.get_depth(img1, img2)
+    np.savez_compressed(os.path.join(HERE, "rig320_default.npz"), img1=img1, img2=img2,
+                        min_disparity=st.min_disparity, K=st.K, R1=st.R1, R2=st.R2,
+                        map1x=st.undistort_rectify_map1[0][::16, ::16], map2y=st.undistort_rectify_map2[1][::16, ::16],
+                        **{k: (v.astype(np.float32) if v.dtype == np.float64 else v) for k, v in res.items()})
+    out["rig320_default"] = {k: (v.shape, str(v.dtype)) for k, v in res.items()}
+    # --- case B: 320x240 rig, 64 disparities, no translation (max_depth=None)
+    st = calibrating.Stereo.load(rig)
+    st.set_stereo_matching(Param64())
+    with np.errstate(all="ignore"):
+        res = st.get_depth(img1, img2)
+    np.savez_compressed(os.path.join(HERE, "rig320_d64.npz"), min_disparity=st.min_disparity,
+                        **{k: (v.astype(np.float32) if v.dtype == np.float64 else v) for k, v in res.items()
+                           if k in ("disparity", "rectify_depth", "unrectify_depth", "undistort_img1")})
+    # --- case C: raw cv2.StereoSGBM outputs on a small rectified pair, both modes (pins oracle/sgbm_ref.c)
+    l, r, _ = synth.rectified_pair(96, 200, 48, seed=3)
+    for mode, name in ((0, "sgbm"), (1, "hh")):
+        m = cv2.StereoSGBM_create(minDisparity=0, numDisparities=48, blockSize=5, P1=8 * 3 * 25, P2=32 * 3 * 25,
+                                  disp12MaxDiff=1, uniquenessRatio=5, speckleWindowSize=50, speckleRange=2, mode=mode)
+        out[name] = m.compute(l, r)
+    m = cv2.StereoSGBM_create(minDisparity=2, numDisparities=40, blockSize=11, P1=968, P2=3872, disp12MaxDiff=0,
+                              uniquenessRatio=5, speckleWindowSize=200, speckleRange=2)
+    np.savez_compressed(os.path.join(HERE, "sgbm_small.npz"), left=l, right=r, disp_sgbm=out["sgbm"], disp_hh=out["hh"],
+                        disp_refparams=m.compute(l, r), cv2_version=cv2.__version__)
+    print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")), "cv2", cv2.__version__)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,14 @@
+"""calibrating_b200 -- B200-native engine for the `Stereo.get_depth` hot path of DIYer22/calibrating.
+
+Public surface mirrors the reference's names for this path:
+    Stereo, Cam                      (calibrating/stereo_camera.py, camera.py: load/dump schema only)
+    MetaStereoMatching, SemiGlobalBlockMatching   (calibrating/stereo_matching.py:10-70)
+    StereoSGBM_create                (keyword-compatible with cv2.StereoSGBM_create, MODE_SGBM / MODE_HH)
+Everything numeric runs in libb2s.so (hand-written sm_100a CUDA behind the C-ABI of include/b2s.h).
+"""
+from .stereo_matching import (MODE_HH, MODE_SGBM, B200StereoMatching, MetaStereoMatching, SemiGlobalBlockMatching,
+                              StereoSGBM, StereoSGBM_create)
+from .stereo_camera import Cam, Stereo
+
+__all__ = ["Stereo", "Cam", "MetaStereoMatching", "SemiGlobalBlockMatching", "B200StereoMatching", "StereoSGBM",
+           "StereoSGBM_create", "MODE_SGBM", "MODE_HH"]

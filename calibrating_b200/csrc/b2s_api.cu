@@ -1,0 +1,487 @@
+// b2s_api.cu -- the C-ABI of libb2s.so (include/b2s.h): handle lifecycle, parameter normalisation, buffer
+// management and the per-pair kernel schedule.  No torch types, no C++ exceptions across the boundary.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "b2s_internal.h"
+
+static thread_local std::string g_create_err;
+
+static int fail(b2s_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_err = buf;
+    return code;
+}
+#define CK(c, call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t _e = (call);                                                                             \
+        if (_e != cudaSuccess) return fail(c, B2S_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" {
+
+int b2s_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *b2s_last_error(b2s_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int b2s_create(int device, b2s_handle *out)
+{
+    if (!out) return fail(nullptr, B2S_EINVAL, "b2s_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(nullptr, B2S_ECUDA, "b2s_create: no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(nullptr, B2S_EINVAL, "b2s_create: device %d out of range [0,%d)", device, n);
+    b2s_ctx *c = new (std::nothrow) b2s_ctx();
+    if (!c) return fail(nullptr, B2S_EINVAL, "b2s_create: out of host memory");
+    c->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete c;
+        return fail(nullptr, B2S_ECUDA, "b2s_create: %s", cudaGetErrorString(e));
+    }
+    for (auto &ev : c->ev) cudaEventCreate(&ev);
+    // Lanczos4 fixed-point table (1024 x 8 x 8 int16 = 128 KB), shared by both rectify remaps
+    std::vector<int16_t> tab(1024 * 64);
+    build_lanczos4_table(tab.data());
+    if ((e = c->lanczos_tab.ensure(tab.size() * 2)) != cudaSuccess ||
+        (e = cudaMemcpy(c->lanczos_tab.p, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        b2s_destroy(c);
+        return fail(nullptr, B2S_ECUDA, "b2s_create: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return B2S_OK;
+}
+
+int b2s_destroy(b2s_handle c)
+{
+    if (!c) return B2S_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->left, &c->right, &c->planesL, &c->planesR, &c->C, &c->S, &c->raw, &c->disp16, &c->disp2key, &c->labels,
+                      &c->sizes, &c->med, &c->dispf, &c->map1x, &c->map1y, &c->map2x, &c->map2y, &c->vmask, &c->umapx, &c->umapy,
+                      &c->und_xy, &c->und_fxy, &c->img1, &c->img2, &c->rect1, &c->rect2, &c->und1, &c->dispfinal, &c->rdepth,
+                      &c->udepth, &c->lanczos_tab, &c->stage_f32};
+    for (DevBuf *b : bufs) b->release();
+    for (auto &ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return B2S_OK;
+}
+
+int b2s_sync(b2s_handle c)
+{
+    if (!c) return B2S_EINVAL;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return B2S_OK;
+}
+
+int b2s_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return B2S_EINVAL;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(nullptr, B2S_ECUDA, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return B2S_OK;
+}
+int b2s_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? B2S_OK : B2S_ECUDA; }
+
+int b2s_set_sgbm_params(b2s_handle c, const b2s_sgbm_params *p)
+{
+    if (!c || !p) return B2S_EINVAL;
+    if (p->num_disparities <= 0) return fail(c, B2S_EINVAL, "numDisparities must be > 0 (got %d)", p->num_disparities);
+    if (p->num_disparities > 256) return fail(c, B2S_EINVAL, "numDisparities > 256 is not supported yet (got %d)", p->num_disparities);
+    if (p->min_disparity < 0) return fail(c, B2S_EINVAL, "negative minDisparity is not supported (got %d)", p->min_disparity);
+    if (p->mode != 0 && p->mode != 1) return fail(c, B2S_EINVAL, "mode must be 0 (MODE_SGBM) or 1 (MODE_HH), got %d", p->mode);
+    int P1 = p->P1 > 0 ? p->P1 : 2;
+    int P2 = p->P2 > 0 ? p->P2 : 5;
+    if (P2 < P1 + 1) P2 = P1 + 1;
+    if (P2 > 32767 - 1) return fail(c, B2S_EINVAL, "P2 = %d does not fit the int16 cost type", P2);
+    c->prm = *p;
+    c->have_prm = true;
+    c->have_volume = false;
+    return B2S_OK;
+}
+
+} // extern "C"
+
+// SURVEY.md Appendix A.1
+static int make_geom(b2s_ctx *c, int H, int W, int cn)
+{
+    if (!c->have_prm) return fail(c, B2S_ESTATE, "b2s_set_sgbm_params has not been called");
+    if (cn != 1 && cn != 3) return fail(c, B2S_EINVAL, "images must have 1 or 3 channels (got %d)", cn);
+    if (H <= 0 || W <= 0 || W > 65535) return fail(c, B2S_EINVAL, "bad image size %dx%d", W, H);
+    const b2s_sgbm_params &p = c->prm;
+    SgbmGeom g;
+    g.H = H; g.W = W; g.cn = cn;
+    g.minD = p.min_disparity;
+    g.maxD = g.minD + p.num_disparities;
+    g.D = p.num_disparities;
+    g.NP = (g.D + 63) / 64;
+    g.Dp = 64 * g.NP;
+    int bs = p.block_size > 0 ? p.block_size : 5;
+    g.SW2 = g.SH2 = bs / 2;
+    g.ftzero = (p.pre_filter_cap > 15 ? p.pre_filter_cap : 15) | 1;
+    g.uniq = p.uniqueness_ratio >= 0 ? p.uniqueness_ratio : 10;
+    g.d12 = p.disp12_max_diff > 0 ? p.disp12_max_diff : 1;
+    g.P1 = p.P1 > 0 ? p.P1 : 2;
+    g.P2 = p.P2 > 0 ? p.P2 : 5;
+    if (g.P2 < g.P1 + 1) g.P2 = g.P1 + 1;
+    g.minX1 = g.maxD;
+    g.width1 = W - g.maxD;
+    g.invalid = (g.minD - 1) * 16;
+    g.speckle_window = p.speckle_window_size;
+    g.speckle_range = p.speckle_range;
+    g.mode = p.mode;
+    if (W - g.maxD <= g.SW2) return fail(c, B2S_ESIZE, "input images are too small for your window size and max disparity");
+    if (g.ftzero > 127) return fail(c, B2S_EINVAL, "preFilterCap %d too large", p.pre_filter_cap);
+    c->g = g;
+    size_t npx = (size_t)H * W, vol = (size_t)H * g.width1 * g.Dp * sizeof(int16_t);
+    CK(c, c->planesL.ensure(npx * 2 * cn * 4));
+    CK(c, c->planesR.ensure(npx * 2 * cn * 4));
+    CK(c, c->C.ensure(vol));
+    CK(c, c->S.ensure(vol));
+    CK(c, c->raw.ensure(npx * 2));
+    CK(c, c->disp16.ensure(npx * 2));
+    CK(c, c->med.ensure(npx * 2));
+    CK(c, c->disp2key.ensure((size_t)H * (W + 2) * 4));
+    CK(c, c->labels.ensure(npx * 4));
+    CK(c, c->sizes.ensure(npx * 4));
+    CK(c, c->dispf.ensure(npx * 4));
+    return B2S_OK;
+}
+
+// events: 0 start, 1 after rectify, 2 after cost, 3 after aggregate, 4 after wta, 5 after post, 6 after depth
+static int matcher_dev(b2s_ctx *c, const uint8_t *dl, const uint8_t *dr, int16_t *d_out16, float *d_outf, bool timed)
+{
+    if (timed) cudaEventRecord(c->ev[1], c->stream);
+    CK(c, launch_cost_volume(c, dl, dr));
+    if (timed) cudaEventRecord(c->ev[2], c->stream);
+    int nl = 0;
+    CK(c, launch_aggregate(c, &nl));
+    c->timing.aggregate_launches = nl;
+    if (timed) cudaEventRecord(c->ev[3], c->stream);
+    CK(c, launch_wta(c));
+    if (timed) cudaEventRecord(c->ev[4], c->stream);
+    CK(c, launch_post(c, d_out16, d_outf));
+    if (timed) cudaEventRecord(c->ev[5], c->stream);
+    c->have_volume = true;
+    return B2S_OK;
+}
+
+static void collect_timing(b2s_ctx *c, bool chain)
+{
+    auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, c->ev[a], c->ev[b]); return t; };
+    c->timing.rectify_ms = chain ? ms(0, 1) : 0.f;
+    c->timing.cost_ms = ms(1, 2);
+    c->timing.aggregate_ms = ms(2, 3);
+    c->timing.wta_ms = ms(3, 4);
+    c->timing.post_ms = ms(4, 5);
+    c->timing.depth_ms = chain ? ms(5, 6) : 0.f;
+    c->timing.total_ms = ms(0, chain ? 6 : 5);
+}
+
+static int compute_disparity_host(b2s_ctx *c, const uint8_t *left, const uint8_t *right, int H, int W, int cn, int16_t *out16, float *outf,
+                                  bool sync)
+{
+    if (!c || !left || !right) return B2S_EINVAL;
+    CK(c, cudaSetDevice(c->device));
+    int rc = make_geom(c, H, W, cn);
+    if (rc) return rc;
+    size_t nb = (size_t)H * W * cn, npx = (size_t)H * W;
+    CK(c, c->left.ensure(nb));
+    CK(c, c->right.ensure(nb));
+    long long l0 = c->launches;
+    cudaEventRecord(c->ev[0], c->stream);
+    CK(c, cudaMemcpyAsync(c->left.p, left, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->right.p, right, nb, cudaMemcpyHostToDevice, c->stream));
+    rc = matcher_dev(c, c->left.as<uint8_t>(), c->right.as<uint8_t>(), c->disp16.as<int16_t>(), outf ? c->dispf.as<float>() : nullptr, true);
+    if (rc) return rc;
+    if (out16) CK(c, cudaMemcpyAsync(out16, c->disp16.p, npx * 2, cudaMemcpyDeviceToHost, c->stream));
+    if (outf) CK(c, cudaMemcpyAsync(outf, c->dispf.p, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+    c->timing.total_launches = (int)(c->launches - l0);
+    if (sync) {
+        CK(c, cudaStreamSynchronize(c->stream));
+        collect_timing(c, false);
+    }
+    return B2S_OK;
+}
+
+extern "C" {
+
+int b2s_compute_disparity(b2s_handle c, const uint8_t *left, const uint8_t *right, int H, int W, int cn, int16_t *out16, float *outf)
+{
+    return compute_disparity_host(c, left, right, H, W, cn, out16, outf, true);
+}
+int b2s_compute_disparity_async(b2s_handle c, const uint8_t *left, const uint8_t *right, int H, int W, int cn, int16_t *out16, float *outf)
+{
+    return compute_disparity_host(c, left, right, H, W, cn, out16, outf, false);
+}
+int b2s_compute_disparity_dev(b2s_handle c, const uint8_t *dl, const uint8_t *dr, int H, int W, int cn, int16_t *d_out16, float *d_outf)
+{
+    if (!c || !dl || !dr) return B2S_EINVAL;
+    CK(c, cudaSetDevice(c->device));
+    int rc = make_geom(c, H, W, cn);
+    if (rc) return rc;
+    long long l0 = c->launches;
+    rc = matcher_dev(c, dl, dr, d_out16 ? d_out16 : c->disp16.as<int16_t>(), d_outf, false);
+    c->timing.total_launches = (int)(c->launches - l0);
+    return rc;
+}
+
+int b2s_set_rig(b2s_handle c, const b2s_rig *r)
+{
+    if (!c || !r) return B2S_EINVAL;
+    if (!r->map1x || !r->map1y || !r->map2x || !r->map2y || !r->valid_mask1) return fail(c, B2S_EINVAL, "b2s_set_rig: rectify maps / mask missing");
+    if (r->W <= 0 || r->H <= 0 || r->W1 <= 0 || r->H1 <= 0 || r->W2 <= 0 || r->H2 <= 0) return fail(c, B2S_EINVAL, "b2s_set_rig: bad sizes");
+    if (r->interp != 0 && r->interp != 1) return fail(c, B2S_EINVAL, "b2s_set_rig: interp must be 0 (LANCZOS4) or 1 (LINEAR)");
+    CK(c, cudaSetDevice(c->device));
+    size_t n = (size_t)r->W * r->H, n1 = (size_t)r->W1 * r->H1;
+    struct Up { DevBuf *b; const void *src; size_t bytes; } ups[] = {
+        {&c->map1x, r->map1x, n * 4}, {&c->map1y, r->map1y, n * 4}, {&c->map2x, r->map2x, n * 4}, {&c->map2y, r->map2y, n * 4},
+        {&c->vmask, r->valid_mask1, n}, {&c->umapx, r->unrect_mapx, n1 * 4}, {&c->umapy, r->unrect_mapy, n1 * 4},
+        {&c->und_xy, r->undist_xy, n1 * 4}, {&c->und_fxy, r->undist_fxy, n1 * 2}};
+    for (auto &u : ups) {
+        if (!u.src) continue;
+        CK(c, u.b->ensure(u.bytes));
+        CK(c, cudaMemcpyAsync(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->rW = r->W; c->rH = r->H; c->rW1 = r->W1; c->rH1 = r->H1; c->rW2 = r->W2; c->rH2 = r->H2;
+    c->r_min_disp = r->min_disparity; c->r_interp = r->interp;
+    c->r_m[0] = r->unrect_m[0]; c->r_m[1] = r->unrect_m[1]; c->r_m[2] = r->unrect_m[2];
+    c->r_fxb = r->fx_baseline; c->r_max_depth = r->max_depth;
+    c->have_rig = true;
+    CK(c, c->dispfinal.ensure(n * 4));
+    CK(c, c->rdepth.ensure(n * 8));
+    CK(c, c->udepth.ensure(n1 * 8));
+    return B2S_OK;
+}
+
+} // extern "C"
+
+static int rectify_dev(b2s_ctx *c, const uint8_t *img1, const uint8_t *img2, int cn)
+{
+    size_t n1 = (size_t)c->rW1 * c->rH1 * cn, n2 = (size_t)c->rW2 * c->rH2 * cn, n = (size_t)c->rW * c->rH * cn;
+    CK(c, c->img1.ensure(n1));
+    CK(c, c->img2.ensure(n2));
+    CK(c, c->rect1.ensure(n));
+    CK(c, c->rect2.ensure(n));
+    CK(c, cudaMemcpyAsync(c->img1.p, img1, n1, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->img2.p, img2, n2, cudaMemcpyHostToDevice, c->stream));
+    CK(c, launch_remap_u8(c, c->img1.as<uint8_t>(), c->rH1, c->rW1, cn, c->map1x.as<float>(), c->map1y.as<float>(), c->rH, c->rW, 0,
+                          c->r_interp, c->rect1.as<uint8_t>()));
+    CK(c, launch_remap_u8(c, c->img2.as<uint8_t>(), c->rH2, c->rW2, cn, c->map2x.as<float>(), c->map2y.as<float>(), c->rH, c->rW,
+                          c->r_min_disp, c->r_interp, c->rect2.as<uint8_t>()));
+    return B2S_OK;
+}
+
+static int depth_tail(b2s_ctx *c, const float *d_disp, int add_min, const uint8_t *d_img1, int cn, int want_unrectify, const b2s_depth_out *o)
+{
+    if (want_unrectify && (!c->umapx.p || !c->umapy.p)) return fail(c, B2S_ESTATE, "rig has no unrectify maps");
+    CK(c, launch_depth(c, d_disp, add_min, want_unrectify));
+    size_t n = (size_t)c->rW * c->rH, n1 = (size_t)c->rW1 * c->rH1;
+    bool und = want_unrectify && d_img1 && o->undistort_img1;
+    if (und) {
+        if (!c->und_xy.p || !c->und_fxy.p) return fail(c, B2S_ESTATE, "rig has no undistort maps");
+        CK(c, c->und1.ensure(n1 * cn));
+        CK(c, launch_undistort_u8(c, d_img1, c->rH1, c->rW1, cn, c->und_xy.as<int16_t>(), c->und_fxy.as<uint16_t>(), c->und1.as<uint8_t>()));
+    }
+    cudaEventRecord(c->ev[6], c->stream);
+    if (o->disparity) CK(c, cudaMemcpyAsync(o->disparity, c->dispfinal.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (o->rectify_depth) CK(c, cudaMemcpyAsync(o->rectify_depth, c->rdepth.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (want_unrectify && o->unrectify_depth) CK(c, cudaMemcpyAsync(o->unrectify_depth, c->udepth.p, n1 * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (und) CK(c, cudaMemcpyAsync(o->undistort_img1, c->und1.p, n1 * cn, cudaMemcpyDeviceToHost, c->stream));
+    return B2S_OK;
+}
+
+static int get_depth_impl(b2s_ctx *c, const uint8_t *img1, const uint8_t *img2, int cn, int want_unrectify, const b2s_depth_out *o, bool sync)
+{
+    if (!c || !img1 || !img2 || !o) return B2S_EINVAL;
+    if (!c->have_rig) return fail(c, B2S_ESTATE, "b2s_set_rig has not been called");
+    CK(c, cudaSetDevice(c->device));
+    int rc = make_geom(c, c->rH, c->rW, cn);
+    if (rc) return rc;
+    long long l0 = c->launches;
+    cudaEventRecord(c->ev[0], c->stream);
+    if ((rc = rectify_dev(c, img1, img2, cn))) return rc;
+    if ((rc = matcher_dev(c, c->rect1.as<uint8_t>(), c->rect2.as<uint8_t>(), c->disp16.as<int16_t>(), c->dispf.as<float>(), true))) return rc;
+    if ((rc = depth_tail(c, c->dispf.as<float>(), 1, c->img1.as<uint8_t>(), cn, want_unrectify, o))) return rc;
+    size_t n = (size_t)c->rW * c->rH;
+    if (o->rectify_img1) CK(c, cudaMemcpyAsync(o->rectify_img1, c->rect1.p, n * cn, cudaMemcpyDeviceToHost, c->stream));
+    if (o->rectify_img2) CK(c, cudaMemcpyAsync(o->rectify_img2, c->rect2.p, n * cn, cudaMemcpyDeviceToHost, c->stream));
+    if (o->disp16) CK(c, cudaMemcpyAsync(o->disp16, c->disp16.p, n * 2, cudaMemcpyDeviceToHost, c->stream));
+    c->timing.total_launches = (int)(c->launches - l0);
+    if (sync) {
+        CK(c, cudaStreamSynchronize(c->stream));
+        collect_timing(c, true);
+    }
+    return B2S_OK;
+}
+
+extern "C" {
+
+int b2s_rectify(b2s_handle c, const uint8_t *img1, const uint8_t *img2, int cn, uint8_t *out1, uint8_t *out2)
+{
+    if (!c || !img1 || !img2) return B2S_EINVAL;
+    if (!c->have_rig) return fail(c, B2S_ESTATE, "b2s_set_rig has not been called");
+    if (cn != 1 && cn != 3) return fail(c, B2S_EINVAL, "images must have 1 or 3 channels (got %d)", cn);
+    CK(c, cudaSetDevice(c->device));
+    int rc = rectify_dev(c, img1, img2, cn);
+    if (rc) return rc;
+    size_t n = (size_t)c->rW * c->rH * cn;
+    if (out1) CK(c, cudaMemcpyAsync(out1, c->rect1.p, n, cudaMemcpyDeviceToHost, c->stream));
+    if (out2) CK(c, cudaMemcpyAsync(out2, c->rect2.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return B2S_OK;
+}
+
+int b2s_get_depth(b2s_handle c, const uint8_t *img1, const uint8_t *img2, int cn, int want_unrectify, const b2s_depth_out *o)
+{
+    return get_depth_impl(c, img1, img2, cn, want_unrectify, o, true);
+}
+int b2s_get_depth_async(b2s_handle c, const uint8_t *img1, const uint8_t *img2, int cn, int want_unrectify, const b2s_depth_out *o)
+{
+    return get_depth_impl(c, img1, img2, cn, want_unrectify, o, false);
+}
+
+int b2s_depth_from_disparity(b2s_handle c, const float *disparity, const uint8_t *img1, int cn, int want_unrectify, const b2s_depth_out *o)
+{
+    if (!c || !disparity || !o) return B2S_EINVAL;
+    if (!c->have_rig) return fail(c, B2S_ESTATE, "b2s_set_rig has not been called");
+    if (img1 && cn != 1 && cn != 3) return fail(c, B2S_EINVAL, "images must have 1 or 3 channels (got %d)", cn);
+    CK(c, cudaSetDevice(c->device));
+    size_t n = (size_t)c->rW * c->rH, n1 = (size_t)c->rW1 * c->rH1;
+    CK(c, c->stage_f32.ensure(n * 4));
+    CK(c, cudaMemcpyAsync(c->stage_f32.p, disparity, n * 4, cudaMemcpyHostToDevice, c->stream));
+    if (img1) {
+        CK(c, c->img1.ensure(n1 * cn));
+        CK(c, cudaMemcpyAsync(c->img1.p, img1, n1 * cn, cudaMemcpyHostToDevice, c->stream));
+    }
+    int rc = depth_tail(c, c->stage_f32.as<float>(), 1, img1 ? c->img1.as<uint8_t>() : nullptr, cn, want_unrectify, o);
+    if (rc) return rc;
+    CK(c, cudaStreamSynchronize(c->stream));
+    return B2S_OK;
+}
+
+int b2s_disparity_to_depth(b2s_handle c, const float *disparity, double *depth)
+{
+    if (!c || !disparity || !depth) return B2S_EINVAL;
+    if (!c->have_rig) return fail(c, B2S_ESTATE, "b2s_set_rig has not been called");
+    CK(c, cudaSetDevice(c->device));
+    size_t n = (size_t)c->rW * c->rH;
+    CK(c, c->stage_f32.ensure(n * 4));
+    CK(c, cudaMemcpyAsync(c->stage_f32.p, disparity, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(c, launch_depth_bare(c, c->stage_f32.as<float>(), c->rdepth.as<double>()));
+    CK(c, cudaMemcpyAsync(depth, c->rdepth.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return B2S_OK;
+}
+
+int b2s_unrectify_depth(b2s_handle c, const double *rectify_depth, double *out)
+{
+    if (!c || !rectify_depth || !out) return B2S_EINVAL;
+    if (!c->have_rig || !c->umapx.p || !c->umapy.p) return fail(c, B2S_ESTATE, "rig (with unrectify maps) has not been set");
+    CK(c, cudaSetDevice(c->device));
+    size_t n = (size_t)c->rW * c->rH, n1 = (size_t)c->rW1 * c->rH1;
+    CK(c, cudaMemcpyAsync(c->rdepth.p, rectify_depth, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(c, launch_unrectify(c, c->rdepth.as<double>(), c->udepth.as<double>()));
+    CK(c, cudaMemcpyAsync(out, c->udepth.p, n1 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return B2S_OK;
+}
+
+int b2s_undistort_img(b2s_handle c, const uint8_t *img1, int cn, uint8_t *out)
+{
+    if (!c || !img1 || !out) return B2S_EINVAL;
+    if (cn != 1 && cn != 3) return fail(c, B2S_EINVAL, "images must have 1 or 3 channels (got %d)", cn);
+    if (!c->have_rig || !c->und_xy.p || !c->und_fxy.p) return fail(c, B2S_ESTATE, "rig (with undistort maps) has not been set");
+    CK(c, cudaSetDevice(c->device));
+    size_t n1 = (size_t)c->rW1 * c->rH1 * cn;
+    CK(c, c->img1.ensure(n1));
+    CK(c, c->und1.ensure(n1));
+    CK(c, cudaMemcpyAsync(c->img1.p, img1, n1, cudaMemcpyHostToDevice, c->stream));
+    CK(c, launch_undistort_u8(c, c->img1.as<uint8_t>(), c->rH1, c->rW1, cn, c->und_xy.as<int16_t>(), c->und_fxy.as<uint16_t>(), c->und1.as<uint8_t>()));
+    CK(c, cudaMemcpyAsync(out, c->und1.p, n1, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return B2S_OK;
+}
+
+int b2s_volume_dims(b2s_handle c, int *H, int *width1, int *D, int *Dp)
+{
+    if (!c || !c->have_volume) return c ? fail(c, B2S_ESTATE, "no cost volume resident") : B2S_EINVAL;
+    if (H) *H = c->g.H;
+    if (width1) *width1 = c->g.width1;
+    if (D) *D = c->g.D;
+    if (Dp) *Dp = c->g.Dp;
+    return B2S_OK;
+}
+
+int b2s_debug_fetch(b2s_handle c, int which, void *dst, size_t bytes)
+{
+    if (!c || !dst) return B2S_EINVAL;
+    if (!c->have_volume) return fail(c, B2S_ESTATE, "no cost volume resident");
+    CK(c, cudaSetDevice(c->device));
+    const SgbmGeom &g = c->g;
+    size_t vol = (size_t)g.H * g.width1 * g.Dp * 2, need;
+    const void *src;
+    switch (which) {
+    case B2S_FETCH_C: src = c->C.p; need = vol; break;
+    case B2S_FETCH_S: src = c->S.p; need = vol; break;
+    case B2S_FETCH_RAW: src = c->raw.p; need = (size_t)g.H * g.W * 2; break;
+    default: return fail(c, B2S_EINVAL, "b2s_debug_fetch: unknown selector %d", which);
+    }
+    if (bytes != need) return fail(c, B2S_EINVAL, "b2s_debug_fetch: need %zu bytes, got %zu", need, bytes);
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
+    return B2S_OK;
+}
+
+int b2s_timings(b2s_handle c, b2s_timing *t)
+{
+    if (!c || !t) return B2S_EINVAL;
+    *t = c->timing;
+    return B2S_OK;
+}
+
+int b2s_launch_count(b2s_handle c, long long *n)
+{
+    if (!c || !n) return B2S_EINVAL;
+    *n = c->launches;
+    return B2S_OK;
+}
+
+int b2s_bench_aggregate(b2s_handle c, int iters, float *ms_per_iter)
+{
+    if (!c || !ms_per_iter || iters <= 0) return B2S_EINVAL;
+    if (!c->have_volume) return fail(c, B2S_ESTATE, "no cost volume resident (run a disparity computation first)");
+    CK(c, cudaSetDevice(c->device));
+    int nl = 0;
+    CK(c, launch_aggregate(c, &nl)); // warm-up
+    CK(c, cudaEventRecord(c->ev[0], c->stream));
+    for (int i = 0; i < iters; i++) CK(c, launch_aggregate(c, &nl));
+    CK(c, cudaEventRecord(c->ev[7], c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[7]));
+    *ms_per_iter = ms / iters;
+    return B2S_OK;
+}
+
+} // extern "C"

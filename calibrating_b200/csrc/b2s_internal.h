@@ -1,0 +1,95 @@
+// b2s_internal.h -- shared declarations of libb2s.so (not part of the public ABI; see include/b2s.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "b2s.h"
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+// Normalised matcher geometry (== StereoSGBM parameter defaulting in OpenCV).
+struct SgbmGeom {
+    int H, W, cn;
+    int minD, maxD, D, Dp, NP; // Dp = 64*NP >= D: d-lanes padded to a whole warp of packed int16 pairs
+    int minX1, width1;
+    int SW2, SH2, ftzero, uniq, d12, P1, P2, invalid;
+    int speckle_window, speckle_range, mode;
+};
+
+enum { AGG_INIT = 0, AGG_ACCUM = 1 };
+
+struct b2s_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+
+    bool have_prm = false;
+    b2s_sgbm_params prm{};
+    SgbmGeom g{};
+    bool have_volume = false;
+
+    // matcher buffers
+    DevBuf left, right;       // (H,W,cn) u8
+    DevBuf planesL, planesR;  // (H, 2cn, W) uchar4 = (value, lo, hi, 0)
+    DevBuf C, S;              // (H, width1, Dp) int16;  S doubles as the horizontal-sum scratch
+    DevBuf raw, disp16;       // (H,W) int16
+    DevBuf disp2key;          // (H,W+2) u32: (minS<<16)|(0xFFFF-x1) of the winning left pixel, 0xFFFFFFFF = none
+    DevBuf labels, sizes;     // (H,W) int32 each (speckle filter)
+    DevBuf med;               // (H,W) int16 (median output before speckle)
+    DevBuf dispf;             // (H,W) f32
+
+    // rig
+    bool have_rig = false;
+    int rW = 0, rH = 0, rW1 = 0, rH1 = 0, rW2 = 0, rH2 = 0, r_min_disp = 0, r_interp = 0;
+    double r_m[3] = {0, 0, 0}, r_fxb = 0, r_max_depth = 0;
+    DevBuf map1x, map1y, map2x, map2y, vmask, umapx, umapy, und_xy, und_fxy;
+    DevBuf img1, img2, rect1, rect2, und1; // raw inputs and remapped outputs
+    DevBuf dispfinal, rdepth, udepth;      // (H,W) f32, (H,W) f64, (H1,W1) f64
+    DevBuf lanczos_tab;                    // (1024, 8, 8) int16
+    DevBuf stage_f32;                      // upload scratch for b2s_depth_from_disparity
+
+    cudaEvent_t ev[8] = {};
+    b2s_timing timing{};
+};
+
+// ---- kernel launchers (each enqueues on ctx->stream and bumps ctx->launches) --------------------------------------
+// sgbm_cost.cu
+cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t *d_right);
+// sgbm_agg.cu
+cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches);
+cudaError_t agg_configure();
+// sgbm_post.cu
+cudaError_t launch_wta(b2s_ctx *c);
+cudaError_t launch_post(b2s_ctx *c, int16_t *d_out_disp16, float *d_out_disp);
+// remap.cu
+void build_lanczos4_table(int16_t *tab /* 1024*64 */);
+cudaError_t launch_remap_u8(b2s_ctx *c, const uint8_t *src, int sH, int sW, int cn, const float *mapx, const float *mapy,
+                            int dH, int dW, int xshift, int interp, uint8_t *dst);
+cudaError_t launch_undistort_u8(b2s_ctx *c, const uint8_t *src, int H, int W, int cn, const int16_t *xy, const uint16_t *fxy,
+                                uint8_t *dst);
+cudaError_t launch_depth(b2s_ctx *c, const float *d_disp_in, int add_min_disp, int want_unrectify);
+cudaError_t launch_depth_bare(b2s_ctx *c, const float *d_disp, double *d_depth);
+cudaError_t launch_unrectify(b2s_ctx *c, const double *d_depth, double *d_out);

@@ -1,0 +1,264 @@
+// remap.cu -- the remap family of Stereo.get_depth, sm_100a.
+//   Stereo.rectify          calibrating/stereo_camera.py:216-242   cv2.remap(u8, f32 maps, INTER_LANCZOS4) + right-image shift
+//   Stereo.undistort_img    calibrating/stereo_camera.py:430-431   cv2.undistort == CV_16SC2 fixed maps + bilinear
+//   disparity_to_depth      calibrating/stereo_camera.py:408-413   (+ the += min_disparity / valid-mask lines :510-512)
+//   unrectify_depth         calibrating/utils.py:173-200           z' = z*(m.[x,y,1]) then INTER_NEAREST remap
+// cv2 semantics restated: coordinates quantised to 1/32 px with round-half-even, 15-bit
+// fixed-point weight tables summing to exactly 32768, rounding (sum + 2^14) >> 15, constant-0 border.
+#include <math.h>
+
+#include "b2s_internal.h"
+
+// ---- host: cv::initInterTab2D(INTER_LANCZOS4, fixpt) restated ------------------------------------------------------
+static void lanczos4_coeffs(float x, float *co)
+{
+    static const double s45 = 0.70710678118654752440084436210485;
+    static const double cs[8][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+    if (x < 1.1920928955078125e-07f) {
+        for (int i = 0; i < 8; i++) co[i] = 0;
+        co[3] = 1;
+        return;
+    }
+    float sum = 0;
+    double y0 = -(x + 3) * 3.1415926535897932384626433832795 * 0.25, s0 = sin(y0), c0 = cos(y0);
+    for (int i = 0; i < 8; i++) {
+        double y = -(x + 3 - i) * 3.1415926535897932384626433832795 * 0.25;
+        co[i] = (float)((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+        sum += co[i];
+    }
+    sum = 1.f / sum;
+    for (int i = 0; i < 8; i++) co[i] *= sum;
+}
+
+void build_lanczos4_table(int16_t *tab)
+{
+    float t1[32][8];
+    for (int i = 0; i < 32; i++) lanczos4_coeffs((float)i * (1.f / 32), t1[i]);
+    for (int i = 0; i < 32; i++)
+        for (int j = 0; j < 32; j++) {
+            int16_t *it = tab + (size_t)(i * 32 + j) * 64;
+            int isum = 0;
+            for (int a = 0; a < 8; a++)
+                for (int b = 0; b < 8; b++) {
+                    float v = t1[i][a] * t1[j][b];
+                    long r = lrintf(v * 32768.f);
+                    r = r > 32767 ? 32767 : (r < -32768 ? -32768 : r);
+                    it[a * 8 + b] = (int16_t)r;
+                    isum += (int)r;
+                }
+            if (isum != 32768) {
+                int diff = isum - 32768;
+                int Mk = 4 * 8 + 4, mk = 4 * 8 + 4;
+                for (int a = 4; a < 6; a++)
+                    for (int b = 4; b < 6; b++) {
+                        if (it[a * 8 + b] < it[mk]) mk = a * 8 + b;
+                        else if (it[a * 8 + b] > it[Mk]) Mk = a * 8 + b;
+                    }
+                if (diff < 0) it[Mk] = (int16_t)(it[Mk] - diff);
+                else it[mk] = (int16_t)(it[mk] - diff);
+            }
+        }
+}
+
+namespace {
+
+__device__ __forceinline__ int sat_short(int v) { return min(max(v, -32768), 32767); }
+__device__ __forceinline__ unsigned char fix_cast(int sum) { return (unsigned char)min(max((sum + (1 << 14)) >> 15, 0), 255); }
+
+// thread = one destination pixel (all channels).  xshift: destination column x samples the map at x - xshift
+// (Stereo.rectify's translation of rectify_img2, stereo_camera.py:230-240); vacated columns are 0.
+template <int CN, int INTERP>
+__global__ void remap_u8_kernel(const uint8_t *__restrict__ src, int sH, int sW, const float *__restrict__ mapx,
+                                const float *__restrict__ mapy, int dH, int dW, int xshift, const int16_t *__restrict__ tab,
+                                uint8_t *__restrict__ dst)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dW) return;
+    uint8_t *o = dst + ((size_t)y * dW + x) * CN;
+    int xm = x - xshift;
+    if (xm < 0 || xm >= dW) {
+#pragma unroll
+        for (int c = 0; c < CN; c++) o[c] = 0;
+        return;
+    }
+    size_t mi = (size_t)y * dW + xm;
+    int sx = __float2int_rn(mapx[mi] * 32.f), sy = __float2int_rn(mapy[mi] * 32.f);
+    int ix = sat_short(sx >> 5), iy = sat_short(sy >> 5);
+    int fx = sx & 31, fy = sy & 31;
+    int acc[CN];
+#pragma unroll
+    for (int c = 0; c < CN; c++) acc[c] = 0;
+    if (INTERP == 0) {
+        const int x0 = ix - 3, y0 = iy - 3;
+        if (x0 >= sW || x0 + 8 <= 0 || y0 >= sH || y0 + 8 <= 0) {
+#pragma unroll
+            for (int c = 0; c < CN; c++) o[c] = 0;
+            return;
+        }
+        const uint4 *w4 = (const uint4 *)(tab + (size_t)(fy * 32 + fx) * 64);
+        const bool inside = x0 >= 0 && x0 + 8 <= sW && y0 >= 0 && y0 + 8 <= sH;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            uint4 wq = w4[r];
+            int w[8] = {(short)(wq.x & 0xffff), ((int)wq.x) >> 16, (short)(wq.y & 0xffff), ((int)wq.y) >> 16,
+                        (short)(wq.z & 0xffff), ((int)wq.z) >> 16, (short)(wq.w & 0xffff), ((int)wq.w) >> 16};
+            int yy = y0 + r;
+            if (!inside && (yy < 0 || yy >= sH)) continue;
+            const uint8_t *row = src + ((size_t)yy * sW + x0) * CN;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (!inside && (x0 + k < 0 || x0 + k >= sW)) continue;
+#pragma unroll
+                for (int c = 0; c < CN; c++) acc[c] += (int)row[k * CN + c] * w[k];
+            }
+        }
+    } else {
+        if (ix >= sW || ix + 2 <= 0 || iy >= sH || iy + 2 <= 0) {
+#pragma unroll
+            for (int c = 0; c < CN; c++) o[c] = 0;
+            return;
+        }
+        // (1-fx)(1-fy)*32768 etc. are exact integers for fx,fy multiples of 1/32
+        int w[4] = {(32 - fx) * (32 - fy) * 32, fx * (32 - fy) * 32, (32 - fx) * fy * 32, fx * fy * 32};
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            int yy = iy + r;
+            if (yy < 0 || yy >= sH) continue;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                int xx = ix + k;
+                if (xx < 0 || xx >= sW) continue;
+                const uint8_t *p = src + ((size_t)yy * sW + xx) * CN;
+#pragma unroll
+                for (int c = 0; c < CN; c++) acc[c] += (int)p[c] * w[r * 2 + k];
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CN; c++) o[c] = fix_cast(acc[c]);
+}
+
+// cv2.undistort: pre-quantised CV_16SC2 maps (xy = integer part, fxy = fy*32+fx), bilinear, border 0
+template <int CN>
+__global__ void undistort_u8_kernel(const uint8_t *__restrict__ src, int H, int W, const short2 *__restrict__ xy,
+                                    const uint16_t *__restrict__ fxy, uint8_t *__restrict__ dst)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    size_t i = (size_t)y * W + x;
+    short2 p = xy[i];
+    int f = fxy[i] & 1023, fx = f & 31, fy = f >> 5;
+    int ix = p.x, iy = p.y;
+    uint8_t *o = dst + i * CN;
+    int acc[CN];
+#pragma unroll
+    for (int c = 0; c < CN; c++) acc[c] = 0;
+    if (!(ix >= W || ix + 2 <= 0 || iy >= H || iy + 2 <= 0)) {
+        int w[4] = {(32 - fx) * (32 - fy) * 32, fx * (32 - fy) * 32, (32 - fx) * fy * 32, fx * fy * 32};
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            int yy = iy + r;
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                int xx = ix + k;
+                if (xx < 0 || xx >= W) continue;
+                const uint8_t *q = src + ((size_t)yy * W + xx) * CN;
+#pragma unroll
+                for (int c = 0; c < CN; c++) acc[c] += (int)q[c] * w[r * 2 + k];
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CN; c++) o[c] = fix_cast(acc[c]);
+}
+
+// stereo_camera.py:510-513: disparity += min_disparity (every pixel); *= valid mask; depth = fx*B/disparity in f64
+// (np.float64 scalar / f32 array under NumPy 2), > max_depth -> 0, < 0 -> 0 (inf > max_depth -> 0).
+__global__ void disp_to_depth_kernel(const float *__restrict__ disp_in, const uint8_t *__restrict__ mask, float *__restrict__ disp_out,
+                                     double *__restrict__ depth, size_t n, float add, double fxb, double max_depth)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float d = disp_in[i] + add;
+    if (mask) d = mask[i] ? d : d * 0.0f;
+    if (disp_out) disp_out[i] = d;
+    double z = fxb / (double)d;
+    if (z > max_depth) z = 0.0;
+    if (z < 0.0) z = 0.0;
+    if (z != z) z = 0.0 * z; // keep NaN as NaN like NumPy (0/0 cannot occur: fxb > 0)
+    depth[i] = z;
+}
+
+// utils.rotate_depth_by_remap: new_z(x,y) = z(x,y)*(m0*x + m1*y + m2); out(u,v) = new_z[rint(mapy), rint(mapx)], outside -> 0
+__global__ void unrectify_kernel(const double *__restrict__ depth, int H, int W, const float *__restrict__ mapx,
+                                 const float *__restrict__ mapy, double *__restrict__ out, int H1, int W1, double m0, double m1, double m2)
+{
+    int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+    if (u >= W1) return;
+    size_t i = (size_t)v * W1 + u;
+    int sx = sat_short(__float2int_rn(mapx[i])), sy = sat_short(__float2int_rn(mapy[i]));
+    double r = 0.0;
+    if (sx >= 0 && sx < W && sy >= 0 && sy < H) {
+        double z = depth[(size_t)sy * W + sx];
+        r = (m0 * ((double)sx * z) + m1 * ((double)sy * z)) + m2 * z;
+    }
+    out[i] = r;
+}
+
+} // namespace
+
+cudaError_t launch_remap_u8(b2s_ctx *c, const uint8_t *src, int sH, int sW, int cn, const float *mapx, const float *mapy, int dH,
+                            int dW, int xshift, int interp, uint8_t *dst)
+{
+    dim3 b(128), g((dW + 127) / 128, dH);
+    const int16_t *tab = c->lanczos_tab.as<int16_t>();
+    if (cn == 3 && interp == 0) remap_u8_kernel<3, 0><<<g, b, 0, c->stream>>>(src, sH, sW, mapx, mapy, dH, dW, xshift, tab, dst);
+    else if (cn == 3) remap_u8_kernel<3, 1><<<g, b, 0, c->stream>>>(src, sH, sW, mapx, mapy, dH, dW, xshift, tab, dst);
+    else if (interp == 0) remap_u8_kernel<1, 0><<<g, b, 0, c->stream>>>(src, sH, sW, mapx, mapy, dH, dW, xshift, tab, dst);
+    else remap_u8_kernel<1, 1><<<g, b, 0, c->stream>>>(src, sH, sW, mapx, mapy, dH, dW, xshift, tab, dst);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_undistort_u8(b2s_ctx *c, const uint8_t *src, int H, int W, int cn, const int16_t *xy, const uint16_t *fxy, uint8_t *dst)
+{
+    dim3 b(128), g((W + 127) / 128, H);
+    if (cn == 3) undistort_u8_kernel<3><<<g, b, 0, c->stream>>>(src, H, W, (const short2 *)xy, fxy, dst);
+    else undistort_u8_kernel<1><<<g, b, 0, c->stream>>>(src, H, W, (const short2 *)xy, fxy, dst);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_depth_bare(b2s_ctx *c, const float *d_disp, double *d_depth)
+{
+    size_t n = (size_t)c->rH * c->rW;
+    disp_to_depth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_disp, nullptr, nullptr, d_depth, n, 0.f, c->r_fxb, c->r_max_depth);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unrectify(b2s_ctx *c, const double *d_depth, double *d_out)
+{
+    dim3 b(128), g((c->rW1 + 127) / 128, c->rH1);
+    unrectify_kernel<<<g, b, 0, c->stream>>>(d_depth, c->rH, c->rW, c->umapx.as<float>(), c->umapy.as<float>(), d_out, c->rH1, c->rW1,
+                                             c->r_m[0], c->r_m[1], c->r_m[2]);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_depth(b2s_ctx *c, const float *d_disp_in, int add_min_disp, int want_unrectify)
+{
+    size_t n = (size_t)c->rH * c->rW;
+    disp_to_depth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_disp_in, c->vmask.as<uint8_t>(), c->dispfinal.as<float>(),
+                                                                            c->rdepth.as<double>(), n, add_min_disp ? (float)c->r_min_disp : 0.f,
+                                                                            c->r_fxb, c->r_max_depth);
+    c->launches++;
+    if (want_unrectify) {
+        dim3 b(128), g((c->rW1 + 127) / 128, c->rH1);
+        unrectify_kernel<<<g, b, 0, c->stream>>>(c->rdepth.as<double>(), c->rH, c->rW, c->umapx.as<float>(), c->umapy.as<float>(),
+                                                 c->udepth.as<double>(), c->rH1, c->rW1, c->r_m[0], c->r_m[1], c->r_m[2]);
+        c->launches++;
+    }
+    return cudaGetLastError();
+}

@@ -1,0 +1,235 @@
+// sgbm_post.cu -- winner-take-all, uniqueness, sub-pixel, right-view map, L/R check, 3x3 median, speckle filter and the
+// reference's float post-processing, sm_100a.
+//
+// Replaces the tail of cv2.StereoSGBM.compute (calibrating/stereo_matching.py:63) and the NumPy post-processing at
+// calibrating/stereo_matching.py:63-64 (+ the /16 of :66).
+#include "b2s_internal.h"
+
+namespace {
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// ---- A.5: one warp per pixel ----------------------------------------------------------------------------------
+// cv2 visits x1 from width1-1 down to 0 and keeps, per right-image column x2, the candidate with the smallest minS
+// (strict '>' => among equal costs the largest x1 wins).  That order-dependent rule is an atomicMin on the key
+// (minS << 16) | (0xFFFF - x1).
+template <int NP>
+__global__ void __launch_bounds__(256) wta_kernel(const int16_t *__restrict__ S, int16_t *__restrict__ raw,
+                                                  unsigned *__restrict__ disp2key, SgbmGeom g)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t npix = (size_t)g.H * g.width1;
+    const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const int Dp = 64 * NP;
+    for (size_t pix = warp0; pix < npix; pix += nwarps) {
+        const int y = (int)(pix / g.width1), x = (int)(pix % g.width1);
+        const int16_t *Sp = S + pix * Dp;
+        uint32_t v[NP];
+        if constexpr (NP == 1) v[0] = *(const uint32_t *)(Sp + lane * 2);
+        else if constexpr (NP == 2) { uint2 t = *(const uint2 *)(Sp + lane * 4); v[0] = t.x; v[1] = t.y; }
+        else if constexpr (NP == 4) { uint4 t = *(const uint4 *)(Sp + lane * 8); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+        else {
+#pragma unroll
+            for (int i = 0; i < NP; i++) v[i] = ((const uint32_t *)(Sp + lane * 2 * NP))[i];
+        }
+        int sv[2 * NP];
+        unsigned key = 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            sv[2 * i] = (int)(short)(v[i] & 0xffffu);
+            sv[2 * i + 1] = ((int)v[i]) >> 16;
+        }
+#pragma unroll
+        for (int j = 0; j < 2 * NP; j++) {
+            int d = lane * 2 * NP + j;
+            if (d < g.D) key = min(key, ((unsigned)(sv[j] & 0xffff) << 16) | (unsigned)d);
+        }
+        key = __reduce_min_sync(0xffffffffu, key);
+        const int minS = (int)(key >> 16);
+        int best = (int)(key & 0xffffu);
+        if (minS >= 32767) best = -1; // cv2: strict '<' against MAX_COST never fires
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < 2 * NP; j++) {
+            int d = lane * 2 * NP + j;
+            if (d < g.D && sv[j] * (100 - g.uniq) < minS * 100 && abs(best - d) > 1) bad = true;
+        }
+        if (__any_sync(0xffffffffu, bad)) continue;
+        if (lane == 0) {
+            int d = best;
+            int x2 = x + g.minX1 - d - g.minD;
+            if (minS < 32767 && x2 >= 0 && x2 < g.W + 2)
+                atomicMin(&disp2key[(size_t)y * (g.W + 2) + x2], ((unsigned)minS << 16) | (unsigned)(0xFFFF - x));
+            if (0 < d && d < g.D - 1) {
+                int sm = Sp[d - 1], sp = Sp[d + 1], s0 = Sp[d];
+                int den2 = max(sm + sp - 2 * s0, 1);
+                d = d * 16 + ((sm - sp) * 16 + den2) / (den2 * 2);
+            } else
+                d *= 16;
+            raw[(size_t)y * g.W + x + g.minX1] = (int16_t)(d + g.minD * 16);
+        }
+    }
+}
+
+__global__ void fill_i16_kernel(int16_t *p, size_t n, int16_t v)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---- A.6 + A.7a: L/R check applied on load, then 3x3 median with replicated border --------------------------
+__device__ __forceinline__ int disp2_at(const unsigned *__restrict__ keys, const SgbmGeom &g, int y, int xq)
+{
+    unsigned k = keys[(size_t)y * (g.W + 2) + xq];
+    if (k == 0xFFFFFFFFu) return g.invalid; // never written: keeps the SCALED invalid value (A.6 quirk)
+    int x1 = 0xFFFF - (int)(k & 0xffffu);
+    return x1 + g.minX1 - xq; // best + minD
+}
+
+__device__ __forceinline__ int lr_checked(const int16_t *__restrict__ raw, const unsigned *__restrict__ keys, const SgbmGeom &g, int y, int x)
+{
+    int d1 = raw[(size_t)y * g.W + x];
+    if (d1 == g.invalid || x < g.minX1) return d1;
+    int _d = d1 >> 4, d_ = (d1 + 15) >> 4;
+    int _x = x - _d, x_ = x - d_;
+    if (0 <= _x && _x < g.W && 0 <= x_ && x_ < g.W) {
+        int a = disp2_at(keys, g, y, _x), b = disp2_at(keys, g, y, x_);
+        if (a >= g.minD && abs(a - _d) > g.d12 && b >= g.minD && abs(b - d_) > g.d12) return g.invalid;
+    }
+    return d1;
+}
+
+#define CSWAP(a, b) { int _t = min(a, b); b = max(a, b); a = _t; }
+__global__ void lr_median_kernel(const int16_t *__restrict__ raw, const unsigned *__restrict__ keys, int16_t *__restrict__ out, SgbmGeom g)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= g.W) return;
+    int v[9];
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++)
+            v[(dy + 1) * 3 + dx + 1] = lr_checked(raw, keys, g, clampi(y + dy, 0, g.H - 1), clampi(x + dx, 0, g.W - 1));
+    // median-of-9 exchange network
+    CSWAP(v[1], v[2]); CSWAP(v[4], v[5]); CSWAP(v[7], v[8]); CSWAP(v[0], v[1]); CSWAP(v[3], v[4]); CSWAP(v[6], v[7]);
+    CSWAP(v[1], v[2]); CSWAP(v[4], v[5]); CSWAP(v[7], v[8]); CSWAP(v[0], v[3]); CSWAP(v[5], v[8]); CSWAP(v[4], v[7]);
+    CSWAP(v[3], v[6]); CSWAP(v[1], v[4]); CSWAP(v[2], v[5]); CSWAP(v[4], v[7]); CSWAP(v[4], v[2]); CSWAP(v[6], v[4]);
+    CSWAP(v[4], v[2]);
+    out[(size_t)y * g.W + x] = (int16_t)v[4];
+}
+
+// ---- A.7b: cv2.filterSpeckles as connected-component labelling (union-find in global memory) -----------------
+__device__ __forceinline__ int uf_find(int *lab, int a)
+{
+    const volatile int *vl = lab; // other threads re-parent roots concurrently (atomicMin in uf_union)
+    int p = vl[a];
+    while (p != a) { a = p; p = vl[a]; }
+    return a;
+}
+__device__ __forceinline__ void uf_union(int *lab, int a, int b)
+{
+    while (true) {
+        a = uf_find(lab, a);
+        b = uf_find(lab, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicMin(&lab[a], b); // a > b: hang the larger root under the smaller
+        if (old == a) return;
+        a = old;
+    }
+}
+__global__ void ccl_init_kernel(const int16_t *__restrict__ img, int *lab, int *sizes, size_t n, int newVal)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lab[i] = img[i] == newVal ? -1 : (int)i;
+    sizes[i] = 0;
+}
+__global__ void ccl_merge_kernel(const int16_t *__restrict__ img, int *lab, int H, int W, int newVal, int maxDiff)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    int i = y * W + x;
+    int v = img[i];
+    if (v == newVal) return;
+    if (x + 1 < W) { int q = img[i + 1]; if (q != newVal && abs(v - q) <= maxDiff) uf_union(lab, i, i + 1); }
+    if (y + 1 < H) { int q = img[i + W]; if (q != newVal && abs(v - q) <= maxDiff) uf_union(lab, i, i + W); }
+}
+__global__ void ccl_count_kernel(int *lab, int *sizes, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || lab[i] < 0) return;
+    int r = uf_find(lab, (int)i);
+    atomicAdd(&sizes[r], 1);
+}
+__global__ void ccl_apply_kernel(const int16_t *__restrict__ img, int *lab, const int *__restrict__ sizes, int16_t *__restrict__ out,
+                                 size_t n, int newVal, int maxSize)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int v = img[i];
+    if (lab[i] >= 0 && sizes[uf_find(lab, (int)i)] <= maxSize) v = newVal;
+    out[i] = (int16_t)v;
+}
+
+// ---- A.8: reference post-processing (stereo_matching.py:63-64, /16) ------------------------------------------
+__global__ void disp_to_float_kernel(const int16_t *__restrict__ d16, float *__restrict__ out, size_t n, int minD16)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float f = fmaxf((float)d16[i], 0.f);
+    if (f < (float)minD16) f = 0.f;
+    out[i] = f / 16.0f;
+}
+
+} // namespace
+
+cudaError_t launch_wta(b2s_ctx *c)
+{
+    const SgbmGeom &g = c->g;
+    size_t n = (size_t)g.H * g.W;
+    fill_i16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->raw.as<int16_t>(), n, (int16_t)g.invalid);
+    cudaError_t e = cudaMemsetAsync(c->disp2key.p, 0xFF, (size_t)g.H * (g.W + 2) * sizeof(unsigned), c->stream);
+    if (e != cudaSuccess) return e;
+    size_t npix = (size_t)g.H * g.width1;
+    size_t want = (npix + 7) / 8;
+    unsigned blocks = (unsigned)(want < 148 * 8 * 4 ? want : 148 * 8 * 4);
+    const int16_t *S = c->S.as<int16_t>();
+    int16_t *raw = c->raw.as<int16_t>();
+    unsigned *keys = c->disp2key.as<unsigned>();
+    switch (g.NP) {
+    case 1: wta_kernel<1><<<blocks, 256, 0, c->stream>>>(S, raw, keys, g); break;
+    case 2: wta_kernel<2><<<blocks, 256, 0, c->stream>>>(S, raw, keys, g); break;
+    case 3: wta_kernel<3><<<blocks, 256, 0, c->stream>>>(S, raw, keys, g); break;
+    case 4: wta_kernel<4><<<blocks, 256, 0, c->stream>>>(S, raw, keys, g); break;
+    default: return cudaErrorInvalidValue;
+    }
+    c->launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_post(b2s_ctx *c, int16_t *d_out_disp16, float *d_out_disp)
+{
+    const SgbmGeom &g = c->g;
+    size_t n = (size_t)g.H * g.W;
+    dim3 b2(128), g2((g.W + 127) / 128, g.H);
+    unsigned nb = (unsigned)((n + 255) / 256);
+    int16_t *final16 = d_out_disp16 ? d_out_disp16 : c->disp16.as<int16_t>();
+    int16_t *med = g.speckle_window > 0 ? c->med.as<int16_t>() : final16;
+    lr_median_kernel<<<g2, b2, 0, c->stream>>>(c->raw.as<int16_t>(), c->disp2key.as<unsigned>(), med, g);
+    c->launches++;
+    if (g.speckle_window > 0) {
+        int *lab = c->labels.as<int>(), *sizes = c->sizes.as<int>();
+        ccl_init_kernel<<<nb, 256, 0, c->stream>>>(med, lab, sizes, n, g.invalid);
+        ccl_merge_kernel<<<g2, b2, 0, c->stream>>>(med, lab, g.H, g.W, g.invalid, 16 * g.speckle_range);
+        ccl_count_kernel<<<nb, 256, 0, c->stream>>>(lab, sizes, n);
+        ccl_apply_kernel<<<nb, 256, 0, c->stream>>>(med, lab, sizes, final16, n, g.invalid, g.speckle_window);
+        c->launches += 4;
+    }
+    if (d_out_disp) {
+        disp_to_float_kernel<<<nb, 256, 0, c->stream>>>(final16, d_out_disp, n, g.minD * 16);
+        c->launches++;
+    }
+    return cudaGetLastError();
+}

@@ -1,0 +1,381 @@
+"""`Stereo`: host-side mirror of calibrating/stereo_camera.py for the `get_depth` hot path, executed on a B200.
+
+Same surface as the reference class for this path (`load/dump`, `rectify`, `set_stereo_matching`, `get_depth`,
+`disparity_to_depth`, `depth_to_disparity`, `unrectify_depth`, `undistort_img`, attributes `R t R1 R2 K xy
+undistort_rectify_map1/2 rectify_valid_mask1 min_disparity max_depth translation_rectify_img`), same result-dict keys,
+shapes and dtypes (calibrating/stereo_camera.py:492-533).  What differs is where the arithmetic runs: every per-pair
+array operation goes through the C-ABI of libb2s.so (include/b2s.h); the once-per-rig setup (3x3 algebra and
+`cv2.initUndistortRectifyMap`, stereo_camera.py:125-177, 199-214) stays on the host exactly as SURVEY.md section 2 scopes
+it.  Calibration (`Stereo(cam1, cam2)` from image points, stereo_camera.py:55-123) is out of scope: rigs are built
+from the reference's own yaml/dict schema via `Stereo.load`, or from (cam1, cam2, R, t).
+"""
+import copy as _copy
+import ctypes
+
+import cv2
+import numpy as np
+import yaml
+
+from . import _ffi
+from .stereo_matching import MetaStereoMatching, SemiGlobalBlockMatching
+
+_EPS = 1e-8  # calibrating/utils.py:12
+
+
+class Cam:
+    """Intrinsics holder with the reference's dict schema {fx,fy,cx,cy,D,xy,name} or {K,D,xy} (camera.py:407-448)."""
+
+    def __init__(self, K=None, D=None, xy=None, name=None):
+        self.K = None if K is None else np.float64(K).reshape(3, 3)
+        self.D = np.zeros((1, 5)) if D is None else np.float64(D)
+        self.xy = None if xy is None else tuple(int(v) for v in xy)
+        self.name = name
+
+    @classmethod
+    def load(cls, src):
+        if isinstance(src, Cam):
+            return src.copy()
+        if not isinstance(src, dict):
+            if "\n" in src:
+                src = yaml.safe_load(src)
+            else:
+                with open(src) as f:
+                    src = yaml.safe_load(f)
+        d = _copy.deepcopy(src)
+        if "K" in d:
+            K = np.float64(d["K"])
+        else:
+            K = np.float64([[d["fx"], 0, d["cx"]], [0, d["fy"], d["cy"]], [0, 0, 1]])
+        assert "xy" in d and len(d["xy"]), "Need xy"
+        return cls(K, d.get("D"), d["xy"], d.get("name"))
+
+    def dump(self, path="", return_dict=False):
+        dic = dict(D=self.D.tolist(), xy=list(self.xy), fx=float(self.K[0, 0]), fy=float(self.K[1, 1]),
+                   cx=float(self.K[0, 2]), cy=float(self.K[1, 2]))
+        if self.name is not None:
+            dic["name"] = self.name
+        if return_dict:
+            return dic
+        s = yaml.safe_dump(dic)
+        if path:
+            with open(path, "w") as f:
+                f.write(s)
+        return s
+
+    def copy(self):
+        return Cam(self.K.copy(), self.D.copy(), self.xy, self.name)
+
+
+def _project_on_plane(v, plane_normal):
+    # calibrating/utils.py:139-140
+    return v - np.dot(v, plane_normal) / (np.linalg.norm(plane_normal) ** 2) * plane_normal
+
+
+def _shortest_rotation(v1, v2):
+    # calibrating/utils.py:143-149
+    axis = np.cross(v1, v2)
+    angle = np.arccos((v1 * v2).sum() / np.linalg.norm(v1) / np.linalg.norm(v2))
+    return cv2.Rodrigues(angle * axis / (np.linalg.norm(axis) + _EPS))[0]
+
+
+class Stereo:
+    MAX_DEPTH = 1000
+    DUMP_ATTRS = ["R", "t", "retval"]
+
+    def __init__(self, cam1=None, cam2=None, xy_target=None, K_target=1, R=None, t=None, device=0, interp="lanczos4"):
+        """interp: "lanczos4" (what the reference's rectify uses) or "linear" (north_star's fast bilinear mode)."""
+        self.xy_target = xy_target
+        self.K_target = K_target
+        self.device = device
+        self.interp = interp
+        self._handle = None
+        self._rig_dirty = True
+        if cam1 is None:
+            return
+        if R is None or t is None:
+            raise NotImplementedError("stereo calibration from image points (cv2.stereoCalibrate, stereo_camera.py:95-123) is "
+                                      "out of scope; pass R and t, or use Stereo.load(yaml_or_dict)")
+        self.cam1, self.cam2 = cam1, cam2
+        self.R = np.float64(R).reshape(3, 3)
+        self.t = np.float64(t).reshape(3, 1)
+        self._get_undistort_rectify_map()
+
+    # ---- persistence (stereo_camera.py:244-297) --------------------------------------------------------------
+    def dump(self, path="", return_dict=False):
+        dic = {k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in self.__dict__.items() if k in self.DUMP_ATTRS}
+        dic["cam1"] = self.cam1.dump(return_dict=True)
+        dic["cam2"] = self.cam2.dump(return_dict=True)
+        if return_dict:
+            return dic
+        s = yaml.safe_dump(dic)
+        if path:
+            with open(path, "w") as f:
+                f.write(s)
+        return s
+
+    def load(self, src=None, **kw):
+        if src is None or not isinstance(self, Stereo):  # called as Stereo.load(x)
+            src, self = (self if src is None else src), Stereo(**kw)
+        if isinstance(src, Stereo):
+            return src.copy()
+        if not isinstance(src, (list, dict)):
+            if "\n" in src:
+                dic = yaml.safe_load(src)
+            else:
+                with open(src) as f:
+                    dic = yaml.safe_load(f)
+        else:
+            dic = dict(src)
+        self.cam1 = Cam.load(dic.pop("cam1"))
+        self.cam2 = Cam.load(dic.pop("cam2"))
+        if "R" not in dic and "T" in dic:
+            T = np.float64(dic.pop("T"))
+            dic["r"], dic["t"] = cv2.Rodrigues(T[:3, :3])[0], T[:3, 3:]
+        if "R" not in dic and "r" in dic:
+            dic["R"] = cv2.Rodrigues(np.float64(dic.pop("r")))[0]
+        dic.setdefault("R", np.eye(3))
+        dic.pop("_calibrating_version", None)
+        for k, v in dic.items():
+            setattr(self, k, np.array(v) if k in self.DUMP_ATTRS else v)
+        self.R = np.float64(self.R)
+        self.t = np.float64(self.t).reshape(3, 1)
+        self._get_undistort_rectify_map()
+        return self
+
+    def copy(self):
+        new = type(self)(device=self.device, interp=self.interp)
+        new.load(self.dump(return_dict=True))
+        return new
+
+    # ---- once-per-rig setup on the host (stereo_camera.py:125-177, 199-214) -----------------------------------
+    def stereo_recitfy(self):
+        z_axis = np.array([0, 0, 1.0])
+        neg_x = np.array([-1.0, 0, 0])
+        t = self.t.squeeze()
+        z2 = _project_on_plane(z_axis, t)
+        z1 = _project_on_plane(self.R @ z_axis, t)
+        z_mean = z2 / np.linalg.norm(z2) + z1 / np.linalg.norm(z1)
+        R_align_x = _shortest_rotation(neg_x, t)
+        R_align_z = _shortest_rotation(R_align_x @ z_axis, z_mean)
+        self.R2 = (R_align_z @ R_align_x).T
+        self.R1 = self.R2 @ self.R[:3, :3]
+
+    def _get_undistort_rectify_map(self):
+        self.stereo_recitfy()
+        if self.xy_target is None:
+            self.xy_target = self.cam1.xy
+        if isinstance(self.xy_target, (int, float)):
+            self.xy_target = [int(round(i * self.xy_target)) for i in self.cam1.xy]
+        self.xy = xy = tuple(self.xy_target)
+        self.K = self.K_target
+        if isinstance(self.K_target, (int, float)):
+            self.K = self.cam1.K.copy()
+            self.K[:2, :2] *= self.K_target
+            self.K[:2, 2] += (np.array(xy) - self.cam1.xy) / 2
+        if not isinstance(self.K_target, np.ndarray):
+            # "better_cx_cy" (stereo_camera.py:137-157): centre the projected corners of both raw images
+            def centre_offset(cam_xy, cam_K, R):
+                corners = np.array([[0, 0, 1], [cam_xy[0], 0, 1], list(cam_xy) + [1], [0, cam_xy[1], 1]])
+                rays = corners @ np.linalg.inv(cam_K).T
+                uv = (rays @ R.T) @ self.K.T
+                uv = uv[:, :2] / uv[:, 2:]
+                return uv.mean(0) - self.K[:2, 2]
+
+            c = (centre_offset(self.cam1.xy, self.cam1.K, self.R1) + centre_offset(self.cam2.xy, self.cam2.K, self.R2)) / 2
+            self.K[:2, 2] = np.array(xy) / 2 - c
+        self.undistort_rectify_map1 = cv2.initUndistortRectifyMap(self.cam1.K, self.cam1.D, self.R1, self.K, xy, cv2.CV_32FC1)
+        self.undistort_rectify_map2 = cv2.initUndistortRectifyMap(self.cam2.K, self.cam2.D, self.R2, self.K, xy, cv2.CV_32FC1)
+        mx, my = self.undistort_rectify_map1
+        w1, h1 = self.cam1.xy
+        self.rectify_valid_mask1 = (-0.5 < mx) & (mx < w1 - 0.5) & (-0.5 < my) & (my < h1 - 0.5)
+        self._unrectify_depth_maps = None
+        self._rig_dirty = True
+
+    # ---- small properties (stereo_camera.py:386-406) -------------------------------------------------------------
+    def get_max_depth(self):
+        return getattr(self, "max_depth", self.MAX_DEPTH)
+
+    @property
+    def D(self):
+        return np.zeros((1, 5))
+
+    @property
+    def T(self):
+        T = np.eye(4)
+        T[:3, :3] = self.R
+        T[:3, 3] = self.t.squeeze()
+        return T
+
+    @property
+    def baseline(self):
+        return np.sum(self.t ** 2) ** 0.5
+
+    def depth_to_disparity(self, depth):
+        return 1.0 * self.baseline * self.K[0, 0] / depth
+
+    # ---- engine plumbing ---------------------------------------------------------------------------------------------
+    @property
+    def handle(self):
+        if self._handle is None:
+            sm = getattr(self, "stereo_matching", None)
+            own = getattr(getattr(sm, "stereo_sgbm", None), "handle", None)
+            self._handle = own if own is not None and own.device == self.device else _ffi.Handle(self.device)
+        return self._handle
+
+    def _unrectify_maps(self):
+        # maps of rotate_depth_by_remap (utils.py:184-191), cached like Stereo._unrectify_depth_maps
+        if self._unrectify_depth_maps is None:
+            self._unrectify_depth_maps = cv2.initUndistortRectifyMap(self.K, None, self.R1.T, self.cam1.K.copy(),
+                                                                     tuple(self.cam1.xy), cv2.CV_32FC1)
+        return self._unrectify_depth_maps
+
+    def _push_rig(self):
+        if not self._rig_dirty:
+            return
+        h = self.handle
+        m1x, m1y = (np.ascontiguousarray(m, np.float32) for m in self.undistort_rectify_map1)
+        m2x, m2y = (np.ascontiguousarray(m, np.float32) for m in self.undistort_rectify_map2)
+        mask = np.ascontiguousarray(self.rectify_valid_mask1, np.uint8)
+        umx, umy = (np.ascontiguousarray(m, np.float32) for m in self._unrectify_maps())
+        w1, h1 = self.cam1.xy
+        und_xy, und_fxy = cv2.initUndistortRectifyMap(self.cam1.K, self.cam1.D, None, self.cam1.K, (w1, h1), cv2.CV_16SC2)
+        und_xy, und_fxy = np.ascontiguousarray(und_xy, np.int16), np.ascontiguousarray(und_fxy, np.uint16)
+        M = self.R1.T @ np.linalg.inv(self.K)
+        rig = _ffi.Rig()
+        rig.W, rig.H = self.xy
+        rig.W1, rig.H1 = w1, h1
+        rig.W2, rig.H2 = self.cam2.xy
+        keep = [m1x, m1y, m2x, m2y, mask, umx, umy, und_xy, und_fxy]
+        (rig.map1x, rig.map1y, rig.map2x, rig.map2y, rig.valid_mask1, rig.unrect_mapx, rig.unrect_mapy, rig.undist_xy,
+         rig.undist_fxy) = [a.ctypes.data for a in keep]
+        rig.unrect_m = (ctypes.c_double * 3)(*M[2])
+        rig.fx_baseline = float(1.0 * self.baseline * self.K[0, 0])
+        rig.max_depth = float(self.get_max_depth())
+        rig.min_disparity = int(self.min_disparity) if getattr(self, "translation_rectify_img", None) else 0
+        rig.interp = {"lanczos4": 0, "linear": 1}[self.interp]
+        h.call("b2s_set_rig", ctypes.byref(rig))
+        self._rig_dirty = False
+
+    @staticmethod
+    def _get_img(path_or_np):
+        if isinstance(path_or_np, str):
+            return cv2.imread(path_or_np)[..., ::-1]
+        return path_or_np
+
+    @staticmethod
+    def _prep(img):
+        img = np.ascontiguousarray(Stereo._get_img(img))
+        if img.dtype != np.uint8 or img.ndim not in (2, 3):
+            raise ValueError("images must be uint8 (h,w) or (h,w,3)")
+        return img, (1 if img.ndim == 2 else img.shape[2])
+
+    def _check_raw(self, img1, img2):
+        (w1, h1), (w2, h2) = self.cam1.xy, self.cam2.xy
+        if img1.shape[:2] != (h1, w1) or img2.shape[:2] != (h2, w2):
+            raise ValueError("image sizes %s/%s do not match cam1.xy/cam2.xy %s/%s" % (img1.shape, img2.shape, self.cam1.xy, self.cam2.xy))
+
+    # ---- the hot path -------------------------------------------------------------------------------------------------------
+    def rectify(self, img1, img2):
+        """stereo_camera.py:216-242 -- two INTER_LANCZOS4 remaps (+ the min_disparity shift of the right image)."""
+        img1, cn = self._prep(img1)
+        img2, cn2 = self._prep(img2)
+        if cn != cn2:
+            raise ValueError("img1/img2 channel counts differ")
+        self._check_raw(img1, img2)
+        self._push_rig()
+        w, h = self.xy
+        shape = (h, w) if img1.ndim == 2 else (h, w, cn)
+        out1, out2 = np.empty(shape, np.uint8), np.empty(shape, np.uint8)
+        self.handle.call("b2s_rectify", _ffi.ptr(img1), _ffi.ptr(img2), cn, _ffi.ptr(out1), _ffi.ptr(out2))
+        return [out1, out2]
+
+    def disparity_to_depth(self, disparity):
+        """stereo_camera.py:408-413 (float64 result, like NumPy 2 promotion of the reference expression)."""
+        self._push_rig()
+        disparity = np.ascontiguousarray(disparity, np.float32)
+        w, h = self.xy
+        if disparity.shape != (h, w):
+            raise ValueError("disparity must have shape %s" % ((h, w),))
+        depth = np.empty((h, w), np.float64)
+        self.handle.call("b2s_disparity_to_depth", _ffi.ptr(disparity), _ffi.ptr(depth))
+        return depth
+
+    def unrectify_depth(self, depth):
+        """stereo_camera.py:415-428 -> utils.rotate_depth_by_remap (utils.py:173-200)."""
+        self._push_rig()
+        depth = np.ascontiguousarray(depth, np.float64)
+        w, h = self.xy
+        w1, h1 = self.cam1.xy
+        if depth.shape != (h, w):
+            raise ValueError("depth must have shape %s" % ((h, w),))
+        out = np.empty((h1, w1), np.float64)
+        self.handle.call("b2s_unrectify_depth", _ffi.ptr(depth), _ffi.ptr(out))
+        return out
+
+    def undistort_img(self, img1):
+        """stereo_camera.py:430-431 (cv2.undistort) on the device."""
+        self._push_rig()
+        img1, cn = self._prep(img1)
+        w1, h1 = self.cam1.xy
+        if img1.shape[:2] != (h1, w1):
+            raise ValueError("img1 must be cam1-sized %s" % ((h1, w1),))
+        out = np.empty(img1.shape, np.uint8)
+        self.handle.call("b2s_undistort_img", _ffi.ptr(img1), cn, _ffi.ptr(out))
+        return out
+
+    def set_stereo_matching(self, stereo_matching, max_depth=None, translation_rectify_img=None):
+        """stereo_camera.py:466-489."""
+        self.stereo_matching = stereo_matching
+        self.translation_rectify_img = bool(max_depth) if translation_rectify_img is None else translation_rectify_img
+        self.max_depth = max_depth or self.MAX_DEPTH
+        self.min_disparity = int(self.cam1.K[0, 0] * self.baseline / self.max_depth)
+        self._rig_dirty = True
+        return self
+
+    def get_depth(self, img1, img2, return_unrectify_depth=True, return_distort_depth=False):
+        """stereo_camera.py:492-533.  With the built-in `SemiGlobalBlockMatching` at full resolution the whole chain runs
+        in one C-ABI call (one upload, one stream of kernels, one download); with a foreign `MetaStereoMatching` plugin
+        the rectify half and the depth half run on the device around the plugin's host call."""
+        assert hasattr(self, "stereo_matching"), "Please stereo.set_stereo_matching(stereo_matching)"
+        if return_distort_depth:
+            raise NotImplementedError("distort_depth (stereo_camera.py:433-464) is a 'next' row (SURVEY.md section 8(f))")
+        img1, cn = self._prep(img1)
+        img2, cn2 = self._prep(img2)
+        if cn != cn2:
+            raise ValueError("img1/img2 channel counts differ")
+        self._check_raw(img1, img2)
+        w, h = self.xy
+        w1, h1 = self.cam1.xy
+        want = bool(return_unrectify_depth)
+        sm = self.stereo_matching
+        fused = (isinstance(sm, SemiGlobalBlockMatching) and sm.stereo_sgbm.handle is self.handle and sm.max_size >= max(h, w))
+        self._push_rig()
+        ishape = (h, w) if img1.ndim == 2 else (h, w, cn)
+        result = {}
+        out = _ffi.DepthOut()
+        disparity = np.empty((h, w), np.float32)
+        rectify_depth = np.empty((h, w), np.float64)
+        out.disparity, out.rectify_depth = disparity.ctypes.data, rectify_depth.ctypes.data
+        if want:
+            unrectify_depth = np.empty((h1, w1), np.float64)
+            undistort_img1 = np.empty(img1.shape, np.uint8)
+            out.unrectify_depth, out.undistort_img1 = unrectify_depth.ctypes.data, undistort_img1.ctypes.data
+        if fused:
+            rectify_img1, rectify_img2 = np.empty(ishape, np.uint8), np.empty(ishape, np.uint8)
+            out.rectify_img1, out.rectify_img2 = rectify_img1.ctypes.data, rectify_img2.ctypes.data
+            self.handle.call("b2s_get_depth", _ffi.ptr(img1), _ffi.ptr(img2), cn, int(want), ctypes.byref(out))
+        else:
+            rectify_img1, rectify_img2 = self.rectify(img1, img2)
+            plug = sm(rectify_img1, rectify_img2)
+            if isinstance(plug, dict):
+                result.update(plug)
+                plug = plug["disparity"]
+            plug = np.ascontiguousarray(plug, np.float32)
+            self.handle.call("b2s_depth_from_disparity", _ffi.ptr(plug), _ffi.ptr(img1), cn, int(want), ctypes.byref(out))
+        result.update(rectify_img1=rectify_img1, rectify_depth=rectify_depth, disparity=disparity, rectify_img2=rectify_img2)
+        if want:
+            result.update(unrectify_depth=unrectify_depth, undistort_img1=undistort_img1)
+        return result
+
+
+__all__ = ["Stereo", "Cam", "MetaStereoMatching", "SemiGlobalBlockMatching"]

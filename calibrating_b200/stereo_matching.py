@@ -1,0 +1,126 @@
+"""Matcher plugins: host-side mirror of calibrating/stereo_matching.py:10-70 over the B200 engine.
+
+`MetaStereoMatching` is the reference's plugin protocol verbatim in meaning (cfg dict; `__call__(img1, img2)` with
+RGB uint8 (h,w,3) in, float (h,w) disparity or dict(disparity=...) out).  `SemiGlobalBlockMatching` is the drop-in for
+the reference class of the same name: same constructor, same defaults (minDisparity 2, numDisparities 218, block 11,
+uniqueness 5, speckle 200/2, disp12MaxDiff 0, P1/P2 = 968/3872, MODE_SGBM), same post-processing -- but `compute`
+runs on the GPU through the C-ABI (include/b2s.h) instead of cv2.StereoSGBM.  Extra cfg keys expose the cv2 parameters
+the reference hard-codes.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _ffi
+
+MODE_SGBM, MODE_HH = 0, 1
+
+# calibrating/stereo_matching.py:29-58
+REFERENCE_DEFAULTS = dict(min_disparity=2, num_disparities=218, block_size=11, uniqueness_ratio=5, speckle_window_size=200,
+                          speckle_range=2, disp12_max_diff=0, P1=8 * 1 * 11 * 11, P2=32 * 1 * 11 * 11, pre_filter_cap=0,
+                          mode=MODE_SGBM)
+
+
+class MetaStereoMatching:
+    def __init__(self, cfg=None):
+        self.cfg = cfg
+
+    def __call__(self, img1, img2):
+        # input: RGB uint8 (h, w, 3); output: float disparity (h, w) in pixels, or dict(disparity=disparity)
+        raise NotImplementedError()
+
+
+class StereoSGBM:
+    """The part of the cv2.StereoSGBM object surface the reference touches (create / compute / getMinDisparity),
+    executed by libb2s.so.  `compute` returns int16 16*disparity exactly like cv2."""
+
+    def __init__(self, device=0, handle=None, **params):
+        unknown = set(params) - set(REFERENCE_DEFAULTS)
+        if unknown:
+            raise TypeError("unknown StereoSGBM parameters: %s" % sorted(unknown))
+        self.params = dict(min_disparity=0, num_disparities=16, block_size=3, P1=0, P2=0, disp12_max_diff=0, pre_filter_cap=0,
+                           uniqueness_ratio=0, speckle_window_size=0, speckle_range=0, mode=MODE_SGBM)
+        self.params.update(params)
+        self.handle = handle or _ffi.Handle(device)
+        self._push()
+
+    def _push(self):
+        p = _ffi.SgbmParams(**{k: int(v) for k, v in self.params.items()})
+        self.handle.call("b2s_set_sgbm_params", ctypes.byref(p))
+
+    def getMinDisparity(self):
+        return self.params["min_disparity"]
+
+    def getNumDisparities(self):
+        return self.params["num_disparities"]
+
+    @staticmethod
+    def _check_pair(left, right):
+        left = np.ascontiguousarray(left)
+        right = np.ascontiguousarray(right)
+        if left.dtype != np.uint8 or right.dtype != np.uint8:
+            raise ValueError("images must be uint8")
+        if left.shape != right.shape or left.ndim not in (2, 3):
+            raise ValueError("left/right shapes differ or are not images: %s vs %s" % (left.shape, right.shape))
+        cn = 1 if left.ndim == 2 else left.shape[2]
+        return left, right, left.shape[0], left.shape[1], cn
+
+    def compute(self, left, right):
+        left, right, H, W, cn = self._check_pair(left, right)
+        out = np.empty((H, W), np.int16)
+        self.handle.call("b2s_compute_disparity", _ffi.ptr(left), _ffi.ptr(right), H, W, cn, _ffi.ptr(out), None)
+        return out
+
+    def compute_float(self, left, right):
+        """compute + the reference's post-processing (stereo_matching.py:63-64, /16) fused on the device."""
+        left, right, H, W, cn = self._check_pair(left, right)
+        out = np.empty((H, W), np.float32)
+        self.handle.call("b2s_compute_disparity", _ffi.ptr(left), _ffi.ptr(right), H, W, cn, None, _ffi.ptr(out))
+        return out
+
+
+def StereoSGBM_create(minDisparity=0, numDisparities=16, blockSize=3, P1=0, P2=0, disp12MaxDiff=0, preFilterCap=0,
+                      uniquenessRatio=0, speckleWindowSize=0, speckleRange=0, mode=MODE_SGBM, device=0, handle=None):
+    """Keyword-compatible with cv2.StereoSGBM_create (MODE_SGBM=0 and MODE_HH=1 only)."""
+    return StereoSGBM(device=device, handle=handle, min_disparity=minDisparity, num_disparities=numDisparities, block_size=blockSize,
+                      P1=P1, P2=P2, disp12_max_diff=disp12MaxDiff, pre_filter_cap=preFilterCap, uniqueness_ratio=uniquenessRatio,
+                      speckle_window_size=speckleWindowSize, speckle_range=speckleRange, mode=mode)
+
+
+def _resize(img, arg):
+    """Stand-in for boxx.resize (calibrating/stereo_matching.py:62,66).  boxx is not vendored and its interpolation is
+    unpinned; this uses cv2 bilinear.  Full-resolution matching (`max_size >= max(h, w)`, the
+    documented way to get it) never reaches this function."""
+    import cv2
+    h, w = img.shape[:2]
+    if isinstance(arg, (int, float)):
+        nh, nw = int(round(h * arg)), int(round(w * arg))
+    else:
+        nh, nw = arg
+    if (nh, nw) == (h, w):
+        return img
+    return cv2.resize(img, (nw, nh), interpolation=cv2.INTER_LINEAR)
+
+
+class SemiGlobalBlockMatching(MetaStereoMatching):
+    """Drop-in for calibrating.SemiGlobalBlockMatching (calibrating/stereo_matching.py:22-70)."""
+
+    def __init__(self, cfg=None, device=0, handle=None):
+        if cfg is None:
+            cfg = {}
+        self.cfg = cfg
+        self.max_size = self.cfg.get("max_size", 1000)
+        params = dict(REFERENCE_DEFAULTS)
+        params.update({k: cfg[k] for k in REFERENCE_DEFAULTS if k in cfg})
+        self.stereo_sgbm = StereoSGBM(device=device, handle=handle, **params)
+
+    def __call__(self, img1, img2):
+        resize_ratio = min(self.max_size / max(img1.shape[:2]), 1)
+        if resize_ratio == 1:
+            return self.stereo_sgbm.compute_float(img1, img2)
+        simg1, simg2 = _resize(img1, resize_ratio), _resize(img2, resize_ratio)
+        sdisparity = self.stereo_sgbm.compute_float(simg1, simg2)
+        return _resize(sdisparity, img1.shape[:2]) * img1.shape[1] / simg1.shape[1]
+
+
+B200StereoMatching = SemiGlobalBlockMatching

@@ -1,0 +1,144 @@
+/*
+ * b2s.h -- C-ABI of the B200-native `Stereo.get_depth` engine (libb2s.so).
+ *
+ * This is the drop-in boundary for the hot path of DIYer22/calibrating:
+ *   Stereo.get_depth            calibrating/stereo_camera.py:492-533
+ *   Stereo.rectify              calibrating/stereo_camera.py:216-242   (cv2.remap INTER_LANCZOS4 x2 + shift)
+ *   SemiGlobalBlockMatching     calibrating/stereo_matching.py:22-70   (cv2.StereoSGBM.compute + post-processing)
+ *   Stereo.disparity_to_depth   calibrating/stereo_camera.py:408-413
+ *   Stereo.unrectify_depth      calibrating/stereo_camera.py:415-428 -> utils.rotate_depth_by_remap, utils.py:173-200
+ *   Stereo.undistort_img        calibrating/stereo_camera.py:430-431   (cv2.undistort)
+ * The reference has no FFI of its own (it is pure Python over cv2); the binding a maintainer adds is the
+ * ctypes stub shown in INTEGRATION.md (calibrating_b200/_ffi.py is that stub).
+ *
+ * Conventions: every entry point returns 0 on success or a negative B2S_E* code; b2s_last_error() gives the
+ * message.  No C++ exception crosses the boundary.  A handle owns one CUDA stream and all device buffers; it
+ * is not thread-safe, distinct handles may be driven from distinct threads.  "host" pointers are ordinary
+ * (pageable or pinned) caller-owned memory, C-contiguous, alive until the call (or the matching b2s_sync for
+ * *_async calls) returns.  Images are (H,W,cn) uint8, cn in {1,3}.  There is no CPU fallback: without a
+ * CUDA device b2s_create fails with B2S_ECUDA.
+ */
+#ifndef B2S_H
+#define B2S_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_OK 0
+#define B2S_EINVAL (-1)   /* bad argument / unsupported parameter combination */
+#define B2S_ESIZE (-2)    /* cv2's precondition: "input images are too small for your window size and max disparity" */
+#define B2S_ECUDA (-3)    /* CUDA runtime error (message has the CUDA error string) */
+#define B2S_ESTATE (-4)   /* call order: rig / parameters not set */
+
+typedef struct b2s_ctx *b2s_handle;
+
+/* Same fields and meaning as cv2.StereoSGBM_create (calibrating/stereo_matching.py:48-58);
+ * mode: 0 = MODE_SGBM (5 paths, the reference default), 1 = MODE_HH (8 paths). */
+typedef struct {
+    int min_disparity, num_disparities, block_size;
+    int P1, P2, disp12_max_diff, pre_filter_cap, uniqueness_ratio;
+    int speckle_window_size, speckle_range, mode;
+} b2s_sgbm_params;
+
+/* Per-rig constants produced once on the host by Stereo._get_undistort_rectify_map
+ * (calibrating/stereo_camera.py:125-177) and Stereo.set_stereo_matching (:466-489). */
+typedef struct {
+    int W, H;                   /* rectified size  (Stereo.xy) */
+    int W1, H1;                 /* cam1 raw size   (cam1.xy)   */
+    int W2, H2;                 /* cam2 raw size   (cam2.xy)   */
+    const float *map1x, *map1y; /* (H,W) f32: undistort_rectify_map1 */
+    const float *map2x, *map2y; /* (H,W) f32: undistort_rectify_map2 */
+    const uint8_t *valid_mask1; /* (H,W) u8 0/1: rectify_valid_mask1 */
+    const float *unrect_mapx, *unrect_mapy; /* (H1,W1) f32: maps of rotate_depth_by_remap (utils.py:184-191) */
+    const int16_t *undist_xy;   /* (H1,W1,2) i16 and                                                    */
+    const uint16_t *undist_fxy; /* (H1,W1) u16: CV_16SC2 maps of cv2.undistort(img1, cam1.K, cam1.D)     */
+    double unrect_m[3];         /* third row of R1^T * K^-1: z' = z*(m0*x + m1*y + m2) (utils.py:192-197) */
+    double fx_baseline;         /* K[0,0] * |t|   (disparity_to_depth, stereo_camera.py:408-410)         */
+    double max_depth;           /* Stereo.get_max_depth()                                                */
+    int min_disparity;          /* Stereo.min_disparity (translation of rectify_img2), 0 when disabled   */
+    int interp;                 /* 0 = INTER_LANCZOS4 (reference), 1 = INTER_LINEAR (fast mode)          */
+} b2s_rig;
+
+/* Which arrays b2s_get_depth copies back; NULL pointers are skipped. */
+typedef struct {
+    uint8_t *rectify_img1, *rectify_img2; /* (H,W,cn) u8 */
+    float *disparity;                     /* (H,W) f32, after += min_disparity and the valid mask */
+    double *rectify_depth;                /* (H,W) f64 */
+    double *unrectify_depth;              /* (H1,W1) f64 */
+    uint8_t *undistort_img1;              /* (H1,W1,cn) u8 */
+    int16_t *disp16;                      /* (H,W) i16: raw StereoSGBM output (debug / parity) */
+} b2s_depth_out;
+
+typedef struct {
+    float rectify_ms, cost_ms, aggregate_ms, wta_ms, post_ms, depth_ms, total_ms;
+    int aggregate_launches, total_launches;
+} b2s_timing;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------- */
+int b2s_device_count(void);
+int b2s_create(int device, b2s_handle *out);
+int b2s_destroy(b2s_handle h);
+const char *b2s_last_error(b2s_handle h); /* h may be NULL: error of the last failed b2s_create */
+int b2s_sync(b2s_handle h);               /* wait for the handle's stream */
+
+/* pinned host memory for the async API (cudaHostAlloc / cudaFreeHost) */
+int b2s_host_alloc(size_t bytes, void **out);
+int b2s_host_free(void *p);
+
+/* ---- matcher: replaces cv2.StereoSGBM_create + .compute (stereo_matching.py:48-63) ----------------------- */
+int b2s_set_sgbm_params(b2s_handle h, const b2s_sgbm_params *p);
+/* left/right host (H,W,cn) u8.  out_disp16 (nullable): (H,W) i16 = 16*disparity exactly as cv2 returns it.
+ * out_disp (nullable): (H,W) f32 with the reference's post-processing (stereo_matching.py:63-64 and /16):
+ * clip(0), values < 16*minDisparity zeroed, divided by 16.  Synchronous. */
+int b2s_compute_disparity(b2s_handle h, const uint8_t *left, const uint8_t *right, int H, int W, int cn,
+                          int16_t *out_disp16, float *out_disp);
+/* Same, enqueued on the handle's stream; host buffers should be pinned; complete after b2s_sync(). */
+int b2s_compute_disparity_async(b2s_handle h, const uint8_t *left, const uint8_t *right, int H, int W, int cn,
+                                int16_t *out_disp16, float *out_disp);
+/* Device-resident variant: all pointers are device memory on the handle's device; enqueues and returns. */
+int b2s_compute_disparity_dev(b2s_handle h, const uint8_t *d_left, const uint8_t *d_right, int H, int W, int cn,
+                              int16_t *d_out_disp16, float *d_out_disp);
+
+/* ---- full chain: replaces Stereo.rectify / get_depth / unrectify_depth / undistort_img ------------------- */
+int b2s_set_rig(b2s_handle h, const b2s_rig *rig);
+/* Stereo.rectify (stereo_camera.py:216-242): img1 (H1,W1,cn), img2 (H2,W2,cn) host -> out1/out2 (H,W,cn). */
+int b2s_rectify(b2s_handle h, const uint8_t *img1, const uint8_t *img2, int cn, uint8_t *out1, uint8_t *out2);
+/* Stereo.get_depth with the built-in matcher (stereo_camera.py:492-533). want_unrectify: also run
+ * unrectify_depth + undistort_img (return_unrectify_depth, default True in the reference). */
+int b2s_get_depth(b2s_handle h, const uint8_t *img1, const uint8_t *img2, int cn, int want_unrectify,
+                  const b2s_depth_out *out);
+int b2s_get_depth_async(b2s_handle h, const uint8_t *img1, const uint8_t *img2, int cn, int want_unrectify,
+                        const b2s_depth_out *out);
+/* Tail of get_depth for a foreign MetaStereoMatching plugin: disparity (H,W) f32 host, as returned by the
+ * plugin (stereo_camera.py:506-533 after the plugin call). img1 (nullable) feeds undistort_img. */
+int b2s_depth_from_disparity(b2s_handle h, const float *disparity, const uint8_t *img1, int cn,
+                             int want_unrectify, const b2s_depth_out *out);
+
+/* Stand-alone stages, same meaning as the reference methods of the same name (host buffers, synchronous):
+ * Stereo.disparity_to_depth (stereo_camera.py:408-413): (H,W) f32 -> (H,W) f64, no mask, no offset. */
+int b2s_disparity_to_depth(b2s_handle h, const float *disparity, double *depth);
+/* Stereo.unrectify_depth (stereo_camera.py:415-428): (H,W) f64 -> (H1,W1) f64. */
+int b2s_unrectify_depth(b2s_handle h, const double *rectify_depth, double *out);
+/* Stereo.undistort_img (stereo_camera.py:430-431): (H1,W1,cn) u8 -> (H1,W1,cn) u8. */
+int b2s_undistort_img(b2s_handle h, const uint8_t *img1, int cn, uint8_t *out);
+
+/* ---- introspection ----------------------------------------------------------------------------------------- */
+#define B2S_FETCH_C 0    /* cost volume (H,width1,Dp) i16 */
+#define B2S_FETCH_S 1    /* aggregated volume (H,width1,Dp) i16 */
+#define B2S_FETCH_RAW 2  /* (H,W) i16 disparity before median/speckle */
+int b2s_volume_dims(b2s_handle h, int *H, int *width1, int *D, int *Dp);
+int b2s_debug_fetch(b2s_handle h, int which, void *dst, size_t bytes);
+int b2s_timings(b2s_handle h, b2s_timing *t);      /* CUDA-event stage times of the last synchronous call */
+int b2s_launch_count(b2s_handle h, long long *n);  /* kernels launched by this handle since creation */
+/* Timed loop of the aggregation kernels alone on the resident cost volume of the last call (bench.py roofline):
+ * runs `iters` repetitions on the handle's stream between two CUDA events, returns the mean ms per repetition. */
+int b2s_bench_aggregate(b2s_handle h, int iters, float *ms_per_iter);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2S_H */

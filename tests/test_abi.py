@@ -1,0 +1,56 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol include/b2s.h declares, and fails loudly without a GPU."""
+import os
+import re
+
+import pytest
+
+from calibrating_b200 import _ffi, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _ffi.lib()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "b2s.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2s_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libb2s.so does not export %s" % n
+    assert sorted(_ffi.SIGNATURES) == names, "ctypes stub and header disagree"
+
+
+def test_struct_layouts_match_header():
+    import ctypes
+    assert ctypes.sizeof(_ffi.SgbmParams) == 11 * 4
+    assert ctypes.sizeof(_ffi.DepthOut) == 7 * 8
+    assert ctypes.sizeof(_ffi.Timing) == 7 * 4 + 2 * 4
+    assert ctypes.sizeof(_ffi.Rig) == 6 * 4 + 9 * 8 + 5 * 8 + 2 * 4
+
+
+def test_no_cpu_fallback(lib):
+    if lib.b2s_device_count() > 0:
+        pytest.skip("a GPU is present")
+    import calibrating_b200 as cb
+    with pytest.raises(_ffi.B2SError, match="no CPU fallback"):
+        cb.StereoSGBM_create(numDisparities=16)
+    with pytest.raises(_ffi.B2SError):
+        cb.SemiGlobalBlockMatching()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "calibrating_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f

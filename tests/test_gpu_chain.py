@@ -1,0 +1,103 @@
+"""GPU parity of the full `Stereo.get_depth` chain against the reference's own outputs (golden) and the cv2 restatement."""
+import os
+
+import numpy as np
+import pytest
+
+import calibrating_b200 as cb
+from calibrating_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _close_depth(a, b, rtol=1e-3):
+    """north_star tolerance: <= 1e-3 relative on the float depth map (we expect ~1e-15)."""
+    both = (a > 0) & (b > 0)
+    assert ((a > 0) == (b > 0)).all(), "validity masks differ"
+    return np.abs(a[both] - b[both]) <= rtol * np.abs(b[both])
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "rig320_default.npz")), np.load(os.path.join(golden_dir, "rig320_d64.npz"))
+
+
+def test_get_depth_default_matches_reference_golden(golden):
+    g, _ = golden
+    st = cb.Stereo.load(synth.rig_dict((320, 240)))
+    st.set_stereo_matching(cb.SemiGlobalBlockMatching({"max_size": 4000}), max_depth=3.5)
+    assert st.min_disparity == int(g["min_disparity"])
+    assert np.allclose(st.K, g["K"], rtol=0, atol=1e-12)
+    res = st.get_depth(g["img1"], g["img2"])
+    assert set(res) == {"rectify_img1", "rectify_img2", "disparity", "rectify_depth", "unrectify_depth", "undistort_img1"}
+    for k in ("rectify_img1", "rectify_img2", "undistort_img1"):
+        assert res[k].dtype == np.uint8 and np.array_equal(res[k], g[k]), k
+    assert res["disparity"].dtype == np.float32 and np.array_equal(res["disparity"], g["disparity"])
+    assert res["rectify_depth"].dtype == np.float64 and res["unrectify_depth"].dtype == np.float64
+    assert np.array_equal(res["rectify_depth"].astype(np.float32), g["rectify_depth"])
+    assert _close_depth(res["unrectify_depth"], g["unrectify_depth"].astype(np.float64), 1e-6).all()
+
+
+def test_get_depth_d64_no_translation(golden):
+    g0, g = golden
+    st = cb.Stereo.load(synth.rig_dict((320, 240)))
+    st.set_stereo_matching(cb.SemiGlobalBlockMatching({"max_size": 4000, "num_disparities": 64}))
+    res = st.get_depth(g0["img1"], g0["img2"])
+    assert np.array_equal(res["disparity"], g["disparity"])
+    assert np.array_equal(res["rectify_depth"].astype(np.float32), g["rectify_depth"])
+    assert _close_depth(res["unrectify_depth"], g["unrectify_depth"].astype(np.float64), 1e-6).all()
+    assert np.array_equal(res["undistort_img1"], g["undistort_img1"])
+
+
+def test_foreign_plugin_and_stage_methods(golden):
+    """A user-defined MetaStereoMatching (host code) still plugs in; the stage methods match the cv2 restatement."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import chain
+    g, _ = golden
+    rig = synth.rig_dict((320, 240))
+
+    class Cv2Plugin(cb.MetaStereoMatching):
+        def __call__(self, a, b):
+            return dict(disparity=chain.SgbmPlugin(max_size=4000)(a, b), extra=1)
+
+    st = cb.Stereo.load(rig).set_stereo_matching(Cv2Plugin(), max_depth=3.5)
+    res = st.get_depth(g["img1"], g["img2"])
+    assert res["extra"] == 1
+    assert np.array_equal(res["disparity"], g["disparity"])
+    ref = chain.RefStereo(rig).set_stereo_matching(chain.SgbmPlugin(max_size=4000), max_depth=3.5)
+    r1, r2 = st.rectify(g["img1"], g["img2"])
+    e1, e2 = ref.rectify(g["img1"], g["img2"])
+    assert np.array_equal(r1, e1) and np.array_equal(r2, e2)
+    d = np.abs(np.random.default_rng(0).normal(20, 10, (240, 320))).astype(np.float32)
+    d[::7] = 0
+    assert np.array_equal(st.disparity_to_depth(d), ref.disparity_to_depth(d.copy()))
+    z = ref.disparity_to_depth(d.copy())
+    a, b = st.unrectify_depth(z), ref.unrectify_depth(z)
+    assert ((a > 0) == (b > 0)).all() and np.allclose(a, b, rtol=1e-12, atol=0)
+    assert np.array_equal(st.undistort_img(g["img1"]), ref.undistort_img(g["img1"]))
+    gray = g["img1"][..., 0].copy()
+    assert np.array_equal(st.undistort_img(gray), ref.undistort_img(gray))
+
+
+@pytest.mark.parametrize("interp", ["lanczos4", "linear"])
+def test_chain_1080p_vs_cv2_restatement(interp):
+    """BASELINE config 5 stand-in at 1080p: whole chain vs the cv2 restatement, and depth vs analytic ground truth."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import chain
+    rig = synth.rig_dict((1920, 1080))
+    img1, img2 = synth.render_rig(rig, seed=1)
+    cfg = {"max_size": 4000, "num_disparities": 128, "min_disparity": 0, "block_size": 5, "P1": 600, "P2": 2400, "disp12_max_diff": 1,
+           "mode": cb.MODE_HH}
+    st = cb.Stereo.load(rig, interp=interp).set_stereo_matching(cb.SemiGlobalBlockMatching(cfg), max_depth=4.0)
+    res = st.get_depth(img1, img2)
+    ref = chain.RefStereo(rig).set_stereo_matching(
+        chain.SgbmPlugin(max_size=4000, numDisparities=128, minDisparity=0, blockSize=5, P1=600, P2=2400, disp12MaxDiff=1, mode=1), max_depth=4.0)
+    exp = ref.get_depth(img1, img2, cv2.INTER_LANCZOS4 if interp == "lanczos4" else cv2.INTER_LINEAR)
+    for k in ("rectify_img1", "rectify_img2", "undistort_img1", "disparity"):
+        assert np.array_equal(res[k], exp[k]), k
+    assert np.array_equal(res["rectify_depth"], exp["rectify_depth"])
+    assert _close_depth(res["unrectify_depth"], exp["unrectify_depth"], 1e-9).all()
+    gt = synth.gt_depth_cam1(rig)
+    v = res["unrectify_depth"] > 0
+    assert v.mean() > 0.5
+    assert np.median(np.abs(res["unrectify_depth"][v] - gt[v]) / gt[v]) < 0.01

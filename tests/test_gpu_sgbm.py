@@ -1,0 +1,140 @@
+"""GPU parity: the CUDA matcher (through the C-ABI) against the C oracle (oracle/sgbm_ref.c), the golden vectors and,
+when cv2 is importable on the box, cv2.StereoSGBM live.  Integer work: bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import calibrating_b200 as cb
+from calibrating_b200 import synth
+from oracle import sgbm as osgbm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handle():
+    from calibrating_b200 import _ffi
+    h = _ffi.Handle(0)
+    yield h
+    h.close()
+
+
+def _case(rng, D=None, cn=None, mode=None, minD=None, bs=None):
+    D = D or int(rng.choice([16, 24, 32, 48, 64, 70, 100, 128, 130, 200, 218, 256]))
+    minD = int(rng.choice([0, 2, 3, 5])) if minD is None else minD
+    cn = cn or int(rng.choice([1, 3]))
+    mode = int(rng.choice([0, 1])) if mode is None else mode
+    bs = bs or int(rng.choice([1, 3, 5, 7, 9, 11]))
+    h = int(rng.integers(12, 70))
+    w = int(rng.integers(D + minD + 12, D + minD + 150))
+    return dict(h=h, w=w, cn=cn, p=dict(min_disparity=minD, num_disparities=D, block_size=bs, P1=8 * cn * bs * bs, P2=32 * cn * bs * bs,
+                                        disp12_max_diff=int(rng.choice([-1, 0, 1, 2, 100])), uniqueness_ratio=int(rng.choice([0, 1, 5, 10, 15])),
+                                        speckle_window_size=int(rng.choice([0, 20, 200])), speckle_range=2, mode=mode))
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_stage_parity_random(handle, seed):
+    rng = np.random.default_rng(seed)
+    c = _case(rng)
+    if seed % 4 == 0:
+        l = rng.integers(0, 256, (c["h"], c["w"], c["cn"]), dtype=np.uint8).squeeze()
+        r = rng.integers(0, 256, (c["h"], c["w"], c["cn"]), dtype=np.uint8).squeeze()
+    else:
+        l, r, _ = synth.rectified_pair(c["h"], c["w"], c["p"]["num_disparities"], seed, c["cn"])
+    ref = osgbm.sgbm_compute(l, r, want_volumes=True, **c["p"])
+    m = cb.StereoSGBM(handle=handle, **c["p"])
+    got = m.compute(l, r)
+    assert np.array_equal(handle.fetch_volume(0), ref["C"]), "cost volume"
+    assert np.array_equal(handle.fetch_volume(1), ref["S"]), "aggregated volume"
+    assert np.array_equal(handle.fetch_raw(*l.shape[:2]), ref["raw"]), "WTA / uniqueness / subpixel"
+    assert np.array_equal(got, ref["disp"]), "L/R check, median, speckle"
+    f = m.compute_float(l, r)
+    exp = ref["disp"].astype(np.float32).clip(0)
+    exp[exp < c["p"]["min_disparity"] * 16] = 0
+    assert f.dtype == np.float32 and np.array_equal(f, exp / 16.0)
+
+
+def test_golden_vectors(handle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "sgbm_small.npz"))
+    l, r = g["left"], g["right"]
+    common = dict(min_disparity=0, num_disparities=48, block_size=5, P1=8 * 3 * 25, P2=32 * 3 * 25, disp12_max_diff=1,
+                  uniqueness_ratio=5, speckle_window_size=50, speckle_range=2)
+    assert np.array_equal(cb.StereoSGBM(handle=handle, mode=0, **common).compute(l, r), g["disp_sgbm"])
+    assert np.array_equal(cb.StereoSGBM(handle=handle, mode=1, **common).compute(l, r), g["disp_hh"])
+    m = cb.StereoSGBM_create(minDisparity=2, numDisparities=40, blockSize=11, P1=968, P2=3872, disp12MaxDiff=0, uniquenessRatio=5,
+                             speckleWindowSize=200, speckleRange=2, handle=handle)
+    assert np.array_equal(m.compute(l, r), g["disp_refparams"])
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_vs_cv2_live_640(handle, mode):
+    cv2 = pytest.importorskip("cv2")
+    l, r, _ = synth.rectified_pair(480, 640, 64, seed=7)
+    kw = dict(minDisparity=0, numDisparities=64, blockSize=5, P1=8 * 3 * 25, P2=32 * 3 * 25, disp12MaxDiff=1, uniquenessRatio=5,
+              speckleWindowSize=200, speckleRange=2, mode=mode)
+    ref = cv2.StereoSGBM_create(**kw).compute(l, r)
+    got = cb.StereoSGBM_create(handle=handle, **kw).compute(l, r)
+    assert np.array_equal(ref, got)
+
+
+def test_reference_default_matcher_vs_cv2(handle):
+    """The reference's literal parameter set (stereo_matching.py:29-58): D=218 (not a multiple of 16), minD=2, 5-path."""
+    cv2 = pytest.importorskip("cv2")
+    l, r, _ = synth.rectified_pair(360, 720, 200, seed=11)
+    ref = cv2.StereoSGBM_create(minDisparity=2, numDisparities=218, blockSize=11, uniquenessRatio=5, speckleWindowSize=200,
+                                speckleRange=2, disp12MaxDiff=0, P1=968, P2=3872).compute(l, r)
+    sm = cb.SemiGlobalBlockMatching({"max_size": 4000}, handle=handle)
+    got16 = sm.stereo_sgbm.compute(l, r)
+    assert np.array_equal(ref, got16)
+    exp = ref.astype(np.float32).clip(0)
+    exp[exp < 2 * 16] = 0
+    assert np.array_equal(sm(l, r), exp / 16.0)
+
+
+def test_full_size_1080p_hh(handle):
+    """BASELINE config 2 at full size: bit-exact against cv2 when available, plus size-independent properties."""
+    l, r, gt = synth.rectified_pair(1080, 1920, 128, seed=0)
+    kw = dict(minDisparity=0, numDisparities=128, blockSize=5, P1=8 * 3 * 25, P2=32 * 3 * 25, disp12MaxDiff=1, uniquenessRatio=5,
+              speckleWindowSize=200, speckleRange=2, mode=1)
+    m = cb.StereoSGBM_create(handle=handle, **kw)
+    got = m.compute(l, r)
+    assert np.array_equal(got, m.compute(l, r)), "deterministic"
+    assert (got[:, :128] == -16).all(), "columns x < minD+D are always invalid"
+    valid = got >= 0
+    assert valid.mean() > 0.7
+    err = np.abs(got[valid] / 16.0 - gt[valid])
+    assert (err <= 1).mean() > 0.97, "accuracy against the synthetic ground truth"
+    # vertical flip equivariance: the algorithm is symmetric under y -> H-1-y
+    assert np.array_equal(m.compute(l[::-1].copy(), r[::-1].copy()), got[::-1])
+    try:
+        import cv2
+    except ImportError:
+        return
+    assert np.array_equal(cv2.StereoSGBM_create(**kw).compute(l, r), got)
+
+
+def test_errors(handle):
+    l = np.zeros((20, 30, 3), np.uint8)
+    m = cb.StereoSGBM(handle=handle, num_disparities=32, block_size=5)
+    with pytest.raises(ValueError, match="too small"):
+        m.compute(l, l)
+    with pytest.raises(ValueError):
+        m.compute(l, l[:, :20])
+    with pytest.raises(ValueError):
+        m.compute(l.astype(np.float32), l.astype(np.float32))
+    with pytest.raises(ValueError):
+        cb.StereoSGBM(handle=handle, num_disparities=0)
+    with pytest.raises(ValueError):
+        cb.StereoSGBM(handle=handle, num_disparities=16, mode=2)
+
+
+def test_textureless_and_saturated(handle):
+    """Constant images (all costs tie) and maximal-contrast noise (S saturates at 32767 with the reference's P2)."""
+    for l, r in [(np.full((40, 300, 3), 128, np.uint8),) * 2,
+                 tuple(np.random.default_rng(s).integers(0, 2, (40, 300, 3), dtype=np.uint8) * 255 for s in (1, 2))]:
+        for mode in (0, 1):
+            p = dict(min_disparity=2, num_disparities=218, block_size=11, P1=968, P2=3872, uniqueness_ratio=0, disp12_max_diff=0,
+                     speckle_window_size=200, speckle_range=2, mode=mode)
+            ref = osgbm.sgbm_compute(l, r, **p)
+            assert np.array_equal(cb.StereoSGBM(handle=handle, **p).compute(l, r), ref)

@@ -1,0 +1,77 @@
+"""CPU: pin the oracle (oracle/sgbm_ref.c, oracle/remap.py, oracle/chain.py) against the committed golden vectors
+(generated from the REAL reference + cv2 by tests/golden/make_golden.py) and against the installed cv2 live."""
+import os
+
+import numpy as np
+import pytest
+
+from calibrating_b200 import synth
+from oracle import remap as oremap
+from oracle import sgbm as osgbm
+
+cv2 = pytest.importorskip("cv2")
+
+
+def test_sgbm_oracle_vs_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "sgbm_small.npz"))
+    l, r = g["left"], g["right"]
+    common = dict(min_disparity=0, num_disparities=48, block_size=5, P1=8 * 3 * 25, P2=32 * 3 * 25, disp12_max_diff=1,
+                  uniqueness_ratio=5, speckle_window_size=50, speckle_range=2)
+    assert np.array_equal(osgbm.sgbm_compute(l, r, mode=0, **common), g["disp_sgbm"])
+    assert np.array_equal(osgbm.sgbm_compute(l, r, mode=1, **common), g["disp_hh"])
+    ref = osgbm.sgbm_compute(l, r, min_disparity=2, num_disparities=40, block_size=11, P1=968, P2=3872, disp12_max_diff=0,
+                             uniqueness_ratio=5, speckle_window_size=200, speckle_range=2)
+    assert np.array_equal(ref, g["disp_refparams"])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_sgbm_oracle_vs_cv2_random(seed):
+    rng = np.random.default_rng(100 + seed)
+    h = int(rng.integers(20, 60)); D = int(rng.choice([16, 24, 32, 48, 70])); minD = int(rng.choice([0, 2, 3, 5]))
+    w = int(rng.integers(D + minD + 12, D + minD + 90)); cn = int(rng.choice([1, 3])); mode = int(rng.choice([0, 1]))
+    bs = int(rng.choice([1, 3, 5, 7, 9, 11])); uniq = int(rng.choice([0, 1, 5, 10, 15])); d12 = int(rng.choice([-1, 0, 1, 2, 100]))
+    spk = int(rng.choice([0, 20, 200]))
+    P1, P2 = 8 * cn * bs * bs, 32 * cn * bs * bs
+    if seed % 3 == 0:
+        l = rng.integers(0, 256, (h, w, cn), dtype=np.uint8).squeeze()
+        r = rng.integers(0, 256, (h, w, cn), dtype=np.uint8).squeeze()
+    else:
+        l, r, _ = synth.rectified_pair(h, w, D, seed, cn)
+    ref = cv2.StereoSGBM_create(minDisparity=minD, numDisparities=D, blockSize=bs, P1=P1, P2=P2, disp12MaxDiff=d12,
+                                uniquenessRatio=uniq, speckleWindowSize=spk, speckleRange=2, mode=mode).compute(l, r)
+    got = osgbm.sgbm_compute(l, r, min_disparity=minD, num_disparities=D, block_size=bs, P1=P1, P2=P2, disp12_max_diff=d12,
+                             uniqueness_ratio=uniq, speckle_window_size=spk, speckle_range=2, mode=mode)
+    assert np.array_equal(ref, got)
+
+
+def test_sgbm_oracle_precondition():
+    l = np.zeros((20, 30), np.uint8)
+    with pytest.raises(ValueError):
+        osgbm.sgbm_compute(l, l, num_disparities=32, block_size=5)
+    with pytest.raises(cv2.error):
+        cv2.StereoSGBM_create(numDisparities=32, blockSize=5).compute(l, l)
+
+
+def test_remap_oracle_vs_cv2():
+    rng = np.random.default_rng(1)
+    H, W = 90, 130
+    src = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    xs, ys = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32))
+    mx = (xs * 1.05 - 6 + 3 * np.sin(ys / 17)).astype(np.float32) + rng.random((H, W), dtype=np.float32)
+    my = (ys * 0.97 + 3 + 2 * np.cos(xs / 23)).astype(np.float32) + rng.random((H, W), dtype=np.float32)
+    assert np.array_equal(oremap.remap_lanczos4_u8(src, mx, my), cv2.remap(src, mx, my, cv2.INTER_LANCZOS4))
+    assert np.array_equal(oremap.remap_linear_u8(src, mx, my), cv2.remap(src, mx, my, cv2.INTER_LINEAR))
+    g = src[..., 1].copy()
+    assert np.array_equal(oremap.remap_lanczos4_u8(g, mx, my), cv2.remap(g, mx, my, cv2.INTER_LANCZOS4))
+    z = rng.random((H, W)) * 5
+    assert np.array_equal(oremap.remap_nearest(z, mx, my), cv2.remap(z, mx, my, cv2.INTER_NEAREST))
+
+
+def test_undistort_oracle_vs_cv2():
+    rng = np.random.default_rng(2)
+    H, W = 120, 160
+    src = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    K = np.array([[0.8 * W, 0, W / 2 + 2.3], [0, 0.81 * W, H / 2 - 1.7], [0, 0, 1]])
+    D = np.array([[-0.10, 0.03, 8e-4, -5e-4, 0.0]])
+    m1, m2 = cv2.initUndistortRectifyMap(K, D, None, K, (W, H), cv2.CV_16SC2)
+    assert np.array_equal(oremap.remap_linear_u8_fixed(src, m1[..., 0], m1[..., 1], m2), cv2.undistort(src, K, D))

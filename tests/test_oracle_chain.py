@@ -1,0 +1,43 @@
+"""CPU: the cv2 restatement of the reference chain (oracle/chain.py) reproduces the REAL reference's outputs
+(tests/golden/rig320_*.npz, written by tests/golden/make_golden.py from /root/reference)."""
+import os
+
+import numpy as np
+import pytest
+
+from calibrating_b200 import synth
+from oracle import chain
+
+pytest.importorskip("cv2")
+
+
+def _run(golden, max_depth, **kw):
+    rig = synth.rig_dict((320, 240))
+    st = chain.RefStereo(rig)
+    st.set_stereo_matching(chain.SgbmPlugin(max_size=4000, **kw), max_depth=max_depth)
+    return st, st.get_depth(golden["img1"], golden["img2"])
+
+
+def test_chain_default_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "rig320_default.npz"))
+    img1, img2 = synth.render_rig(synth.rig_dict((320, 240)), seed=0)
+    assert np.array_equal(img1, g["img1"]) and np.array_equal(img2, g["img2"])  # the generator is deterministic
+    st, res = _run(g, 3.5)
+    assert st.min_disparity == int(g["min_disparity"])
+    assert np.allclose(st.K, g["K"], rtol=0, atol=1e-12) and np.allclose(st.R1, g["R1"], rtol=0, atol=1e-14)
+    assert np.array_equal(st.map1[0][::16, ::16], g["map1x"]) and np.array_equal(st.map2[1][::16, ::16], g["map2y"])
+    for k in ("rectify_img1", "rectify_img2", "undistort_img1"):
+        assert np.array_equal(res[k], g[k]), k
+    for k in ("disparity", "rectify_depth", "unrectify_depth"):
+        assert np.array_equal(res[k].astype(np.float32), g[k]), k
+    assert res["rectify_depth"].dtype == np.float64 and res["disparity"].dtype == np.float32
+
+
+def test_chain_d64_matches_reference(golden_dir):
+    g0 = np.load(os.path.join(golden_dir, "rig320_default.npz"))
+    g = np.load(os.path.join(golden_dir, "rig320_d64.npz"))
+    st, res = _run(g0, None, numDisparities=64)
+    assert int(g["min_disparity"]) == st.min_disparity
+    for k in ("disparity", "rectify_depth", "unrectify_depth"):
+        assert np.array_equal(res[k].astype(np.float32), g[k]), k
+    assert np.array_equal(res["undistort_img1"], g["undistort_img1"])

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
         for (int x1 = xs; x1 < xe; x1++) {
             *out = s;
             out += DW;
+            if (x1 + 1 >= xe) break;
             uint32_t add = pw[(clampi(x1 + 1 + g.SW2, 0, g.width1 - 1) - xlo) * DW + w];
             uint32_t sub = pw[(clampi(x1 - g.SW2, 0, g.width1 - 1) - xlo) * DW + w];
             s = __vsub2(__vadd2(s, add), sub);

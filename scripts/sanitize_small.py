@@ -1,0 +1,22 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck) under gpurun."""
+import sys
+sys.path.insert(0, ".")
+import numpy as np
+import calibrating_b200 as cb
+from calibrating_b200 import synth
+from oracle import sgbm as osgbm
+
+for (h, w, D, cn, mode, bs) in [(24, 150, 64, 3, 1, 5), (17, 300, 218, 3, 0, 11), (30, 120, 16, 1, 1, 3), (20, 400, 256, 1, 0, 7), (21, 330, 130, 3, 1, 9)]:
+    l, r, _ = synth.rectified_pair(h, w, D, 1, cn)
+    p = dict(min_disparity=2, num_disparities=D, block_size=bs, P1=8 * cn * bs * bs, P2=32 * cn * bs * bs, disp12_max_diff=1,
+             uniqueness_ratio=5, speckle_window_size=30, speckle_range=2, mode=mode)
+    m = cb.StereoSGBM(**p)
+    got = m.compute(l, r)
+    ref = osgbm.sgbm_compute(l, r, want_volumes=True, **p)
+    print((h, w, D, cn, mode, bs), "C", np.array_equal(m.handle.fetch_volume(0), ref["C"]), "S", np.array_equal(m.handle.fetch_volume(1), ref["S"]),
+          "raw", np.array_equal(m.handle.fetch_raw(h, w), ref["raw"]), "disp", np.array_equal(got, ref["disp"]))
+rig = synth.rig_dict((320, 240))
+img1, img2 = synth.render_rig(rig, seed=0)
+st = cb.Stereo.load(rig).set_stereo_matching(cb.SemiGlobalBlockMatching({"max_size": 4000, "num_disparities": 64}), max_depth=3.5)
+res = st.get_depth(img1, img2)
+print("chain ok", {k: v.shape for k, v in res.items()})

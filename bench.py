@@ -1,0 +1,267 @@
+#!/usr/bin/env python3
+"""bench.py -- stereo pairs/s of the `Stereo.get_depth` matcher hot path at BASELINE config 2
+(1920x1080 RGB rectified pair, 128 disparities, 8-path SGM = cv2 MODE_HH, block 5), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" = one batch of `--pairs-per-step` independent synthetic pairs per GPU (pairs shard across ranks with no
+data-path collective: weak scaling).  `value` = whole-job pairs/s with the inputs already resident in HBM, timed with
+CUDA events on the engine's own streams, max over ranks.  `e2e` = the same metric through the public host API
+(`DisparityBatchEngine.compute_batch`, i.e. the plugin's batch call) with pinned HOST buffers, H2D and D2H inside the
+timed region.  `roofline` = the aggregation kernels (8 scan launches per pair) timed alone by CUDA events, algorithmic
+bytes 8 B/voxel.  `cpu_baseline` / `--impl reference` = the reference's own CPU arithmetic
+(cv2.StereoSGBM, what calibrating/stereo_matching.py:63 executes) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, D, CN = 1080, 1920, 128, 3
+SGBM = dict(min_disparity=0, num_disparities=D, block_size=5, P1=8 * 3 * 25, P2=32 * 3 * 25, disp12_max_diff=1, pre_filter_cap=0,
+            uniqueness_ratio=5, speckle_window_size=200, speckle_range=2, mode=1)
+WORKLOAD = "BASELINE config 2: 1920x1080 RGB synthetic rectified pair, 128 disparities, 8-path SGM (cv2 MODE_HH), block 5"
+VOXELS = H * (W - D) * D  # cost-volume extent H*(W-minD-D)*D
+AGG_BYTES_PER_PAIR = 8 * VOXELS  # canonical two-sweep schedule: C read twice, S written once and read once, int16
+
+
+def cv2_matcher():
+    import cv2
+    return cv2.StereoSGBM_create(minDisparity=0, numDisparities=D, blockSize=5, P1=600, P2=2400, disp12MaxDiff=1, uniquenessRatio=5,
+                                 speckleWindowSize=200, speckleRange=2, mode=cv2.STEREO_SGBM_MODE_HH)
+
+
+def host_threads():
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        avail_gb = int(next(l for l in open("/proc/meminfo") if l.startswith("MemAvailable")).split()[1]) / 1e6
+    except Exception:
+        avail_gb = 16
+    return max(1, min(n, int(avail_gb / 2.5), 64))  # one MODE_HH matcher holds ~1.3 GB of cost volumes at 1080p/128
+
+
+def cpu_round(pairs, threads):
+    """`threads` cv2 matchers, one pair each, in parallel (cv2 releases the GIL).  Returns seconds."""
+    ms = [cv2_matcher() for _ in range(threads)]
+    out = [None] * threads
+
+    def work(i):
+        l, r = pairs[i % len(pairs)]
+        out[i] = ms[i].compute(l, r)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return time.perf_counter() - t0
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            pass
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            txt = self.p.communicate(timeout=5)[0]
+        except Exception:
+            txt = ""
+        sm, mx, reasons = [], [], set()
+        for line in txt.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower() == "active":
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank):
+    """The reference's own CPU path (cv2.StereoSGBM MODE_HH) with all usable host threads; rank 0 only."""
+    if rank != 0:
+        return
+    import cv2
+    from calibrating_b200 import synth
+    T = host_threads()
+    pairs = [synth.rectified_pair(H, W, D, seed=s)[:2] for s in range(min(T, 4))]
+    for _ in range(args.warmup):
+        cpu_round(pairs, T)
+    t = sum(cpu_round(pairs, T) for _ in range(args.steps))
+    v = T * args.steps / t
+    sample = "%d threads x 1 pair of the workload per step, cv2 %s, getNumThreads=%d" % (T, cv2.__version__, cv2.getNumThreads())
+    print(json.dumps({
+        "impl": "reference", "metric": "stereo pairs/sec @1080p/128-disp SGM", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_step": T, "host": "cv2.StereoSGBM MODE_HH on host cores"},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": T, "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs-per-step", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from calibrating_b200 import _ffi, synth
+    from calibrating_b200.batch import DisparityBatchEngine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    P, S, K, Wm = args.pairs_per_step, args.streams, args.steps, max(args.warmup, 3)
+    pairs = [synth.rectified_pair(H, W, D, seed=rank * P + i)[:2] for i in range(P)]
+    eng = DisparityBatchEngine(SGBM, device=local, streams=S)
+
+    # ---- value: inputs resident in HBM -----------------------------------------------------------------------------
+    dl = [(torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()) for l, r in pairs]
+    dout = [torch.empty((H, W), dtype=torch.int16, device="cuda") for _ in range(P)]
+    ptrs = [(a.data_ptr(), b.data_ptr()) for a, b in dl]
+    optrs = [o.data_ptr() for o in dout]
+    torch.cuda.synchronize()
+
+    def step_dev(sync):
+        for i in range(P):
+            eng.handles[i % S].call("b2s_compute_disparity_dev", ptrs[i][0], ptrs[i][1], H, W, CN, optrs[i], None)
+        if sync:
+            for h in eng.handles:
+                h.sync()
+
+    for _ in range(Wm):
+        step_dev(True)
+    barrier()
+    sampler = ClockSampler(local)
+    l0 = eng.launch_count()
+    for h in eng.handles:
+        h.event_record(0)
+    for _ in range(K):
+        step_dev(False)
+    for h in eng.handles:
+        h.event_record(1)
+    ms = max(eng.handles[0].event_elapsed(0, h, 1) for h in eng.handles)
+    for h in eng.handles:
+        h.sync()
+    barrier()
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop()
+    # parity guard: the timed outputs are the real thing (checked against cv2 in tests/; here a cheap sanity check)
+    d0 = dout[0].cpu().numpy()
+    assert (d0[:, :D] == -16).all() and (d0 >= 0).mean() > 0.5, "benchmark output is not a disparity map"
+
+    # ---- e2e: public host API, pinned host buffers, H2D + D2H inside the timed region --------------------------
+    hp = []
+    for l, r in pairs:
+        a, b = _ffi.pinned_empty(l.shape, np.uint8), _ffi.pinned_empty(r.shape, np.uint8)
+        a[...] = l; b[...] = r
+        hp.append((a, b))
+    hout = [_ffi.pinned_empty((H, W), np.float32) for _ in range(P)]
+    for _ in range(Wm):
+        eng.compute_batch(hp, out=hout)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        eng.compute_batch(hp, out=hout)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    stage = eng.handles[0].timings()
+
+    # ---- roofline: the aggregation kernels alone ---------------------------------------------------------------------
+    agg_ms = eng.handles[0].bench_aggregate(10)
+    n_dir = 8
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "agg_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    achieved = AGG_BYTES_PER_PAIR / n_dir / (agg_ms / n_dir * 1e-3) / 1e9
+    out = {
+        "metric": "stereo pairs/sec @1080p/128-disp SGM", "value": world * K * P / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
+        "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "streams_per_gpu": S, "parallelism": "dp%d (pairs sharded, no collective)" % world,
+                   "l2": "working set per pair (C+S volumes, 0.99 GB) exceeds the 126 MB L2; %d distinct pairs rotate" % P},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": world * K * P / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": P * 2 * H * W * CN, "d2h_bytes_per_step": P * H * W * 4,
+                "api": "DisparityBatchEngine.compute_batch (host uint8 pairs -> host float32 disparity), wall clock between synchronisations"},
+        "roofline": {"bound": "hbm", "kernel": "agg_scan_kernel x%d (one launch per path direction)" % n_dir, "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy), of measured" if peaks else "fallback 6650 GB/s, of fallback",
+                     "algorithmic_bytes_per_launch": AGG_BYTES_PER_PAIR // n_dir, "ms_per_launch": agg_ms / n_dir, "timed": "alone, CUDA events on the engine stream"},
+        "stage_ms_last_pair": {k: round(v, 3) for k, v in stage.items() if k.endswith("_ms")},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        import cv2
+        T = host_threads()
+        cpu_round(pairs, T)  # warm-up round
+        rounds = 2
+        t = sum(cpu_round(pairs, T) for _ in range(rounds))
+        out["cpu_baseline"] = {"value": T * rounds / t, "unit": "pairs/s", "cores": T, "kind": "reference",
+                               "sample": "%d rounds of %d threads x 1 pair (cv2 %s StereoSGBM MODE_HH, same pairs and parameters)" % (rounds, T, cv2.__version__)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

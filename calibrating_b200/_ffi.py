@@ -66,6 +66,9 @@ SIGNATURES = {
     "b2s_timings": (c_int, [c_void_p, ctypes.POINTER(Timing)]),
     "b2s_launch_count": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_longlong)]),
     "b2s_bench_aggregate": (c_int, [c_void_p, c_int, ctypes.POINTER(c_float)]),
+    "b2s_event_record": (c_int, [c_void_p, c_int]),
+    "b2s_event_elapsed": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.POINTER(c_float)]),
+    "b2s_collect_timings": (c_int, [c_void_p, c_int]),
 }
 
 _lib = None
@@ -152,6 +155,15 @@ class Handle:
         out = np.empty((H, W), np.int16)
         self.call("b2s_debug_fetch", 2, ptr(out), out.nbytes)
         return out
+
+    def event_record(self, slot):
+        self.call("b2s_event_record", int(slot))
+
+    def event_elapsed(self, slot_a, other, slot_b):
+        """ms from this handle's event slot_a to `other`'s event slot_b (waits for the latter)."""
+        ms = c_float()
+        check(self._lib.b2s_event_elapsed(self._h, int(slot_a), other._h, int(slot_b), ctypes.byref(ms)), other._h)
+        return ms.value
 
     def bench_aggregate(self, iters=10):
         ms = c_float()

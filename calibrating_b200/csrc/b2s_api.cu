@@ -56,6 +56,7 @@ int b2s_create(int device, b2s_handle *out)
         return fail(nullptr, B2S_ECUDA, "b2s_create: %s", cudaGetErrorString(e));
     }
     for (auto &ev : c->ev) cudaEventCreate(&ev);
+    for (auto &ev : c->uev) cudaEventCreate(&ev);
     // Lanczos4 fixed-point table (1024 x 8 x 8 int16 = 128 KB), shared by both rectify remaps
     std::vector<int16_t> tab(1024 * 64);
     build_lanczos4_table(tab.data());
@@ -79,6 +80,8 @@ int b2s_destroy(b2s_handle c)
                       &c->udepth, &c->lanczos_tab, &c->stage_f32};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->uev)
         if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -481,6 +484,32 @@ int b2s_bench_aggregate(b2s_handle c, int iters, float *ms_per_iter)
     float ms = 0;
     CK(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[7]));
     *ms_per_iter = ms / iters;
+    return B2S_OK;
+}
+
+int b2s_event_record(b2s_handle c, int slot)
+{
+    if (!c || slot < 0 || slot >= 4) return B2S_EINVAL;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaEventRecord(c->uev[slot], c->stream));
+    return B2S_OK;
+}
+
+int b2s_event_elapsed(b2s_handle a, int slot_a, b2s_handle b, int slot_b, float *ms)
+{
+    if (!a || !b || !ms || slot_a < 0 || slot_a >= 4 || slot_b < 0 || slot_b >= 4) return B2S_EINVAL;
+    CK(b, cudaSetDevice(b->device));
+    CK(b, cudaEventSynchronize(b->uev[slot_b]));
+    CK(b, cudaEventElapsedTime(ms, a->uev[slot_a], b->uev[slot_b]));
+    return B2S_OK;
+}
+
+int b2s_collect_timings(b2s_handle c, int chain)
+{
+    if (!c) return B2S_EINVAL;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    collect_timing(c, chain != 0);
     return B2S_OK;
 }
 

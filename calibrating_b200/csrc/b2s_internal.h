@@ -72,6 +72,7 @@ struct b2s_ctx {
     DevBuf stage_f32;                      // upload scratch for b2s_depth_from_disparity
 
     cudaEvent_t ev[8] = {};
+    cudaEvent_t uev[4] = {};
     b2s_timing timing{};
 };
 

@@ -123,4 +123,13 @@ class SemiGlobalBlockMatching(MetaStereoMatching):
         return _resize(sdisparity, img1.shape[:2]) * img1.shape[1] / simg1.shape[1]
 
 
+    def compute_batch(self, pairs, streams=2):
+        """Throughput entry point (not in the reference): full-resolution disparities for a list of (img1, img2)."""
+        from .batch import DisparityBatchEngine
+        eng = getattr(self, "_batch_engine", None)
+        if eng is None or len(eng.handles) != streams:
+            eng = self._batch_engine = DisparityBatchEngine(self.stereo_sgbm.params, self.stereo_sgbm.handle.device, streams)
+        return eng.compute_batch(pairs)
+
+
 B200StereoMatching = SemiGlobalBlockMatching

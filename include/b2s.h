@@ -137,6 +137,12 @@ int b2s_launch_count(b2s_handle h, long long *n);  /* kernels launched by this h
 /* Timed loop of the aggregation kernels alone on the resident cost volume of the last call (bench.py roofline):
  * runs `iters` repetitions on the handle's stream between two CUDA events, returns the mean ms per repetition. */
 int b2s_bench_aggregate(b2s_handle h, int iters, float *ms_per_iter);
+/* User CUDA events on the handle's stream (slot 0..3), for device-side timing of caller-defined regions. */
+int b2s_event_record(b2s_handle h, int slot);
+/* ms between event `slot_a` of handle a and event `slot_b` of handle b (same device); waits for event b. */
+int b2s_event_elapsed(b2s_handle a, int slot_a, b2s_handle b, int slot_b, float *ms);
+/* Re-read the stage timings of the last *_async call (call after b2s_sync). */
+int b2s_collect_timings(b2s_handle h, int chain);
 
 #ifdef __cplusplus
 }

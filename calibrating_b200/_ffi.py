@@ -66,6 +66,7 @@ SIGNATURES = {
     "b2s_timings": (c_int, [c_void_p, ctypes.POINTER(Timing)]),
     "b2s_launch_count": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_longlong)]),
     "b2s_bench_aggregate": (c_int, [c_void_p, c_int, ctypes.POINTER(c_float)]),
+    "b2s_bench_aggregate_parts": (c_int, [c_void_p, c_int, ctypes.POINTER(c_float), c_int, ctypes.POINTER(c_int)]),
     "b2s_event_record": (c_int, [c_void_p, c_int]),
     "b2s_event_elapsed": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.POINTER(c_float)]),
     "b2s_collect_timings": (c_int, [c_void_p, c_int]),
@@ -169,6 +170,13 @@ class Handle:
         ms = c_float()
         self.call("b2s_bench_aggregate", int(iters), ctypes.byref(ms))
         return ms.value
+
+    def bench_aggregate_parts(self, iters=10):
+        """mean ms of every kernel launch of the aggregation group, in launch order"""
+        parts = (c_float * 8)()
+        n = c_int()
+        self.call("b2s_bench_aggregate_parts", int(iters), parts, 8, ctypes.byref(n))
+        return [parts[i] for i in range(n.value)]
 
 
 def pinned_empty(shape, dtype):

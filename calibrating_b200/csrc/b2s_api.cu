@@ -51,12 +51,15 @@ int b2s_create(int device, b2s_handle *out)
     b2s_ctx *c = new (std::nothrow) b2s_ctx();
     if (!c) return fail(nullptr, B2S_EINVAL, "b2s_create: out of host memory");
     c->device = device;
+    cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (c->num_sms <= 0) c->num_sms = 1;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete c;
         return fail(nullptr, B2S_ECUDA, "b2s_create: %s", cudaGetErrorString(e));
     }
     for (auto &ev : c->ev) cudaEventCreate(&ev);
     for (auto &ev : c->uev) cudaEventCreate(&ev);
+    for (auto &ev : c->aev) cudaEventCreate(&ev);
     // Lanczos4 fixed-point table (1024 x 8 x 8 int16 = 128 KB), shared by both rectify remaps
     std::vector<int16_t> tab(1024 * 64);
     build_lanczos4_table(tab.data());
@@ -75,13 +78,15 @@ int b2s_destroy(b2s_handle c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->left, &c->right, &c->planesL, &c->planesR, &c->C, &c->S, &c->raw, &c->disp16, &c->disp2key, &c->labels,
-                      &c->sizes, &c->med, &c->dispf, &c->map1x, &c->map1y, &c->map2x, &c->map2y, &c->vmask, &c->umapx, &c->umapy,
+                      &c->sizes, &c->med, &c->dispf, &c->agg_ho, &c->map1x, &c->map1y, &c->map2x, &c->map2y, &c->vmask, &c->umapx, &c->umapy,
                       &c->und_xy, &c->und_fxy, &c->img1, &c->img2, &c->rect1, &c->rect2, &c->und1, &c->dispfinal, &c->rdepth,
                       &c->udepth, &c->lanczos_tab, &c->stage_f32};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->uev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->aev)
         if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -93,6 +98,7 @@ int b2s_sync(b2s_handle c)
     if (!c) return B2S_EINVAL;
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
+    if (agg_poll_error(c)) return fail(c, B2S_ECUDA, "aggregation hand-over timed out (strips of the fused sweep were not co-resident?)");
     return B2S_OK;
 }
 
@@ -222,6 +228,7 @@ static int compute_disparity_host(b2s_ctx *c, const uint8_t *left, const uint8_t
     if (sync) {
         CK(c, cudaStreamSynchronize(c->stream));
         collect_timing(c, false);
+        if (agg_poll_error(c)) return fail(c, B2S_ECUDA, "aggregation hand-over timed out");
     }
     return B2S_OK;
 }
@@ -334,6 +341,7 @@ static int get_depth_impl(b2s_ctx *c, const uint8_t *img1, const uint8_t *img2, 
     if (sync) {
         CK(c, cudaStreamSynchronize(c->stream));
         collect_timing(c, true);
+        if (agg_poll_error(c)) return fail(c, B2S_ECUDA, "aggregation hand-over timed out");
     }
     return B2S_OK;
 }
@@ -484,6 +492,28 @@ int b2s_bench_aggregate(b2s_handle c, int iters, float *ms_per_iter)
     float ms = 0;
     CK(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[7]));
     *ms_per_iter = ms / iters;
+    return B2S_OK;
+}
+
+int b2s_bench_aggregate_parts(b2s_handle c, int iters, float *ms_parts, int max_parts, int *n_parts)
+{
+    if (!c || !ms_parts || !n_parts || iters <= 0 || max_parts <= 0) return B2S_EINVAL;
+    if (!c->have_volume) return fail(c, B2S_ESTATE, "no cost volume resident (run a disparity computation first)");
+    CK(c, cudaSetDevice(c->device));
+    int nl = 0;
+    CK(c, launch_aggregate(c, &nl)); // warm-up
+    for (int k = 0; k < max_parts; k++) ms_parts[k] = 0.f;
+    for (int i = 0; i < iters; i++) {
+        CK(c, launch_aggregate(c, &nl, c->aev));
+        CK(c, cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < nl && k < max_parts && k < B2S_AGG_MAX_PARTS; k++) {
+            float ms = 0;
+            CK(c, cudaEventElapsedTime(&ms, c->aev[k], c->aev[k + 1]));
+            ms_parts[k] += ms / iters;
+        }
+    }
+    *n_parts = nl < max_parts ? nl : max_parts;
+    if (agg_poll_error(c)) return fail(c, B2S_ECUDA, "aggregation hand-over timed out");
     return B2S_OK;
 }
 

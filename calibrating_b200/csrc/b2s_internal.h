@@ -39,9 +39,11 @@ struct SgbmGeom {
 };
 
 enum { AGG_INIT = 0, AGG_ACCUM = 1 };
+constexpr int B2S_AGG_MAX_PARTS = 8;
 
 struct b2s_ctx {
     int device = 0;
+    int num_sms = 0;
     cudaStream_t stream = nullptr;
     std::string err;
     long long launches = 0;
@@ -60,6 +62,8 @@ struct b2s_ctx {
     DevBuf labels, sizes;     // (H,W) int32 each (speckle filter)
     DevBuf med;               // (H,W) int16 (median output before speckle)
     DevBuf dispf;             // (H,W) f32
+    DevBuf agg_ho;            // hand-over rings of the fused vertical sweep + its error flag (sgbm_agg.cu)
+    int *agg_err = nullptr;   // device address of that flag (valid after an aggregation was enqueued)
 
     // rig
     bool have_rig = false;
@@ -73,6 +77,7 @@ struct b2s_ctx {
 
     cudaEvent_t ev[8] = {};
     cudaEvent_t uev[4] = {};
+    cudaEvent_t aev[B2S_AGG_MAX_PARTS + 1] = {};
     b2s_timing timing{};
 };
 
@@ -80,8 +85,9 @@ struct b2s_ctx {
 // sgbm_cost.cu
 cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t *d_right);
 // sgbm_agg.cu
-cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches);
+cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks = nullptr);
 cudaError_t agg_configure();
+int agg_poll_error(b2s_ctx *c); // after a stream sync: 1 if a hand-over wait of the fused sweep timed out
 // sgbm_post.cu
 cudaError_t launch_wta(b2s_ctx *c);
 cudaError_t launch_post(b2s_ctx *c, int16_t *d_out_disp16, float *d_out_disp);

@@ -12,6 +12,8 @@
 //   * horizontal lines are image rows; vertical and diagonal lines are indexed by their column at the first row and
 //     wrap around the image edge with a state reset (an out-of-image predecessor is L = 0, minL = 0), so all lines
 //     have the same length and every row of C is read as one contiguous span by neighbouring warps.
+#include <stdlib.h>
+
 #include "b2s_internal.h"
 
 namespace {
@@ -25,6 +27,18 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(int n) // wait until at most n groups are pending (n is warp-uniform, 1..7)
+{
+    switch (n) {
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    default: cp_async_wait<7>(); break;
+    }
+}
 
 template <int NP> struct Stages { static constexpr int value = (NP <= 2) ? 16 : (NP == 3 ? 10 : 8); };
 
@@ -191,26 +205,489 @@ cudaError_t launch_dir_np(b2s_ctx *c, const AggArgs &a, int mode)
     }
 }
 
+
+// ================================================================================================================
+// Fused vertical sweep: the three directions that cross image rows, for the top-down sweep (moves (+1,+1) (0,+1) (-1,+1))
+// and -- MODE_HH -- the bottom-up sweep (moves (+1,-1) (0,-1) (-1,-1)) in ONE kernel that reads C once and
+// read-modify-writes S once per sweep (12 B/voxel for six directions instead of 36 with one kernel per direction).
+//
+//   * the image is cut into G <= #SM vertical strips of n columns; CTA = strip, warp = column, lane = 2*NP disparities
+//   * step t handles row t of the top-down sweep and row H-1-t of the bottom-up sweep (J = 2 independent recurrences
+//     interleaved in one instruction stream; the same lane touches the same S words for both, so the two
+//     read-modify-writes of a voxel are ordered by program order and need no fence)
+//   * the vertical state stays in registers; the two diagonal states move one column per row: through a double-buffered
+//     shared-memory slot between warps, and through a 4-deep ring in global memory between neighbouring CTAs.  The ring
+//     carries no flags and needs no fences: states are normalised (L - minL, 15 bits), so bit 15 of every int16 is a
+//     phase bit ((t>>2)&1) written with the data; the consumer lane polls its own words until the phase matches.
+//     A boundary is crossed by one state in each direction every row, so neighbouring CTAs can never be more than one
+//     row apart (lock-step) and a 4-deep ring cannot be overrun.  All G CTAs must be co-resident (G <= #SM, 1 CTA/SM).
+//   * C and S rows are prefetched PF steps ahead into registers (ld.global.cg), ~40 KB in flight per SM.
+struct VsArgs {
+    const int16_t *C;
+    int16_t *S;
+    int H, width1, D, P1, P2;
+    int n;        // columns (= warps) per CTA
+    int up;       // JW == 1 only: 0 = top-down sweep, 1 = bottom-up sweep
+    uint32_t *ho; // hand-over rings [J][G-1][2][HO_SLOTS][32*NP] u32
+    int *err;     // set to 1 if a hand-over wait timed out (never in a correct run)
+};
+constexpr int HO_SLOTS = 4;
+constexpr int HO_SPIN_LIMIT = 1 << 21;
+
+template <int NP> __device__ __forceinline__ void ldcg_regs(const int16_t *src, uint32_t (&v)[NP])
+{
+    if constexpr (NP == 1) v[0] = __ldcg((const uint32_t *)src);
+    else if constexpr (NP == 2) { uint2 t = __ldcg((const uint2 *)src); v[0] = t.x; v[1] = t.y; }
+    else if constexpr (NP == 4) { uint4 t = __ldcg((const uint4 *)src); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) v[i] = __ldcg((const uint32_t *)src + i);
+    }
+}
+template <int NP> __device__ __forceinline__ void stcg_regs(int16_t *dst, const uint32_t (&v)[NP])
+{
+    if constexpr (NP == 1) __stcg((uint32_t *)dst, v[0]);
+    else if constexpr (NP == 2) __stcg((uint2 *)dst, make_uint2(v[0], v[1]));
+    else if constexpr (NP == 4) __stcg((uint4 *)dst, make_uint4(v[0], v[1], v[2], v[3]));
+    else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) __stcg((uint32_t *)dst + i, v[i]);
+    }
+}
+template <int NP> __device__ __forceinline__ void lds_regs(const uint32_t *src, uint32_t (&v)[NP])
+{
+    if constexpr (NP == 2) { uint2 t = *(const uint2 *)src; v[0] = t.x; v[1] = t.y; }
+    else if constexpr (NP == 4) { uint4 t = *(const uint4 *)src; v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) v[i] = src[i];
+    }
+}
+template <int NP> __device__ __forceinline__ void sts_regs(uint32_t *dst, const uint32_t (&v)[NP])
+{
+    if constexpr (NP == 2) *(uint2 *)dst = make_uint2(v[0], v[1]);
+    else if constexpr (NP == 4) *(uint4 *)dst = make_uint4(v[0], v[1], v[2], v[3]);
+    else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) dst[i] = v[i];
+    }
+}
+
+// consumer side of the hand-over ring: poll this lane's words until every int16 carries the expected phase bit
+template <int NP> __device__ __forceinline__ void ho_read(const uint32_t *p, uint32_t phase, uint32_t (&T)[NP], int *err)
+{
+    uint32_t v[NP];
+    int spins = 0;
+    while (true) {
+        if constexpr (NP == 2) asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "l"(p) : "memory");
+        else if constexpr (NP == 4)
+            asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p) : "memory");
+        else {
+#pragma unroll
+            for (int i = 0; i < NP; i++) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[i]) : "l"(p + i) : "memory");
+        }
+        uint32_t bad = 0;
+#pragma unroll
+        for (int i = 0; i < NP; i++) bad |= (v[i] ^ phase) & 0x80008000u;
+        if (__all_sync(0xffffffffu, bad == 0)) break;
+        if (++spins > HO_SPIN_LIMIT || ((spins & 1023) == 0 && *(volatile int *)err != 0)) {
+            *(volatile int *)err = 1;
+            break;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NP; i++) T[i] = v[i] & 0x7FFF7FFFu;
+}
+template <int NP> __device__ __forceinline__ void ho_write(uint32_t *p, uint32_t phase, const uint32_t (&T)[NP])
+{
+    uint32_t v[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) v[i] = (T[i] & 0x7FFF7FFFu) | phase;
+    if constexpr (NP == 2) asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v[0]), "r"(v[1]) : "memory");
+    else if constexpr (NP == 4)
+        asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+    else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p + i), "r"(v[i]) : "memory");
+    }
+}
+
+// one step of one path: T = normalised state of the predecessor pixel (in/out), c = C of this pixel, L = L_r of this pixel
+template <int NP, bool PAD>
+__device__ __forceinline__ void sgm_step(uint32_t (&T)[NP], const uint32_t (&c)[NP], uint32_t (&L)[NP], const uint32_t (&padmask)[NP],
+                                         uint32_t P1v, uint32_t P2mP1v, int lane)
+{
+    const uint32_t BIG = 0x7FFF7FFFu;
+    uint32_t up = __shfl_up_sync(0xffffffffu, T[NP - 1], 1);
+    uint32_t dn = __shfl_down_sync(0xffffffffu, T[0], 1);
+    if (lane == 0) up = BIG;
+    if (lane == 31) dn = BIG;
+    uint32_t m = BIG;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        uint32_t lft = __byte_perm(i == 0 ? up : T[i - 1], T[i], 0x5432);      // L(d-1)
+        uint32_t rgt = __byte_perm(T[i], i == NP - 1 ? dn : T[i + 1], 0x5432); // L(d+1)
+        uint32_t t = __vimin3_s16x2(lft, rgt, P2mP1v);
+        t = __viaddmin_s16x2(t, P1v, T[i]);
+        L[i] = __vadd2(c[i], t);
+        if (PAD) L[i] |= padmask[i];
+        m = __vmins2(m, L[i]);
+    }
+    m = __vmins2(m, __byte_perm(m, m, 0x1032));                 // both halves = min over this lane's disparities
+    m = (uint32_t)__reduce_min_sync(0xffffffffu, (int)m);       // signed 32-bit min of (v,v) pairs = (min,min)
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        T[i] = __vsub2(L[i], m);
+        if (PAD) T[i] |= padmask[i];
+    }
+}
+
+// shared memory through 32-bit shared-window addresses (keeps generic->shared conversions out of the loop)
+template <int NP> __device__ __forceinline__ void lds_s(uint32_t addr, uint32_t (&v)[NP])
+{
+    if constexpr (NP == 2) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(addr) : "memory");
+    else if constexpr (NP == 4)
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr) : "memory");
+    else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[i]) : "r"(addr + 4 * i) : "memory");
+    }
+}
+template <int NP> __device__ __forceinline__ void sts_s(uint32_t addr, const uint32_t (&v)[NP])
+{
+    if constexpr (NP == 2) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(v[0]), "r"(v[1]) : "memory");
+    else if constexpr (NP == 4)
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+    else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + 4 * i), "r"(v[i]) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t saddr, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gsrc) : "memory");
+}
+
+// JW = sweeps handled by one CTA (2: warps [0,n) run the top-down sweep, warps [n,2n) the bottom-up sweep; 1: a.up selects),
+// R = depth of the per-warp cp.async ring.
+template <int NP, bool PAD, int JW, int R>
+__global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
+{
+    constexpr int DW = 32 * NP;           // 32-bit words of one pixel's d-chunk
+    constexpr int CHB = DW * 4;           // ... in bytes
+    constexpr int HO_DIR = HO_SLOTS * DW; // words of one direction's hand-over ring
+    constexpr int NSEG = 2 * DW / 4;      // 16-byte segments of one ring stage: [C | S]
+    constexpr int NLD = (NSEG + 31) / 32; // cp.async instructions per lane and step
+    extern __shared__ __align__(16) uint32_t vs_smem[]; // slots [JW][2 parity][2 dir][n+2][DW], then rings [JW*n][R][2*DW]
+
+    const int lane = threadIdx.x & 31;
+    const int wi = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); // warp-uniform by construction
+    const int n = a.n, G = gridDim.x, H = a.H, Dp = 64 * NP;
+    const int jl = JW == 2 ? (wi >= n ? 1 : 0) : 0; // sweep slot inside the CTA
+    const int w = wi - jl * n;                      // column inside the strip
+    const bool up = JW == 2 ? jl == 1 : a.up != 0;  // bottom-up sweep?
+    const int x = blockIdx.x * n + w;
+    const uint32_t BIG = 0x7FFF7FFFu;
+
+    uint32_t padmask[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        int d0 = (lane * NP + i) * 2;
+        padmask[i] = PAD ? ((d0 >= a.D ? 0x00007FFFu : 0u) | (d0 + 1 >= a.D ? 0x7FFF0000u : 0u)) : 0u;
+    }
+    // every diagonal slot starts as the out-of-image state; the two guard slots (index 0 and n+1) and the slots of idle
+    // columns keep it for ever, which is what the first / last image column must read every row
+    const int NSLOT = JW * 2 * 2 * (n + 2);
+    for (int q = wi; q < NSLOT; q += blockDim.x >> 5) {
+#pragma unroll
+        for (int i = 0; i < NP; i++) vs_smem[q * DW + lane * NP + i] = padmask[i];
+    }
+    __syncthreads();
+    const int gap0 = 1 - H; // gap = 2t - H + 1 >= 0: the other sweep has already passed this step's row
+    if (x >= a.width1) {    // idle warps of the last strip only keep the barrier count
+#pragma unroll 1
+        for (int t = 0; t < H; t++) {
+            if (JW == 2 && gap0 + 2 * t == 0) __syncthreads();
+            __syncthreads();
+        }
+        return;
+    }
+    const bool first_col = x == 0, last_col = x == a.width1 - 1;
+    const bool left_edge = w == 0, right_edge = w == n - 1;
+    const bool out_right = right_edge && !last_col, out_left = left_edge && !first_col;
+    const uint32_t P1v = (uint32_t)a.P1 * 0x10001u, P2mP1v = (uint32_t)(a.P2 - a.P1) * 0x10001u;
+
+    // Processing order of the two diagonals.  dir 0 arrives from column x-1 (moves +1 in x), dir 1 from column x+1.  A warp
+    // on a CTA boundary computes the diagonal it hands to the neighbour CTA FIRST and polls for the one it receives
+    // SECOND, so that the hand-over latency overlaps the rest of the step on both sides.
+    const int fd = (out_left && !out_right) ? 1 : 0;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(vs_smem);
+    const uint32_t PSB = 2 * (n + 2) * CHB; // bytes between the two parities of the slots
+    bool in_glob[2], out_glob[2];
+    uint32_t in_s[2], out_s[2]; // shared addresses (parity 0) of the slot read / written
+    const uint32_t *in_g[2];
+    uint32_t *out_g[2];
+    const int js = up ? 1 : 0; // hand-over rings are indexed by the sweep's direction
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int dir = k == 0 ? fd : fd ^ 1;
+        in_glob[k] = dir == 0 ? (left_edge && !first_col) : (right_edge && !last_col);
+        out_glob[k] = dir == 0 ? out_right : out_left;
+        const uint32_t sl = sbase + ((jl * 2 * 2 + dir) * (n + 2)) * CHB + lane * NP * 4;
+        in_s[k] = sl + (dir == 0 ? w : w + 2) * CHB;
+        out_s[k] = sl + (w + 1) * CHB;
+        // ring of boundary b (between CTA b and b+1), direction dir: ho + ((js*(G-1) + b)*2 + dir) * HO_DIR
+        const int b_in = dir == 0 ? (int)blockIdx.x - 1 : (int)blockIdx.x, b_out = dir == 0 ? (int)blockIdx.x : (int)blockIdx.x - 1;
+        const size_t HJ = (size_t)(G > 1 ? G - 1 : 1) * 2 * HO_DIR;
+        in_g[k] = a.ho + js * HJ + ((size_t)max(b_in, 0) * 2 + dir) * HO_DIR + lane * NP;
+        out_g[k] = a.ho + js * HJ + ((size_t)max(b_out, 0) * 2 + dir) * HO_DIR + lane * NP;
+    }
+    const bool polls = in_glob[1];
+
+    // C and S rows stream through a private cp.async ring of R stages per warp (a register prefetch does not work: the
+    // consumer waits on a scoreboard shared with the younger prefetches, which collapses the prefetch distance)
+    const uint32_t ring = sbase + NSLOT * CHB + wi * (R * 2 * CHB);
+    const long long rs = (long long)a.width1 * Dp * (up ? -1 : 1); // int16 elements to the next row of this sweep
+    const long long o0 = (long long)x * Dp + (up ? (long long)(H - 1) * a.width1 * Dp : 0);
+    const int16_t *src[NLD];
+    uint32_t dsto[NLD];
+#pragma unroll
+    for (int q = 0; q < NLD; q++) {
+        const int seg = lane + 32 * q;
+        const int isS = seg / (DW / 4), r = seg % (DW / 4);
+        src[q] = (isS ? a.S : a.C) + o0 + r * 8;
+        dsto[q] = ring + seg * 16;
+    }
+    auto issue = [&](int stage) { // load the row `src` points at into `stage`, advance to the next row
+#pragma unroll
+        for (int q = 0; q < NLD; q++) {
+            if (lane + 32 * q < NSEG) cp_async16_s(dsto[q] + stage * (2 * CHB), src[q]);
+            src[q] += rs;
+        }
+    };
+#pragma unroll 1
+    for (int p = 0; p < R - 1; p++) {
+        if (p < H) issue(p);
+        cp_async_commit();
+    }
+    int16_t *sp = a.S + o0 + lane * 2 * NP; // this lane's S words in the row of step t
+    const uint32_t cur0 = ring + lane * NP * 4;
+
+    uint32_t Td[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) Td[i] = padmask[i];
+
+    int stage = 0, pstage = R - 1; // stage of step t, stage that step t+R-1 is loaded into
+    uint32_t pin = PSB, pout = 0;  // parity offsets of the slots read (step t-1) and written (step t)
+#pragma unroll 1
+    for (int t = 0; t < H; t++) {
+        __syncwarp();
+        if (t + R - 1 < H) issue(pstage);
+        cp_async_commit();
+        const int so = (t & (HO_SLOTS - 1)) * DW, si = ((t - 1) & (HO_SLOTS - 1)) * DW;
+        const uint32_t ph_out = ((t >> 2) & 1) ? 0x80008000u : 0u, ph_in = (((t - 1) >> 2) & 1) ? 0x80008000u : 0u;
+        const int gap = gap0 + 2 * t;
+        const bool same_row = JW == 2 && gap == 0; // H odd: both sweeps meet on the middle row in this step
+        uint32_t c[NP], s[NP], T0[NP], T1[NP], L0[NP], L1[NP], L2[NP];
+        // predecessor state of the first diagonal
+        if (in_glob[0]) {
+            if (t == 0) {
+#pragma unroll
+                for (int i = 0; i < NP; i++) T0[i] = padmask[i];
+            } else ho_read<NP>(in_g[0] + si, ph_in, T0, a.err);
+        } else lds_s<NP>(in_s[0] + pin, T0);
+        if (!polls) lds_s<NP>(in_s[1] + pin, T1);
+        cp_async_wait<R - 1>();
+        __syncwarp();
+        const uint32_t cur = cur0 + stage * (2 * CHB);
+        lds_s<NP>(cur, c);
+        // the other sweep wrote this row's S less than R steps ago: the prefetched copy may be stale
+        const bool stale = JW == 2 && gap >= 0 && gap <= R;
+        if (!stale) lds_s<NP>(cur + CHB, s);
+        else if (!(same_row && up)) ldcg_regs<NP>(sp, s);
+        if (polls) {
+            sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
+            if (out_glob[0]) ho_write<NP>(out_g[0] + so, ph_out, T0);
+            else sts_s<NP>(out_s[0] + pout, T0);
+            sgm_step<NP, PAD>(Td, c, L2, padmask, P1v, P2mP1v, lane);
+            if (t == 0) {
+#pragma unroll
+                for (int i = 0; i < NP; i++) T1[i] = padmask[i];
+            } else ho_read<NP>(in_g[1] + si, ph_in, T1, a.err);
+            sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
+        } else {
+            sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
+            sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
+            sgm_step<NP, PAD>(Td, c, L2, padmask, P1v, P2mP1v, lane);
+            if (out_glob[0]) ho_write<NP>(out_g[0] + so, ph_out, T0);
+            else sts_s<NP>(out_s[0] + pout, T0);
+        }
+        if (out_glob[1]) ho_write<NP>(out_g[1] + so, ph_out, T1);
+        else sts_s<NP>(out_s[1] + pout, T1);
+        if (same_row) { // both sweeps add to the same S words in this step: top-down first, bottom-up after a barrier
+            if (!up) {
+#pragma unroll
+                for (int i = 0; i < NP; i++) {
+                    uint32_t v = __viaddmin_u16x2(s[i], L0[i], BIG);
+                    v = __viaddmin_u16x2(v, L1[i], BIG);
+                    s[i] = __viaddmin_u16x2(v, L2[i], BIG);
+                }
+                stcg_regs<NP>(sp, s);
+            }
+            __syncthreads();
+            if (up) {
+                ldcg_regs<NP>(sp, s);
+#pragma unroll
+                for (int i = 0; i < NP; i++) {
+                    uint32_t v = __viaddmin_u16x2(s[i], L0[i], BIG);
+                    v = __viaddmin_u16x2(v, L1[i], BIG);
+                    s[i] = __viaddmin_u16x2(v, L2[i], BIG);
+                }
+                stcg_regs<NP>(sp, s);
+            }
+        } else {
+            // S += L, saturating (L >= 0, so the order of the directions does not matter)
+#pragma unroll
+            for (int i = 0; i < NP; i++) {
+                uint32_t v = __viaddmin_u16x2(s[i], L0[i], BIG);
+                v = __viaddmin_u16x2(v, L1[i], BIG);
+                s[i] = __viaddmin_u16x2(v, L2[i], BIG);
+            }
+            stcg_regs<NP>(sp, s);
+        }
+        sp += rs;
+        pstage = stage;
+        stage = stage + 1 == R ? 0 : stage + 1;
+        pin = pout;
+        pout ^= PSB;
+        __syncthreads();
+    }
+}
+
+template <int NP, bool PAD, int JW, int R> cudaError_t launch_vsweep_t(b2s_ctx *c, const VsArgs &a, int G, size_t smem)
+{
+    static bool configured = false; // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(agg_vsweep_kernel<NP, PAD, JW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, agg_vsweep_kernel<NP, PAD, JW, R>, a.n * JW * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1 || G > occ * c->num_sms) return cudaErrorCooperativeLaunchTooLarge; // all strips must be co-resident
+    agg_vsweep_kernel<NP, PAD, JW, R><<<G, a.n * JW * 32, smem, c->stream>>>(a);
+    c->launches++;
+    return cudaGetLastError();
+}
+template <int NP, bool PAD, int JW> cudaError_t launch_vsweep_r(b2s_ctx *c, const VsArgs &a, int G)
+{
+    const size_t slots = (size_t)JW * 2 * 2 * (a.n + 2) * 128 * NP, stage = (size_t)JW * a.n * 2 * 128 * NP;
+    if (slots + 8 * stage <= 200 * 1024) return launch_vsweep_t<NP, PAD, JW, 8>(c, a, G, slots + 8 * stage);
+    if (slots + 4 * stage <= 216 * 1024) return launch_vsweep_t<NP, PAD, JW, 4>(c, a, G, slots + 4 * stage);
+    return cudaErrorInvalidConfiguration;
+}
+// J sweeps (1 = top-down only, 2 = both): in one CTA when 2n warps fit, else one launch per sweep
+template <int NP, bool PAD> cudaError_t launch_vsweep_j(b2s_ctx *c, VsArgs &a, int G, int J)
+{
+    if (J == 2 && a.n * 2 <= 32) return launch_vsweep_r<NP, PAD, 2>(c, a, G);
+    for (int j = 0; j < J; j++) {
+        a.up = j;
+        cudaError_t e = launch_vsweep_r<NP, PAD, 1>(c, a, G);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// columns per CTA for the fused vertical sweep, 0 = not applicable (strip wider than 32 columns: legacy per-direction path)
+int vsweep_cols(const b2s_ctx *c)
+{
+    const SgbmGeom &g = c->g;
+    if (getenv("B2S_AGG_LEGACY")) return 0;
+    int n = (g.width1 + c->num_sms - 1) / c->num_sms;
+    if (n < 8) n = g.width1 < 8 ? g.width1 : 8;
+    if (const char *e = getenv("B2S_VSWEEP_COLS")) { // test hook: force narrow strips so that small images span several CTAs
+        int v = atoi(e);
+        if (v >= 1 && v <= 32 && (g.width1 + v - 1) / v <= c->num_sms) n = v;
+    }
+    return n <= 32 ? n : 0;
+}
+
+cudaError_t launch_vsweep(b2s_ctx *c, int n, int J)
+{
+    const SgbmGeom &g = c->g;
+    const int G = (g.width1 + n - 1) / n;
+    VsArgs a;
+    a.C = c->C.as<int16_t>();
+    a.S = c->S.as<int16_t>();
+    a.H = g.H; a.width1 = g.width1; a.D = g.D; a.P1 = g.P1; a.P2 = g.P2; a.n = n; a.up = 0;
+    size_t ho_bytes = (size_t)2 * (G > 1 ? G - 1 : 1) * 2 * HO_SLOTS * 32 * g.NP * sizeof(uint32_t);
+    cudaError_t e = c->agg_ho.ensure(ho_bytes + 256);
+    if (e != cudaSuccess) return e;
+    // every int16 of the rings starts with phase 1 (steps 0..3 write phase 0); the word after the rings is the error flag
+    if ((e = cudaMemsetAsync(c->agg_ho.p, 0xFF, ho_bytes, c->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync((char *)c->agg_ho.p + ho_bytes, 0, 256, c->stream)) != cudaSuccess) return e;
+    a.ho = c->agg_ho.as<uint32_t>();
+    a.err = (int *)((char *)c->agg_ho.p + ho_bytes);
+    c->agg_err = a.err;
+    const bool pad = g.D != g.Dp;
+    switch (g.NP) {
+    case 1: return pad ? launch_vsweep_j<1, true>(c, a, G, J) : launch_vsweep_j<1, false>(c, a, G, J);
+    case 2: return pad ? launch_vsweep_j<2, true>(c, a, G, J) : launch_vsweep_j<2, false>(c, a, G, J);
+    case 3: return pad ? launch_vsweep_j<3, true>(c, a, G, J) : launch_vsweep_j<3, false>(c, a, G, J);
+    case 4: return pad ? launch_vsweep_j<4, true>(c, a, G, J) : launch_vsweep_j<4, false>(c, a, G, J);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 } // namespace
 
 cudaError_t agg_configure() { return cudaSuccess; }
 
-// Directions as (mx,my) of the MOVE along the path (predecessor = p - move).  cv2 pass 1: (+1,0) (+1,+1) (0,+1) (-1,+1);
-// MODE_SGBM adds (-1,0) during the WTA sweep; MODE_HH pass 2 adds (-1,0) (-1,-1) (0,-1) (+1,-1).
-cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches)
+int agg_poll_error(b2s_ctx *c)
 {
+    if (!c->agg_err) return 0;
+    int v = 0;
+    if (cudaMemcpy(&v, c->agg_err, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    return v;
+}
+
+// Directions as (mx,my) of the MOVE along the path (predecessor = p - move).  cv2 pass 1: (+1,0) (+1,+1) (0,+1) (-1,+1);
+// MODE_SGBM adds (-1,0) during the WTA sweep; MODE_HH pass 2 adds (-1,0) (-1,-1) (0,-1) (+1,-1).  The saturating sum
+// over directions is order-independent, so the schedule is: horizontal (+1,0) initialises S, the fused vertical sweep
+// accumulates three (MODE_SGBM) or six (MODE_HH) directions, horizontal (-1,0) accumulates last.
+cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
+{
+    // marks (nullable): marks[0] is recorded before the first launch and marks[k] after the k-th (at most B2S_AGG_MAX_PARTS)
+    int nm = 0;
+    auto mark = [&]() { if (marks && nm <= B2S_AGG_MAX_PARTS) cudaEventRecord(marks[nm++], c->stream); };
+    mark();
     static const int dirs8[8][2] = {{1, 0}, {-1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, -1}, {0, -1}, {1, -1}};
     const SgbmGeom &g = c->g;
-    int nd = g.mode == 1 ? 8 : 5;
     AggArgs a;
     a.C = c->C.as<int16_t>();
     a.S = c->S.as<int16_t>();
     a.H = g.H; a.width1 = g.width1; a.D = g.D; a.P1 = g.P1; a.P2 = g.P2;
+    cudaError_t e;
+    const int n = vsweep_cols(c);
+    if (n > 0) {
+        a.mx = 1; a.my = 0;
+        if ((e = launch_dir_np(c, a, AGG_INIT)) != cudaSuccess) return e;
+        mark();
+        if ((e = launch_vsweep(c, n, g.mode == 1 ? 2 : 1)) != cudaSuccess) return e;
+        mark();
+        a.mx = -1;
+        if ((e = launch_dir_np(c, a, AGG_ACCUM)) != cudaSuccess) return e;
+        mark();
+        if (n_launches) *n_launches = 3;
+        return cudaSuccess;
+    }
+    int nd = g.mode == 1 ? 8 : 5; // legacy: one scan kernel per direction
     for (int i = 0; i < nd; i++) {
         a.mx = dirs8[i][0];
         a.my = dirs8[i][1];
-        cudaError_t e = launch_dir_np(c, a, i == 0 ? AGG_INIT : AGG_ACCUM);
-        if (e != cudaSuccess) return e;
+        if ((e = launch_dir_np(c, a, i == 0 ? AGG_INIT : AGG_ACCUM)) != cudaSuccess) return e;
+        mark();
     }
     if (n_launches) *n_launches = nd;
     return cudaSuccess;

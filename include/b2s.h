@@ -137,6 +137,10 @@ int b2s_launch_count(b2s_handle h, long long *n);  /* kernels launched by this h
 /* Timed loop of the aggregation kernels alone on the resident cost volume of the last call (bench.py roofline):
  * runs `iters` repetitions on the handle's stream between two CUDA events, returns the mean ms per repetition. */
 int b2s_bench_aggregate(b2s_handle h, int iters, float *ms_per_iter);
+/* Same, with one CUDA-event interval per kernel launch of the aggregation group (in launch order: horizontal +x scan,
+ * fused vertical sweep, horizontal -x scan; or one scan per direction on the legacy path).  ms_parts[k] = mean ms of
+ * launch k over `iters` repetitions, *n_parts = number of launches (<= max_parts). */
+int b2s_bench_aggregate_parts(b2s_handle h, int iters, float *ms_parts, int max_parts, int *n_parts);
 /* User CUDA events on the handle's stream (slot 0..3), for device-side timing of caller-defined regions. */
 int b2s_event_record(b2s_handle h, int slot);
 /* ms between event `slot_a` of handle a and event `slot_b` of handle b (same device); waits for event b. */

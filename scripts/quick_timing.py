@@ -14,3 +14,5 @@ for i in range(3):
 ms = m.handle.bench_aggregate(10)
 V = 1080 * 1792 * 128
 print("aggregate alone: %.3f ms  -> canonical %.1f GB/s (8 B/voxel)" % (ms, V * 8 / ms / 1e6))
+parts = m.handle.bench_aggregate_parts(10)
+print("aggregation launches (ms):", ["%.3f" % p for p in parts], "sum %.3f" % sum(parts))

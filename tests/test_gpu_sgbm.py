@@ -55,6 +55,24 @@ def test_stage_parity_random(handle, seed):
     assert f.dtype == np.float32 and np.array_equal(f, exp / 16.0)
 
 
+@pytest.mark.parametrize("cols", ["1", "2", "3", "5", "32", "legacy"])
+@pytest.mark.parametrize("seed", [1, 2, 3, 5, 6])
+def test_aggregation_strip_handover(handle, seed, cols, monkeypatch):
+    """The fused vertical sweep cut into strips of 1..32 columns (several CTAs exchanging diagonal states through the
+    global hand-over rings) and the legacy one-kernel-per-direction path all give the oracle's S volume."""
+    if cols == "legacy":
+        monkeypatch.setenv("B2S_AGG_LEGACY", "1")
+    else:
+        monkeypatch.setenv("B2S_VSWEEP_COLS", cols)
+    rng = np.random.default_rng(100 + seed)
+    c = _case(rng, mode=seed % 2)
+    l, r, _ = synth.rectified_pair(c["h"], c["w"], c["p"]["num_disparities"], seed, c["cn"])
+    ref = osgbm.sgbm_compute(l, r, want_volumes=True, **c["p"])
+    got = cb.StereoSGBM(handle=handle, **c["p"]).compute(l, r)
+    assert np.array_equal(handle.fetch_volume(1), ref["S"]), "aggregated volume"
+    assert np.array_equal(got, ref["disp"])
+
+
 def test_golden_vectors(handle, golden_dir):
     g = np.load(os.path.join(golden_dir, "sgbm_small.npz"))
     l, r = g["left"], g["right"]

@@ -273,19 +273,29 @@ template <int NP> __device__ __forceinline__ void sts_regs(uint32_t *dst, const 
     }
 }
 
-// consumer side of the hand-over ring: poll this lane's words until every int16 carries the expected phase bit
-template <int NP> __device__ __forceinline__ void ho_read(const uint32_t *p, uint32_t phase, uint32_t (&T)[NP], int *err)
+// consumer side of the hand-over ring: ho_load issues one (non-blocking) load of this lane's words; ho_read takes the loaded
+// words, and while any int16 of the warp does not carry the expected phase bit, loads again
+template <int NP> __device__ __forceinline__ void ho_load(const uint32_t *p, uint32_t (&v)[NP])
+{
+    if constexpr (NP == 2) asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "l"(p) : "memory");
+    else if constexpr (NP == 4)
+        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p) : "memory");
+    else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[i]) : "l"(p + i) : "memory");
+    }
+}
+template <int NP> __device__ __forceinline__ void ho_read(const uint32_t *p, uint32_t phase, uint32_t (&T)[NP], int *err, bool preloaded = false)
 {
     uint32_t v[NP];
     int spins = 0;
-    while (true) {
-        if constexpr (NP == 2) asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "l"(p) : "memory");
-        else if constexpr (NP == 4)
-            asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p) : "memory");
-        else {
+    if (preloaded) {
 #pragma unroll
-            for (int i = 0; i < NP; i++) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[i]) : "l"(p + i) : "memory");
-        }
+        for (int i = 0; i < NP; i++) v[i] = T[i];
+    }
+    while (true) {
+        if (!preloaded) ho_load<NP>(p, v);
+        preloaded = false;
         uint32_t bad = 0;
 #pragma unroll
         for (int i = 0; i < NP; i++) bad |= (v[i] ^ phase) & 0x80008000u;
@@ -403,15 +413,9 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
         for (int i = 0; i < NP; i++) vs_smem[q * DW + lane * NP + i] = padmask[i];
     }
     __syncthreads();
-    const int gap0 = 1 - H; // gap = 2t - H + 1 >= 0: the other sweep has already passed this step's row
-    if (x >= a.width1) {    // idle warps of the last strip only keep the barrier count
-#pragma unroll 1
-        for (int t = 0; t < H; t++) {
-            if (JW == 2 && gap0 + 2 * t == 0) __syncthreads();
-            __syncthreads();
-        }
-        return;
-    }
+    const int gap0 = 1 - H;             // gap = 2t - H + 1 >= 0: the other sweep has already passed this step's row
+    if (x >= a.width1) return;          // idle warps of the last strip
+    const int nact = min(n, a.width1 - (int)blockIdx.x * n) * 32; // threads per sweep that take part in the step barriers
     const bool first_col = x == 0, last_col = x == a.width1 - 1;
     const bool left_edge = w == 0, right_edge = w == n - 1;
     const bool out_right = right_edge && !last_col, out_left = left_edge && !first_col;
@@ -497,6 +501,7 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
             } else ho_read<NP>(in_g[0] + si, ph_in, T0, a.err);
         } else lds_s<NP>(in_s[0] + pin, T0);
         if (!polls) lds_s<NP>(in_s[1] + pin, T1);
+        else if (t != 0) ho_load<NP>(in_g[1] + si, T1); // issued now, checked after the first diagonal: it usually landed a step ago
         cp_async_wait<R - 1>();
         __syncwarp();
         const uint32_t cur = cur0 + stage * (2 * CHB);
@@ -513,7 +518,7 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
             if (t == 0) {
 #pragma unroll
                 for (int i = 0; i < NP; i++) T1[i] = padmask[i];
-            } else ho_read<NP>(in_g[1] + si, ph_in, T1, a.err);
+            } else ho_read<NP>(in_g[1] + si, ph_in, T1, a.err, true);
             sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
         } else {
             sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
@@ -534,7 +539,7 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
                 }
                 stcg_regs<NP>(sp, s);
             }
-            __syncthreads();
+            asm volatile("bar.sync 3, %0;" ::"r"(JW * nact) : "memory");
             if (up) {
                 ldcg_regs<NP>(sp, s);
 #pragma unroll
@@ -560,7 +565,8 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
         stage = stage + 1 == R ? 0 : stage + 1;
         pin = pout;
         pout ^= PSB;
-        __syncthreads();
+        // one barrier per step for both sweeps: besides the slot exchange it orders the two sweeps' updates of S
+        asm volatile("bar.sync 1, %0;" ::"r"(JW * nact) : "memory");
     }
 }
 

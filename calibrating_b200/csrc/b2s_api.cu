@@ -77,7 +77,7 @@ int b2s_destroy(b2s_handle c)
     if (!c) return B2S_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->left, &c->right, &c->planesL, &c->planesR, &c->C, &c->S, &c->raw, &c->disp16, &c->disp2key, &c->labels,
+    DevBuf *bufs[] = {&c->left, &c->right, &c->planesL, &c->planesR, &c->C, &c->S, &c->S2, &c->raw, &c->disp16, &c->disp2key, &c->labels,
                       &c->sizes, &c->med, &c->dispf, &c->agg_ho, &c->map1x, &c->map1y, &c->map2x, &c->map2y, &c->vmask, &c->umapx, &c->umapy,
                       &c->und_xy, &c->und_fxy, &c->img1, &c->img2, &c->rect1, &c->rect2, &c->und1, &c->dispfinal, &c->rdepth,
                       &c->udepth, &c->lanczos_tab, &c->stage_f32};
@@ -166,6 +166,7 @@ static int make_geom(b2s_ctx *c, int H, int W, int cn)
     CK(c, c->planesR.ensure(npx * 2 * cn * 4));
     CK(c, c->C.ensure(vol));
     CK(c, c->S.ensure(vol));
+    if (g.mode == 1) CK(c, c->S2.ensure(vol));
     CK(c, c->raw.ensure(npx * 2));
     CK(c, c->disp16.ensure(npx * 2));
     CK(c, c->med.ensure(npx * 2));

@@ -38,7 +38,7 @@ struct SgbmGeom {
     int speckle_window, speckle_range, mode;
 };
 
-enum { AGG_INIT = 0, AGG_ACCUM = 1 };
+enum { AGG_INIT = 0, AGG_ACCUM = 1, AGG_ACCUM2 = 2 };
 constexpr int B2S_AGG_MAX_PARTS = 8;
 
 struct b2s_ctx {
@@ -57,6 +57,7 @@ struct b2s_ctx {
     DevBuf left, right;       // (H,W,cn) u8
     DevBuf planesL, planesR;  // (H, 2cn, W) uchar4 = (value, lo, hi, 0)
     DevBuf C, S;              // (H, width1, Dp) int16;  S doubles as the horizontal-sum scratch
+    DevBuf S2;                // MODE_HH: partial sum of the bottom-up sweep, same shape
     DevBuf raw, disp16;       // (H,W) int16
     DevBuf disp2key;          // (H,W+2) u32: (minS<<16)|(0xFFFF-x1) of the winning left pixel, 0xFFFFFFFF = none
     DevBuf labels, sizes;     // (H,W) int32 each (speckle filter)

@@ -40,11 +40,12 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) // wait until at most n
     }
 }
 
-template <int NP> struct Stages { static constexpr int value = (NP <= 2) ? 16 : (NP == 3 ? 10 : 8); };
+template <int NP> struct Stages { static constexpr int value = (NP <= 2) ? 16 : (NP == 3 ? 10 : 8); }; // x 3 sources x 8 warps <= 98 KB
 
 struct AggArgs {
     const int16_t *C;
     int16_t *S;
+    const int16_t *S2; // AGG_ACCUM2: second partial sum added on the fly (the bottom-up sweep's)
     int H, width1, D;
     int mx, my;
     int P1, P2;
@@ -65,7 +66,7 @@ template <int NP, bool PAD, int MODE>
 __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
 {
     constexpr int CH = 128 * NP;                       // bytes of one pixel's d-chunk
-    constexpr int NSRC = (MODE == AGG_ACCUM) ? 2 : 1;  // C only, or C and S
+    constexpr int NSRC = MODE == AGG_ACCUM2 ? 3 : (MODE == AGG_ACCUM ? 2 : 1); // C only; C and S; C, S and S2
     constexpr int STAGE_BYTES = CH * NSRC;
     constexpr int STAGES = Stages<NP>::value;
     constexpr int NSEG = STAGE_BYTES / 16;
@@ -95,7 +96,8 @@ __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
         unsigned char *dst = ring + stage * STAGE_BYTES;
 #pragma unroll
         for (int seg = lane; seg < NSEG; seg += 32) {
-            const int16_t *src = (NSRC == 1 || seg < CH / 16) ? a.C + off + seg * 8 : a.S + off + (seg - CH / 16) * 8;
+            const int which = NSRC == 1 ? 0 : seg / (CH / 16), r = seg - which * (CH / 16);
+            const int16_t *src = (which == 0 ? a.C : (which == 1 ? a.S : a.S2)) + off + r * 8;
             cp_async16(dst + seg * 16, src);
         }
         advance(px, py);
@@ -132,9 +134,13 @@ __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
         uint32_t c[NP], sv[NP];
 #pragma unroll
         for (int i = 0; i < NP; i++) c[i] = st[lane * NP + i];
-        if (MODE == AGG_ACCUM) {
+        if (MODE != AGG_INIT) {
 #pragma unroll
             for (int i = 0; i < NP; i++) sv[i] = st[CH / 4 + lane * NP + i];
+        }
+        if (MODE == AGG_ACCUM2) {
+#pragma unroll
+            for (int i = 0; i < NP; i++) sv[i] = __viaddmin_u16x2(sv[i], st[2 * (CH / 4) + lane * NP + i], BIG);
         }
         // out-of-image predecessor: L = 0, minL = 0
         bool reset = (k == 0) || (a.my != 0 && ((a.mx > 0 && x == 0) || (a.mx < 0 && x == a.width1 - 1)));
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
 #pragma unroll
         for (int i = 0; i < NP; i++) {
             Ln[i] = __vadd2(L[i], negmin) | padmask[i];
-            out[i] = (MODE == AGG_ACCUM) ? __viaddmin_u16x2(sv[i], L[i], BIG) : L[i]; // saturating accumulate (L >= 0)
+            out[i] = (MODE != AGG_INIT) ? __viaddmin_u16x2(sv[i], L[i], BIG) : L[i]; // saturating accumulate (L >= 0)
         }
         store_regs<NP>(a.S + ((size_t)y * a.width1 + x) * Dp + lane * 2 * NP, out);
         advance(x, y);
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
 
 template <int NP, bool PAD, int MODE> cudaError_t launch_scan(b2s_ctx *c, const AggArgs &a)
 {
-    constexpr int STAGE_BYTES = 128 * NP * (MODE == AGG_ACCUM ? 2 : 1);
+    constexpr int STAGE_BYTES = 128 * NP * (MODE == AGG_ACCUM2 ? 3 : (MODE == AGG_ACCUM ? 2 : 1));
     size_t smem = (size_t)WARPS * Stages<NP>::value * STAGE_BYTES;
     static bool configured = false; // per instantiation
     if (!configured) {
@@ -190,6 +196,7 @@ template <int NP, bool PAD, int MODE> cudaError_t launch_scan(b2s_ctx *c, const 
 
 template <int NP, bool PAD> cudaError_t launch_dir(b2s_ctx *c, const AggArgs &a, int mode)
 {
+    if (mode == AGG_ACCUM2) return launch_scan<NP, PAD, AGG_ACCUM2>(c, a);
     return mode == AGG_INIT ? launch_scan<NP, PAD, AGG_INIT>(c, a) : launch_scan<NP, PAD, AGG_ACCUM>(c, a);
 }
 
@@ -224,7 +231,8 @@ cudaError_t launch_dir_np(b2s_ctx *c, const AggArgs &a, int mode)
 //   * C and S rows are prefetched PF steps ahead into registers (ld.global.cg), ~40 KB in flight per SM.
 struct VsArgs {
     const int16_t *C;
-    int16_t *S;
+    int16_t *S;   // top-down sweep: S += its three paths
+    int16_t *S2;  // bottom-up sweep: S2 = sum of its three paths
     int H, width1, D, P1, P2;
     int n;        // columns (= warps) per CTA
     int up;       // JW == 1 only: 0 = top-down sweep, 1 = bottom-up sweep
@@ -232,7 +240,7 @@ struct VsArgs {
     int *err;     // set to 1 if a hand-over wait timed out (never in a correct run)
 };
 constexpr int HO_SLOTS = 4;
-constexpr int HO_SPIN_LIMIT = 1 << 21;
+constexpr int HO_SPIN_LIMIT = 1 << 18;
 
 template <int NP> __device__ __forceinline__ void ldcg_regs(const int16_t *src, uint32_t (&v)[NP])
 {
@@ -347,7 +355,7 @@ __device__ __forceinline__ void sgm_step(uint32_t (&T)[NP], const uint32_t (&c)[
     m = (uint32_t)__reduce_min_sync(0xffffffffu, (int)m);       // signed 32-bit min of (v,v) pairs = (min,min)
 #pragma unroll
     for (int i = 0; i < NP; i++) {
-        T[i] = __vsub2(L[i], m);
+        T[i] = L[i] - m; // both halves of L are >= their half of m: the 32-bit difference has no borrow = packed difference
         if (PAD) T[i] |= padmask[i];
     }
 }
@@ -378,8 +386,34 @@ __device__ __forceinline__ void cp_async16_s(uint32_t saddr, const void *gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gsrc) : "memory");
 }
 
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t addr)
+{
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(addr) : "memory");
+}
+// wait until the phase of parity `parity` of the mbarrier has completed (acquire)
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity, int *err)
+{
+    uint32_t ok;
+    int spins = 0;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (!ok && (++spins > (1 << 16) || ((spins & 63) == 0 && *(volatile int *)err != 0))) {
+            *(volatile int *)err = 1;
+            break;
+        }
+    } while (!ok);
+}
+
 // JW = sweeps handled by one CTA (2: warps [0,n) run the top-down sweep, warps [n,2n) the bottom-up sweep; 1: a.up selects),
-// R = depth of the per-warp cp.async ring.
+// R = depth of the per-warp cp.async ring.  The top-down sweep adds its three paths to S; the bottom-up sweep (MODE_HH)
+// writes the sum of its three paths to S2 without reading anything but C, so the two sweeps share no data at all.
+// Warps synchronise only with their two neighbour columns (one mbarrier per warp, phase = row), so the warps of an SM
+// drift apart by up to a row per column and keep the issue slots busy while others wait.
 template <int NP, bool PAD, int JW, int R>
 __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
 {
@@ -388,7 +422,8 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
     constexpr int HO_DIR = HO_SLOTS * DW; // words of one direction's hand-over ring
     constexpr int NSEG = 2 * DW / 4;      // 16-byte segments of one ring stage: [C | S]
     constexpr int NLD = (NSEG + 31) / 32; // cp.async instructions per lane and step
-    extern __shared__ __align__(16) uint32_t vs_smem[]; // slots [JW][2 parity][2 dir][n+2][DW], then rings [JW*n][R][2*DW]
+    // mbarriers [JW*n][2] (8 B each), slots [JW][2 parity][2 dir][n+2][DW], rings [JW*n][R][2*DW]
+    extern __shared__ __align__(16) uint32_t vs_smem[];
 
     const int lane = threadIdx.x & 31;
     const int wi = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); // warp-uniform by construction
@@ -396,8 +431,12 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
     const int jl = JW == 2 ? (wi >= n ? 1 : 0) : 0; // sweep slot inside the CTA
     const int w = wi - jl * n;                      // column inside the strip
     const bool up = JW == 2 ? jl == 1 : a.up != 0;  // bottom-up sweep?
+    const bool acc = !up;                           // top-down: S += paths; bottom-up: S2 = paths
     const int x = blockIdx.x * n + w;
     const uint32_t BIG = 0x7FFF7FFFu;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(vs_smem);
+    const uint32_t MBB = JW * n * 16; // two mbarriers per warp (even rows, odd rows)
+    uint32_t *slots = vs_smem + MBB / 4;
 
     uint32_t padmask[NP];
 #pragma unroll
@@ -410,12 +449,11 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
     const int NSLOT = JW * 2 * 2 * (n + 2);
     for (int q = wi; q < NSLOT; q += blockDim.x >> 5) {
 #pragma unroll
-        for (int i = 0; i < NP; i++) vs_smem[q * DW + lane * NP + i] = padmask[i];
+        for (int i = 0; i < NP; i++) slots[q * DW + lane * NP + i] = padmask[i];
     }
+    if (threadIdx.x < JW * n * 2) mbar_init(sbase + threadIdx.x * 8, 1);
     __syncthreads();
-    const int gap0 = 1 - H;             // gap = 2t - H + 1 >= 0: the other sweep has already passed this step's row
-    if (x >= a.width1) return;          // idle warps of the last strip
-    const int nact = min(n, a.width1 - (int)blockIdx.x * n) * 32; // threads per sweep that take part in the step barriers
+    if (x >= a.width1) return; // idle warps of the last strip
     const bool first_col = x == 0, last_col = x == a.width1 - 1;
     const bool left_edge = w == 0, right_edge = w == n - 1;
     const bool out_right = right_edge && !last_col, out_left = left_edge && !first_col;
@@ -425,10 +463,9 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
     // on a CTA boundary computes the diagonal it hands to the neighbour CTA FIRST and polls for the one it receives
     // SECOND, so that the hand-over latency overlaps the rest of the step on both sides.
     const int fd = (out_left && !out_right) ? 1 : 0;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(vs_smem);
     const uint32_t PSB = 2 * (n + 2) * CHB; // bytes between the two parities of the slots
     bool in_glob[2], out_glob[2];
-    uint32_t in_s[2], out_s[2]; // shared addresses (parity 0) of the slot read / written
+    uint32_t in_s[2], out_s[2], in_mb[2]; // shared addresses: slot read / written (parity 0), mbarrier of the producing warp (0: none)
     const uint32_t *in_g[2];
     uint32_t *out_g[2];
     const int js = up ? 1 : 0; // hand-over rings are indexed by the sweep's direction
@@ -437,9 +474,12 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
         const int dir = k == 0 ? fd : fd ^ 1;
         in_glob[k] = dir == 0 ? (left_edge && !first_col) : (right_edge && !last_col);
         out_glob[k] = dir == 0 ? out_right : out_left;
-        const uint32_t sl = sbase + ((jl * 2 * 2 + dir) * (n + 2)) * CHB + lane * NP * 4;
+        const uint32_t sl = sbase + MBB + ((jl * 2 * 2 + dir) * (n + 2)) * CHB + lane * NP * 4;
         in_s[k] = sl + (dir == 0 ? w : w + 2) * CHB;
         out_s[k] = sl + (w + 1) * CHB;
+        const int wn = dir == 0 ? w - 1 : w + 1; // producing warp (column) inside the strip
+        const bool has = wn >= 0 && wn < n && (int)blockIdx.x * n + wn < a.width1;
+        in_mb[k] = has ? sbase + (jl * n + wn) * 16 : 0u;
         // ring of boundary b (between CTA b and b+1), direction dir: ho + ((js*(G-1) + b)*2 + dir) * HO_DIR
         const int b_in = dir == 0 ? (int)blockIdx.x - 1 : (int)blockIdx.x, b_out = dir == 0 ? (int)blockIdx.x : (int)blockIdx.x - 1;
         const size_t HJ = (size_t)(G > 1 ? G - 1 : 1) * 2 * HO_DIR;
@@ -447,25 +487,28 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
         out_g[k] = a.ho + js * HJ + ((size_t)max(b_out, 0) * 2 + dir) * HO_DIR + lane * NP;
     }
     const bool polls = in_glob[1];
+    const uint32_t my_mb = sbase + (jl * n + w) * 16;
 
-    // C and S rows stream through a private cp.async ring of R stages per warp (a register prefetch does not work: the
+    // C (and S) rows stream through a private cp.async ring of R stages per warp (a register prefetch does not work: the
     // consumer waits on a scoreboard shared with the younger prefetches, which collapses the prefetch distance)
-    const uint32_t ring = sbase + NSLOT * CHB + wi * (R * 2 * CHB);
+    const uint32_t ring = sbase + MBB + NSLOT * CHB + wi * (R * 2 * CHB);
     const long long rs = (long long)a.width1 * Dp * (up ? -1 : 1); // int16 elements to the next row of this sweep
     const long long o0 = (long long)x * Dp + (up ? (long long)(H - 1) * a.width1 * Dp : 0);
     const int16_t *src[NLD];
     uint32_t dsto[NLD];
+    bool ldok[NLD];
 #pragma unroll
     for (int q = 0; q < NLD; q++) {
         const int seg = lane + 32 * q;
         const int isS = seg / (DW / 4), r = seg % (DW / 4);
         src[q] = (isS ? a.S : a.C) + o0 + r * 8;
         dsto[q] = ring + seg * 16;
+        ldok[q] = seg < NSEG && (acc || !isS);
     }
     auto issue = [&](int stage) { // load the row `src` points at into `stage`, advance to the next row
 #pragma unroll
         for (int q = 0; q < NLD; q++) {
-            if (lane + 32 * q < NSEG) cp_async16_s(dsto[q] + stage * (2 * CHB), src[q]);
+            if (ldok[q]) cp_async16_s(dsto[q] + stage * (2 * CHB), src[q]);
             src[q] += rs;
         }
     };
@@ -474,99 +517,86 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
         if (p < H) issue(p);
         cp_async_commit();
     }
-    int16_t *sp = a.S + o0 + lane * 2 * NP; // this lane's S words in the row of step t
+    int16_t *sp = (acc ? a.S : a.S2) + o0 + lane * 2 * NP; // this lane's output words in the row of step t
     const uint32_t cur0 = ring + lane * NP * 4;
 
-    uint32_t Td[NP];
+    uint32_t Td[NP], Tpre[NP], c[NP], s[NP];
 #pragma unroll
-    for (int i = 0; i < NP; i++) Td[i] = padmask[i];
+    for (int i = 0; i < NP; i++) Td[i] = Tpre[i] = s[i] = padmask[i];
+    cp_async_wait<R - 2>();
+    __syncwarp();
+    lds_s<NP>(cur0, c);
+    if (acc) lds_s<NP>(cur0 + CHB, s);
 
-    int stage = 0, pstage = R - 1; // stage of step t, stage that step t+R-1 is loaded into
-    uint32_t pin = PSB, pout = 0;  // parity offsets of the slots read (step t-1) and written (step t)
+    int stage = 1 % R, pstage = R - 1; // stage of step t+1, stage that step t+R-1 is loaded into
+    uint32_t pin = PSB, pout = 0;      // parity offsets of the slots read (step t-1) and written (step t)
 #pragma unroll 1
     for (int t = 0; t < H; t++) {
-        __syncwarp();
-        if (t + R - 1 < H) issue(pstage);
-        cp_async_commit();
-        const int so = (t & (HO_SLOTS - 1)) * DW, si = ((t - 1) & (HO_SLOTS - 1)) * DW;
-        const uint32_t ph_out = ((t >> 2) & 1) ? 0x80008000u : 0u, ph_in = (((t - 1) >> 2) & 1) ? 0x80008000u : 0u;
-        const int gap = gap0 + 2 * t;
-        const bool same_row = JW == 2 && gap == 0; // H odd: both sweeps meet on the middle row in this step
-        uint32_t c[NP], s[NP], T0[NP], T1[NP], L0[NP], L1[NP], L2[NP];
-        // predecessor state of the first diagonal
-        if (in_glob[0]) {
+        // ---- critical section: from the neighbours' row t-1 states to this column's row t states ------------------
+        // a warp signals even rows on its first mbarrier and odd rows on the second: a neighbour may run one row ahead, and
+        // with a single barrier two completed phases would look like none
+        const uint32_t mb_off = ((t - 1) & 1) * 8, par_in = ((t - 1) >> 1) & 1;
+        uint32_t T0[NP], T1[NP], L0[NP], L1[NP], L2[NP];
+        if (in_glob[0]) { // (only a one-column strip receives both diagonals from other CTAs)
             if (t == 0) {
 #pragma unroll
                 for (int i = 0; i < NP; i++) T0[i] = padmask[i];
-            } else ho_read<NP>(in_g[0] + si, ph_in, T0, a.err);
-        } else lds_s<NP>(in_s[0] + pin, T0);
-        if (!polls) lds_s<NP>(in_s[1] + pin, T1);
-        else if (t != 0) ho_load<NP>(in_g[1] + si, T1); // issued now, checked after the first diagonal: it usually landed a step ago
-        cp_async_wait<R - 1>();
-        __syncwarp();
-        const uint32_t cur = cur0 + stage * (2 * CHB);
-        lds_s<NP>(cur, c);
-        // the other sweep wrote this row's S less than R steps ago: the prefetched copy may be stale
-        const bool stale = JW == 2 && gap >= 0 && gap <= R;
-        if (!stale) lds_s<NP>(cur + CHB, s);
-        else if (!(same_row && up)) ldcg_regs<NP>(sp, s);
+            } else ho_read<NP>(in_g[0] + ((t - 1) & (HO_SLOTS - 1)) * DW, (((t - 1) >> 2) & 1) ? 0x80008000u : 0u, T0, a.err);
+        } else {
+            if (in_mb[0] && t != 0) mbar_wait(in_mb[0] + mb_off, par_in, a.err);
+            lds_s<NP>(in_s[0] + pin, T0);
+        }
         if (polls) {
             sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
-            if (out_glob[0]) ho_write<NP>(out_g[0] + so, ph_out, T0);
+            if (out_glob[0]) ho_write<NP>(out_g[0] + (t & (HO_SLOTS - 1)) * DW, ((t >> 2) & 1) ? 0x80008000u : 0u, T0);
             else sts_s<NP>(out_s[0] + pout, T0);
-            sgm_step<NP, PAD>(Td, c, L2, padmask, P1v, P2mP1v, lane);
             if (t == 0) {
 #pragma unroll
                 for (int i = 0; i < NP; i++) T1[i] = padmask[i];
-            } else ho_read<NP>(in_g[1] + si, ph_in, T1, a.err, true);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NP; i++) T1[i] = Tpre[i]; // loaded at the end of the previous step
+                ho_read<NP>(in_g[1] + ((t - 1) & (HO_SLOTS - 1)) * DW, (((t - 1) >> 2) & 1) ? 0x80008000u : 0u, T1, a.err, true);
+            }
             sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
         } else {
+            if (in_mb[1] && t != 0) mbar_wait(in_mb[1] + mb_off, par_in, a.err);
+            lds_s<NP>(in_s[1] + pin, T1);
             sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
             sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
-            sgm_step<NP, PAD>(Td, c, L2, padmask, P1v, P2mP1v, lane);
-            if (out_glob[0]) ho_write<NP>(out_g[0] + so, ph_out, T0);
+            if (out_glob[0]) ho_write<NP>(out_g[0] + (t & (HO_SLOTS - 1)) * DW, ((t >> 2) & 1) ? 0x80008000u : 0u, T0);
             else sts_s<NP>(out_s[0] + pout, T0);
         }
-        if (out_glob[1]) ho_write<NP>(out_g[1] + so, ph_out, T1);
+        if (out_glob[1]) ho_write<NP>(out_g[1] + (t & (HO_SLOTS - 1)) * DW, ((t >> 2) & 1) ? 0x80008000u : 0u, T1);
         else sts_s<NP>(out_s[1] + pout, T1);
-        if (same_row) { // both sweeps add to the same S words in this step: top-down first, bottom-up after a barrier
-            if (!up) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(my_mb + (t & 1) * 8); // this column's row-t states are in their slots
+        // the neighbour CTA wrote the state this warp needs in the next step early in ITS step t: fetch it now
+        if (polls) ho_load<NP>(in_g[1] + (t & (HO_SLOTS - 1)) * DW, Tpre);
+        // ---- off the critical path: vertical path, sums, store, next row's C and S -----------------------------------
+        asm volatile("" : "+r"(Td[0]) : : "memory"); // keeps the compiler from hoisting the vertical path above the hand-over
+        sgm_step<NP, PAD>(Td, c, L2, padmask, P1v, P2mP1v, lane);
+        // saturating sums (L >= 0, so the order of the directions does not matter)
 #pragma unroll
-                for (int i = 0; i < NP; i++) {
-                    uint32_t v = __viaddmin_u16x2(s[i], L0[i], BIG);
-                    v = __viaddmin_u16x2(v, L1[i], BIG);
-                    s[i] = __viaddmin_u16x2(v, L2[i], BIG);
-                }
-                stcg_regs<NP>(sp, s);
-            }
-            asm volatile("bar.sync 3, %0;" ::"r"(JW * nact) : "memory");
-            if (up) {
-                ldcg_regs<NP>(sp, s);
-#pragma unroll
-                for (int i = 0; i < NP; i++) {
-                    uint32_t v = __viaddmin_u16x2(s[i], L0[i], BIG);
-                    v = __viaddmin_u16x2(v, L1[i], BIG);
-                    s[i] = __viaddmin_u16x2(v, L2[i], BIG);
-                }
-                stcg_regs<NP>(sp, s);
-            }
-        } else {
-            // S += L, saturating (L >= 0, so the order of the directions does not matter)
-#pragma unroll
-            for (int i = 0; i < NP; i++) {
-                uint32_t v = __viaddmin_u16x2(s[i], L0[i], BIG);
-                v = __viaddmin_u16x2(v, L1[i], BIG);
-                s[i] = __viaddmin_u16x2(v, L2[i], BIG);
-            }
-            stcg_regs<NP>(sp, s);
+        for (int i = 0; i < NP; i++) {
+            uint32_t v = __viaddmin_u16x2(L0[i], L1[i], BIG);
+            v = __viaddmin_u16x2(v, L2[i], BIG);
+            s[i] = acc ? __viaddmin_u16x2(s[i], v, BIG) : v;
         }
+        stcg_regs<NP>(sp, s);
         sp += rs;
-        pstage = stage;
+        __syncwarp();
+        if (t + R - 1 < H) issue(pstage);
+        cp_async_commit();
+        cp_async_wait<R - 2>(); // row t+1 has landed
+        __syncwarp();
+        const uint32_t cur = cur0 + stage * (2 * CHB);
+        lds_s<NP>(cur, c);
+        if (acc) lds_s<NP>(cur + CHB, s);
+        pstage = pstage + 1 == R ? 0 : pstage + 1;
         stage = stage + 1 == R ? 0 : stage + 1;
         pin = pout;
         pout ^= PSB;
-        // one barrier per step for both sweeps: besides the slot exchange it orders the two sweeps' updates of S
-        asm volatile("bar.sync 1, %0;" ::"r"(JW * nact) : "memory");
     }
 }
 
@@ -588,9 +618,9 @@ template <int NP, bool PAD, int JW, int R> cudaError_t launch_vsweep_t(b2s_ctx *
 }
 template <int NP, bool PAD, int JW> cudaError_t launch_vsweep_r(b2s_ctx *c, const VsArgs &a, int G)
 {
-    const size_t slots = (size_t)JW * 2 * 2 * (a.n + 2) * 128 * NP, stage = (size_t)JW * a.n * 2 * 128 * NP;
-    if (slots + 8 * stage <= 200 * 1024) return launch_vsweep_t<NP, PAD, JW, 8>(c, a, G, slots + 8 * stage);
-    if (slots + 4 * stage <= 216 * 1024) return launch_vsweep_t<NP, PAD, JW, 4>(c, a, G, slots + 4 * stage);
+    const size_t fixed = (size_t)JW * a.n * 16 + (size_t)JW * 2 * 2 * (a.n + 2) * 128 * NP, stage = (size_t)JW * a.n * 2 * 128 * NP;
+    if (fixed + 8 * stage <= 200 * 1024) return launch_vsweep_t<NP, PAD, JW, 8>(c, a, G, fixed + 8 * stage);
+    if (fixed + 4 * stage <= 216 * 1024) return launch_vsweep_t<NP, PAD, JW, 4>(c, a, G, fixed + 4 * stage);
     return cudaErrorInvalidConfiguration;
 }
 // J sweeps (1 = top-down only, 2 = both): in one CTA when 2n warps fit, else one launch per sweep
@@ -626,6 +656,7 @@ cudaError_t launch_vsweep(b2s_ctx *c, int n, int J)
     VsArgs a;
     a.C = c->C.as<int16_t>();
     a.S = c->S.as<int16_t>();
+    a.S2 = c->S2.as<int16_t>();
     a.H = g.H; a.width1 = g.width1; a.D = g.D; a.P1 = g.P1; a.P2 = g.P2; a.n = n; a.up = 0;
     size_t ho_bytes = (size_t)2 * (G > 1 ? G - 1 : 1) * 2 * HO_SLOTS * 32 * g.NP * sizeof(uint32_t);
     cudaError_t e = c->agg_ho.ensure(ho_bytes + 256);
@@ -660,8 +691,9 @@ int agg_poll_error(b2s_ctx *c)
 
 // Directions as (mx,my) of the MOVE along the path (predecessor = p - move).  cv2 pass 1: (+1,0) (+1,+1) (0,+1) (-1,+1);
 // MODE_SGBM adds (-1,0) during the WTA sweep; MODE_HH pass 2 adds (-1,0) (-1,-1) (0,-1) (+1,-1).  The saturating sum
-// over directions is order-independent, so the schedule is: horizontal (+1,0) initialises S, the fused vertical sweep
-// accumulates three (MODE_SGBM) or six (MODE_HH) directions, horizontal (-1,0) accumulates last.
+// over directions is order-independent, so the schedule is: horizontal (+1,0) initialises S; the fused vertical sweep
+// adds the three top-down directions to S and (MODE_HH) writes the sum of the three bottom-up directions to S2;
+// horizontal (-1,0) comes last and folds S2 in: S = sat(S + S2 + L).
 cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
 {
     // marks (nullable): marks[0] is recorded before the first launch and marks[k] after the k-th (at most B2S_AGG_MAX_PARTS)
@@ -673,6 +705,7 @@ cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
     AggArgs a;
     a.C = c->C.as<int16_t>();
     a.S = c->S.as<int16_t>();
+    a.S2 = c->S2.as<int16_t>();
     a.H = g.H; a.width1 = g.width1; a.D = g.D; a.P1 = g.P1; a.P2 = g.P2;
     cudaError_t e;
     const int n = vsweep_cols(c);
@@ -683,7 +716,7 @@ cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
         if ((e = launch_vsweep(c, n, g.mode == 1 ? 2 : 1)) != cudaSuccess) return e;
         mark();
         a.mx = -1;
-        if ((e = launch_dir_np(c, a, AGG_ACCUM)) != cudaSuccess) return e;
+        if ((e = launch_dir_np(c, a, g.mode == 1 ? AGG_ACCUM2 : AGG_ACCUM)) != cudaSuccess) return e;
         mark();
         if (n_launches) *n_launches = 3;
         return cudaSuccess;

@@ -14,6 +14,8 @@
 //     have the same length and every row of C is read as one contiguous span by neighbouring warps.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "b2s_internal.h"
 
 namespace {
@@ -27,19 +29,6 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void cp_async_wait_dyn(int n) // wait until at most n groups are pending (n is warp-uniform, 1..7)
-{
-    switch (n) {
-    case 1: cp_async_wait<1>(); break;
-    case 2: cp_async_wait<2>(); break;
-    case 3: cp_async_wait<3>(); break;
-    case 4: cp_async_wait<4>(); break;
-    case 5: cp_async_wait<5>(); break;
-    case 6: cp_async_wait<6>(); break;
-    default: cp_async_wait<7>(); break;
-    }
-}
-
 template <int NP> struct Stages { static constexpr int value = (NP <= 2) ? 16 : (NP == 3 ? 10 : 8); }; // x 3 sources x 8 warps <= 98 KB
 
 struct AggArgs {
@@ -530,74 +519,81 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
 
     int stage = 1 % R, pstage = R - 1; // stage of step t+1, stage that step t+R-1 is loaded into
     uint32_t pin = PSB, pout = 0;      // parity offsets of the slots read (step t-1) and written (step t)
+    // The row loop exists twice: warps on a CTA boundary (EDGE) carry the hand-over code, the others do not pay for it.
+    auto rows = [&](auto edge_tag) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
 #pragma unroll 1
-    for (int t = 0; t < H; t++) {
-        // ---- critical section: from the neighbours' row t-1 states to this column's row t states ------------------
-        // a warp signals even rows on its first mbarrier and odd rows on the second: a neighbour may run one row ahead, and
-        // with a single barrier two completed phases would look like none
-        const uint32_t mb_off = ((t - 1) & 1) * 8, par_in = ((t - 1) >> 1) & 1;
-        uint32_t T0[NP], T1[NP], L0[NP], L1[NP], L2[NP];
-        if (in_glob[0]) { // (only a one-column strip receives both diagonals from other CTAs)
-            if (t == 0) {
+        for (int t = 0; t < H; t++) {
+            // ---- critical section: from the neighbours' row t-1 states to this column's row t states --------------
+            // A warp signals even rows on its first mbarrier and odd rows on the second (a neighbour may run one row
+            // ahead; with a single barrier two completed phases would look like none).  At t = 0 the wait is for the
+            // phase before the first one, which counts as complete, and the slots hold the out-of-image state.
+            const uint32_t mb_off = ((t - 1) & 1) * 8, par_in = ((t - 1) >> 1) & 1;
+            uint32_t T0[NP], T1[NP], L0[NP], L1[NP], L2[NP];
+            if (EDGE && in_glob[0]) { // (only a one-column strip receives both diagonals from other CTAs)
+                if (t == 0) {
 #pragma unroll
-                for (int i = 0; i < NP; i++) T0[i] = padmask[i];
-            } else ho_read<NP>(in_g[0] + ((t - 1) & (HO_SLOTS - 1)) * DW, (((t - 1) >> 2) & 1) ? 0x80008000u : 0u, T0, a.err);
-        } else {
-            if (in_mb[0] && t != 0) mbar_wait(in_mb[0] + mb_off, par_in, a.err);
-            lds_s<NP>(in_s[0] + pin, T0);
-        }
-        if (polls) {
-            sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
-            if (out_glob[0]) ho_write<NP>(out_g[0] + (t & (HO_SLOTS - 1)) * DW, ((t >> 2) & 1) ? 0x80008000u : 0u, T0);
-            else sts_s<NP>(out_s[0] + pout, T0);
-            if (t == 0) {
-#pragma unroll
-                for (int i = 0; i < NP; i++) T1[i] = padmask[i];
+                    for (int i = 0; i < NP; i++) T0[i] = padmask[i];
+                } else ho_read<NP>(in_g[0] + ((t - 1) & (HO_SLOTS - 1)) * DW, (((t - 1) >> 2) & 1) ? 0x80008000u : 0u, T0, a.err);
             } else {
-#pragma unroll
-                for (int i = 0; i < NP; i++) T1[i] = Tpre[i]; // loaded at the end of the previous step
-                ho_read<NP>(in_g[1] + ((t - 1) & (HO_SLOTS - 1)) * DW, (((t - 1) >> 2) & 1) ? 0x80008000u : 0u, T1, a.err, true);
+                if (in_mb[0]) mbar_wait(in_mb[0] + mb_off, par_in, a.err);
+                lds_s<NP>(in_s[0] + pin, T0);
             }
-            sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
-        } else {
-            if (in_mb[1] && t != 0) mbar_wait(in_mb[1] + mb_off, par_in, a.err);
-            lds_s<NP>(in_s[1] + pin, T1);
-            sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
-            sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
-            if (out_glob[0]) ho_write<NP>(out_g[0] + (t & (HO_SLOTS - 1)) * DW, ((t >> 2) & 1) ? 0x80008000u : 0u, T0);
-            else sts_s<NP>(out_s[0] + pout, T0);
-        }
-        if (out_glob[1]) ho_write<NP>(out_g[1] + (t & (HO_SLOTS - 1)) * DW, ((t >> 2) & 1) ? 0x80008000u : 0u, T1);
-        else sts_s<NP>(out_s[1] + pout, T1);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(my_mb + (t & 1) * 8); // this column's row-t states are in their slots
-        // the neighbour CTA wrote the state this warp needs in the next step early in ITS step t: fetch it now
-        if (polls) ho_load<NP>(in_g[1] + (t & (HO_SLOTS - 1)) * DW, Tpre);
-        // ---- off the critical path: vertical path, sums, store, next row's C and S -----------------------------------
-        asm volatile("" : "+r"(Td[0]) : : "memory"); // keeps the compiler from hoisting the vertical path above the hand-over
-        sgm_step<NP, PAD>(Td, c, L2, padmask, P1v, P2mP1v, lane);
-        // saturating sums (L >= 0, so the order of the directions does not matter)
+            if (EDGE && polls) {
+                sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
+                if (out_glob[0]) ho_write<NP>(out_g[0] + (t & (HO_SLOTS - 1)) * DW, ((t >> 2) & 1) ? 0x80008000u : 0u, T0);
+                else sts_s<NP>(out_s[0] + pout, T0);
+                if (t == 0) {
 #pragma unroll
-        for (int i = 0; i < NP; i++) {
-            uint32_t v = __viaddmin_u16x2(L0[i], L1[i], BIG);
-            v = __viaddmin_u16x2(v, L2[i], BIG);
-            s[i] = acc ? __viaddmin_u16x2(s[i], v, BIG) : v;
+                    for (int i = 0; i < NP; i++) T1[i] = padmask[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NP; i++) T1[i] = Tpre[i]; // loaded at the end of the previous step
+                    ho_read<NP>(in_g[1] + ((t - 1) & (HO_SLOTS - 1)) * DW, (((t - 1) >> 2) & 1) ? 0x80008000u : 0u, T1, a.err, true);
+                }
+                sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
+            } else {
+                if (in_mb[1]) mbar_wait(in_mb[1] + mb_off, par_in, a.err);
+                lds_s<NP>(in_s[1] + pin, T1);
+                sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
+                sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
+                if (EDGE && out_glob[0]) ho_write<NP>(out_g[0] + (t & (HO_SLOTS - 1)) * DW, ((t >> 2) & 1) ? 0x80008000u : 0u, T0);
+                else sts_s<NP>(out_s[0] + pout, T0);
+            }
+            if (EDGE && out_glob[1]) ho_write<NP>(out_g[1] + (t & (HO_SLOTS - 1)) * DW, ((t >> 2) & 1) ? 0x80008000u : 0u, T1);
+            else sts_s<NP>(out_s[1] + pout, T1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(my_mb + (t & 1) * 8); // this column's row-t states are in their slots
+            // the neighbour CTA wrote the state this warp needs in the next step early in ITS step t: fetch it now
+            if (EDGE && polls) ho_load<NP>(in_g[1] + (t & (HO_SLOTS - 1)) * DW, Tpre);
+            // ---- off the critical path: vertical path, sums, store, next row's C and S -------------------------------
+            asm volatile("" : "+r"(Td[0]) : : "memory"); // keeps the compiler from hoisting the vertical path above the hand-over
+            sgm_step<NP, PAD>(Td, c, L2, padmask, P1v, P2mP1v, lane);
+            // saturating sums (L >= 0, so the order of the directions does not matter)
+#pragma unroll
+            for (int i = 0; i < NP; i++) {
+                uint32_t v = __viaddmin_u16x2(L0[i], L1[i], BIG);
+                v = __viaddmin_u16x2(v, L2[i], BIG);
+                s[i] = acc ? __viaddmin_u16x2(s[i], v, BIG) : v;
+            }
+            stcg_regs<NP>(sp, s);
+            sp += rs;
+            __syncwarp();
+            if (t + R - 1 < H) issue(pstage);
+            cp_async_commit();
+            cp_async_wait<R - 2>(); // row t+1 has landed
+            __syncwarp();
+            const uint32_t cur = cur0 + stage * (2 * CHB);
+            lds_s<NP>(cur, c);
+            if (acc) lds_s<NP>(cur + CHB, s);
+            pstage = pstage + 1 == R ? 0 : pstage + 1;
+            stage = stage + 1 == R ? 0 : stage + 1;
+            pin = pout;
+            pout ^= PSB;
         }
-        stcg_regs<NP>(sp, s);
-        sp += rs;
-        __syncwarp();
-        if (t + R - 1 < H) issue(pstage);
-        cp_async_commit();
-        cp_async_wait<R - 2>(); // row t+1 has landed
-        __syncwarp();
-        const uint32_t cur = cur0 + stage * (2 * CHB);
-        lds_s<NP>(cur, c);
-        if (acc) lds_s<NP>(cur + CHB, s);
-        pstage = pstage + 1 == R ? 0 : pstage + 1;
-        stage = stage + 1 == R ? 0 : stage + 1;
-        pin = pout;
-        pout ^= PSB;
-    }
+    };
+    if (in_glob[0] || in_glob[1] || out_glob[0] || out_glob[1]) rows(std::true_type{});
+    else rows(std::false_type{});
 }
 
 template <int NP, bool PAD, int JW, int R> cudaError_t launch_vsweep_t(b2s_ctx *c, const VsArgs &a, int G, size_t smem)

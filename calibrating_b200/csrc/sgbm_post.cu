@@ -119,7 +119,13 @@ __global__ void lr_median_kernel(const int16_t *__restrict__ raw, const unsigned
     out[(size_t)y * g.W + x] = (int16_t)v[4];
 }
 
-// ---- A.7b: cv2.filterSpeckles as connected-component labelling (union-find in global memory) -----------------
+// ---- A.7b: cv2.filterSpeckles as connected-component labelling ------------------------------------------------------
+// Components are 4-connected sets of valid pixels whose neighbouring values differ by at most maxDiff; a component of at
+// most maxSize pixels is replaced by newVal.  Labelling works on horizontal RUNS (maximal linked pixel sequences of a row):
+//   rows  : label of every pixel = index of its run's first pixel (one block-wide max-scan per row)
+//   merge : union-find over run starts for vertically linked pixels (skipped where the left pixel pair made the same union)
+//   count : the last pixel of every run adds the run length to its root's size (few atomics, compresses the path)
+//   apply : pixel -> run start -> root -> size test
 __device__ __forceinline__ int uf_find(int *lab, int a)
 {
     const volatile int *vl = lab; // other threads re-parent roots concurrently (atomicMin in uf_union)
@@ -139,37 +145,87 @@ __device__ __forceinline__ void uf_union(int *lab, int a, int b)
         a = old;
     }
 }
-__global__ void ccl_init_kernel(const int16_t *__restrict__ img, int *lab, int *sizes, size_t n, int newVal)
+__device__ __forceinline__ bool linked(int a, int b, int newVal, int maxDiff) { return a != newVal && b != newVal && abs(a - b) <= maxDiff; }
+
+constexpr int CCL_T = 256;
+__global__ void __launch_bounds__(CCL_T) ccl_rows_kernel(const int16_t *__restrict__ img, int *__restrict__ lab, int *__restrict__ sizes, int W,
+                                                         int newVal, int maxDiff)
 {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    lab[i] = img[i] == newVal ? -1 : (int)i;
-    sizes[i] = 0;
+    __shared__ int wmax[CCL_T / 32];
+    const int y = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int16_t *row = img + (size_t)y * W;
+    const int ppt = (W + CCL_T - 1) / CCL_T, x0 = tid * ppt, x1 = min(x0 + ppt, W);
+    // last run start inside this thread's segment
+    int last = -1, prev = x0 > 0 && x0 < W ? row[x0 - 1] : newVal;
+    for (int x = x0; x < x1; x++) {
+        int v = row[x];
+        if (!linked(v, prev, newVal, maxDiff)) last = x;
+        prev = v;
+    }
+    // exclusive max-scan of `last` over the threads of the block = run start carried into the segment
+    int inc = last;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = max(inc, t);
+    }
+    if (lane == 31) wmax[wid] = inc;
+    __syncthreads();
+    int carry = -1;
+    for (int k = 0; k < wid; k++) carry = max(carry, wmax[k]);
+    int exc = __shfl_up_sync(0xffffffffu, inc, 1);
+    carry = lane == 0 ? carry : max(carry, exc);
+    // labels
+    int start = carry;
+    prev = x0 > 0 && x0 < W ? row[x0 - 1] : newVal;
+    const int base = y * W;
+    for (int x = x0; x < x1; x++) {
+        int v = row[x];
+        if (!linked(v, prev, newVal, maxDiff)) start = x;
+        lab[base + x] = v == newVal ? -1 : base + start;
+        sizes[base + x] = 0;
+        prev = v;
+    }
 }
 __global__ void ccl_merge_kernel(const int16_t *__restrict__ img, int *lab, int H, int W, int newVal, int maxDiff)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y + 1;
+    if (x >= W || y >= H) return;
+    int i = y * W + x;
+    int v = img[i], u = img[i - W];
+    if (!linked(v, u, newVal, maxDiff)) return;
+    if (x > 0) {
+        int vl = img[i - 1], ul = img[i - W - 1];
+        if (linked(v, vl, newVal, maxDiff) && linked(u, ul, newVal, maxDiff) && linked(vl, ul, newVal, maxDiff)) return; // implied
+    }
+    uf_union(lab, lab[i], lab[i - W]); // (a run start's label is its parent, which is in the same set)
+}
+__global__ void ccl_count_kernel(const int16_t *__restrict__ img, int *lab, int *sizes, int H, int W, int newVal, int maxDiff)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     int i = y * W + x;
     int v = img[i];
     if (v == newVal) return;
-    if (x + 1 < W) { int q = img[i + 1]; if (q != newVal && abs(v - q) <= maxDiff) uf_union(lab, i, i + 1); }
-    if (y + 1 < H) { int q = img[i + W]; if (q != newVal && abs(v - q) <= maxDiff) uf_union(lab, i, i + W); }
-}
-__global__ void ccl_count_kernel(int *lab, int *sizes, size_t n)
-{
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || lab[i] < 0) return;
-    int r = uf_find(lab, (int)i);
-    atomicAdd(&sizes[r], 1);
+    if (x + 1 < W && linked(img[i + 1], v, newVal, maxDiff)) return; // not the last pixel of its run
+    const bool is_start = x == 0 || !linked(v, img[i - 1], newVal, maxDiff);
+    const int rs = is_start ? i : lab[i];
+    const int root = uf_find(lab, rs);
+    atomicAdd(&sizes[root], i - rs + 1);
+    if (root != rs) atomicMin(&lab[rs], root); // path compression for ccl_apply (only ever moves towards the root)
 }
 __global__ void ccl_apply_kernel(const int16_t *__restrict__ img, int *lab, const int *__restrict__ sizes, int16_t *__restrict__ out,
-                                 size_t n, int newVal, int maxSize)
+                                 int H, int W, int newVal, int maxDiff, int maxSize)
 {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    int i = y * W + x;
     int v = img[i];
-    if (lab[i] >= 0 && sizes[uf_find(lab, (int)i)] <= maxSize) v = newVal;
+    if (v != newVal) {
+        const bool is_start = x == 0 || !linked(v, img[i - 1], newVal, maxDiff);
+        const int rs = is_start ? i : lab[i];
+        if (sizes[uf_find(lab, rs)] <= maxSize) v = newVal;
+    }
     out[i] = (int16_t)v;
 }
 
@@ -221,11 +277,13 @@ cudaError_t launch_post(b2s_ctx *c, int16_t *d_out_disp16, float *d_out_disp)
     c->launches++;
     if (g.speckle_window > 0) {
         int *lab = c->labels.as<int>(), *sizes = c->sizes.as<int>();
-        ccl_init_kernel<<<nb, 256, 0, c->stream>>>(med, lab, sizes, n, g.invalid);
-        ccl_merge_kernel<<<g2, b2, 0, c->stream>>>(med, lab, g.H, g.W, g.invalid, 16 * g.speckle_range);
-        ccl_count_kernel<<<nb, 256, 0, c->stream>>>(lab, sizes, n);
-        ccl_apply_kernel<<<nb, 256, 0, c->stream>>>(med, lab, sizes, final16, n, g.invalid, g.speckle_window);
-        c->launches += 4;
+        const int md = 16 * g.speckle_range;
+        dim3 gm((g.W + 127) / 128, g.H > 1 ? g.H - 1 : 1);
+        ccl_rows_kernel<<<g.H, CCL_T, 0, c->stream>>>(med, lab, sizes, g.W, g.invalid, md);
+        if (g.H > 1) ccl_merge_kernel<<<gm, b2, 0, c->stream>>>(med, lab, g.H, g.W, g.invalid, md);
+        ccl_count_kernel<<<g2, b2, 0, c->stream>>>(med, lab, sizes, g.H, g.W, g.invalid, md);
+        ccl_apply_kernel<<<g2, b2, 0, c->stream>>>(med, lab, sizes, final16, g.H, g.W, g.invalid, md, g.speckle_window);
+        c->launches += g.H > 1 ? 4 : 3;
     }
     if (d_out_disp) {
         disp_to_float_kernel<<<nb, 256, 0, c->stream>>>(final16, d_out_disp, n, g.minD * 16);

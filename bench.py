@@ -9,8 +9,8 @@ A "step" = one batch of `--pairs-per-step` independent synthetic pairs per GPU (
 data-path collective: weak scaling).  `value` = whole-job pairs/s with the inputs already resident in HBM, timed with
 CUDA events on the engine's own streams, max over ranks.  `e2e` = the same metric through the public host API
 (`DisparityBatchEngine.compute_batch`, i.e. the plugin's batch call) with pinned HOST buffers, H2D and D2H inside the
-timed region.  `roofline` = the aggregation kernels (8 scan launches per pair) timed alone by CUDA events, algorithmic
-bytes 8 B/voxel.  `cpu_baseline` / `--impl reference` = the reference's own CPU arithmetic
+timed region.  `roofline` = the aggregation kernel group (horizontal +x scan, fused vertical sweep, horizontal -x scan: 3
+launches per pair) timed alone by CUDA events, algorithmic bytes 8 B/voxel per pair.  `cpu_baseline` / `--impl reference` = the reference's own CPU arithmetic
 (cv2.StereoSGBM, what calibrating/stereo_matching.py:63 executes) on the box's host cores.
 """
 import argparse
@@ -64,27 +64,45 @@ def cpu_round(pairs, threads):
 
 
 class ClockSampler:
+    """nvidia-smi polled in the background; samples are time-stamped on arrival so that only those taken while the GPU
+    was under load (warm-up + timed region, marked with begin()/end()) are summarised."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.p = None
+        self.p, self.rows, self.t0, self.t1 = None, [], None, None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
         except Exception:
-            pass
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), line))
+
+    def wait_first(self, timeout=10.0):
+        t = time.time()
+        while self.p and not self.rows and time.time() - t < timeout:
+            time.sleep(0.02)
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
         self.p.terminate()
-        try:
-            txt = self.p.communicate(timeout=5)[0]
-        except Exception:
-            txt = ""
         sm, mx, reasons = [], [], set()
-        for line in txt.strip().splitlines():
+        for ts, line in list(self.rows):
+            if self.t0 is not None and not (self.t0 <= ts <= (self.t1 or ts) + 0.05):
+                continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
@@ -172,10 +190,12 @@ def main():
             for h in eng.handles:
                 h.sync()
 
+    sampler = ClockSampler(local)
+    sampler.wait_first()
+    sampler.begin()  # clocks are sampled under load: warm-up + timed region
     for _ in range(Wm):
         step_dev(True)
     barrier()
-    sampler = ClockSampler(local)
     l0 = eng.launch_count()
     for h in eng.handles:
         h.event_record(0)
@@ -188,6 +208,7 @@ def main():
         h.sync()
     barrier()
     launches = eng.launch_count() - l0
+    sampler.end()
     clocks = sampler.stop()
     # parity guard: the timed outputs are the real thing (checked against cv2 in tests/; here a cheap sanity check)
     d0 = dout[0].cpu().numpy()
@@ -208,11 +229,13 @@ def main():
         eng.compute_batch(hp, out=hout)
     barrier()
     e2e_s = time.perf_counter() - t0
+    eng.matchers[0].compute(*pairs[0])  # one synchronous call for the per-stage CUDA-event times
     stage = eng.handles[0].timings()
 
     # ---- roofline: the aggregation kernels alone ---------------------------------------------------------------------
-    agg_ms = eng.handles[0].bench_aggregate(10)
-    n_dir = 8
+    agg_parts = eng.handles[0].bench_aggregate_parts(10)   # one CUDA-event interval per launch of the group
+    agg_ms = eng.handles[0].bench_aggregate(10)            # the group back to back
+    n_launch = len(agg_parts)
 
     if world > 1:
         t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
@@ -234,20 +257,27 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "agg_traffic.json")))["dram_bytes_per_launch"]
     except Exception:
         pass
-    achieved = AGG_BYTES_PER_PAIR / n_dir / (agg_ms / n_dir * 1e-3) / 1e9
+    achieved = AGG_BYTES_PER_PAIR / (agg_ms * 1e-3) / 1e9  # = (bytes per pair / launches) / (group time / launches)
+    names = ["agg_scan_kernel<INIT> (+x)", "agg_vsweep_kernel (6 of 8 directions)", "agg_scan_kernel<ACCUM2> (-x)"] if n_launch == 3 else \
+        ["agg_scan_kernel"] * n_launch
+    dirs = [1, 6, 1] if n_launch == 3 else [1] * n_launch
     out = {
         "metric": "stereo pairs/sec @1080p/128-disp SGM", "value": world * K * P / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
         "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "streams_per_gpu": S, "parallelism": "dp%d (pairs sharded, no collective)" % world,
-                   "l2": "working set per pair (C+S volumes, 0.99 GB) exceeds the 126 MB L2; %d distinct pairs rotate" % P},
+                   "l2": "working set per pair (C, S, S2 volumes, 1.49 GB) exceeds the 126 MB L2; %d distinct pairs rotate" % P},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": world * K * P / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": P * 2 * H * W * CN, "d2h_bytes_per_step": P * H * W * 4,
                 "api": "DisparityBatchEngine.compute_batch (host uint8 pairs -> host float32 disparity), wall clock between synchronisations"},
-        "roofline": {"bound": "hbm", "kernel": "agg_scan_kernel x%d (one launch per path direction)" % n_dir, "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "roofline": {"bound": "hbm", "kernel": "aggregation group: %d launches per pair (dominant: agg_vsweep_kernel)" % n_launch,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy), of measured" if peaks else "fallback 6650 GB/s, of fallback",
-                     "algorithmic_bytes_per_launch": AGG_BYTES_PER_PAIR // n_dir, "ms_per_launch": agg_ms / n_dir, "timed": "alone, CUDA events on the engine stream"},
+                     "algorithmic_bytes_per_launch": AGG_BYTES_PER_PAIR // n_launch, "ms_per_launch": agg_ms / n_launch,
+                     "launches": [{"kernel": nm, "ms": round(t, 4), "algorithmic_bytes": AGG_BYTES_PER_PAIR * d // sum(dirs),
+                                   "achieved_GBps": round(AGG_BYTES_PER_PAIR * d / sum(dirs) / (t * 1e-3) / 1e9, 1)}
+                                  for nm, t, d in zip(names, agg_parts, dirs)],
+                     "timed": "alone, CUDA events on the engine stream; canonical 8 B/voxel (SURVEY 8(d)), this schedule moves 22 B/voxel"},
         "stage_ms_last_pair": {k: round(v, 3) for k, v in stage.items() if k.endswith("_ms")},
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -61,6 +61,7 @@ SIGNATURES = {
     "b2s_disparity_to_depth": (c_int, [c_void_p, c_void_p, c_void_p]),
     "b2s_unrectify_depth": (c_int, [c_void_p, c_void_p, c_void_p]),
     "b2s_undistort_img": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "b2s_set_option": (c_int, [c_void_p, c_int, c_int]),
     "b2s_volume_dims": (c_int, [c_void_p] + [ctypes.POINTER(c_int)] * 4),
     "b2s_debug_fetch": (c_int, [c_void_p, c_int, c_void_p, c_size_t]),
     "b2s_timings": (c_int, [c_void_p, ctypes.POINTER(Timing)]),
@@ -138,6 +139,14 @@ class Handle:
         n = ctypes.c_longlong()
         self.call("b2s_launch_count", ctypes.byref(n))
         return n.value
+
+    def keep_volumes(self, on=True):
+        """With fuse_wta: make the last aggregation pass store S as well, so that fetch_volume(1) works."""
+        self.call("b2s_set_option", 1, int(bool(on)))
+
+    def fuse_wta(self, on=True):
+        """Fuse the winner-take-all step into the last aggregation pass (same results; see include/b2s.h)."""
+        self.call("b2s_set_option", 2, int(bool(on)))
 
     def volume_dims(self):
         v = [c_int() for _ in range(4)]

@@ -184,6 +184,7 @@ static int matcher_dev(b2s_ctx *c, const uint8_t *dl, const uint8_t *dr, int16_t
     CK(c, launch_cost_volume(c, dl, dr));
     if (timed) cudaEventRecord(c->ev[2], c->stream);
     int nl = 0;
+    CK(c, launch_wta_prepare(c));
     CK(c, launch_aggregate(c, &nl));
     c->timing.aggregate_launches = nl;
     if (timed) cudaEventRecord(c->ev[3], c->stream);
@@ -455,7 +456,11 @@ int b2s_debug_fetch(b2s_handle c, int which, void *dst, size_t bytes)
     const void *src;
     switch (which) {
     case B2S_FETCH_C: src = c->C.p; need = vol; break;
-    case B2S_FETCH_S: src = c->S.p; need = vol; break;
+    case B2S_FETCH_S:
+        if (c->wta_fused && !c->keep_volumes)
+            return fail(c, B2S_ESTATE, "the aggregated volume was not stored (winner-take-all is fused into the last scan); "
+                                       "call b2s_set_option(h, B2S_OPT_KEEP_VOLUMES, 1) before computing");
+        src = c->S.p; need = vol; break;
     case B2S_FETCH_RAW: src = c->raw.p; need = (size_t)g.H * g.W * 2; break;
     default: return fail(c, B2S_EINVAL, "b2s_debug_fetch: unknown selector %d", which);
     }
@@ -463,6 +468,16 @@ int b2s_debug_fetch(b2s_handle c, int which, void *dst, size_t bytes)
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
     return B2S_OK;
+}
+
+int b2s_set_option(b2s_handle c, int option, int value)
+{
+    if (!c) return B2S_EINVAL;
+    switch (option) {
+    case B2S_OPT_KEEP_VOLUMES: c->keep_volumes = value != 0; return B2S_OK;
+    case B2S_OPT_FUSE_WTA: c->fuse_wta = value != 0; return B2S_OK;
+    default: return fail(c, B2S_EINVAL, "b2s_set_option: unknown option %d", option);
+    }
 }
 
 int b2s_timings(b2s_handle c, b2s_timing *t)

@@ -14,6 +14,7 @@
 //     have the same length and every row of C is read as one contiguous span by neighbouring warps.
 #include <stdlib.h>
 
+#include <mutex>
 #include <type_traits>
 
 #include "b2s_internal.h"
@@ -38,6 +39,10 @@ struct AggArgs {
     int H, width1, D;
     int mx, my;
     int P1, P2;
+    // fused winner-take-all of the last scan (WTA != 0): see wta_pixel in b2s_internal.h
+    int16_t *raw;
+    unsigned *disp2key;
+    int W, minX1, minD, uniq;
 };
 
 template <int NP> __device__ __forceinline__ void store_regs(int16_t *dst, const uint32_t (&v)[NP])
@@ -51,7 +56,8 @@ template <int NP> __device__ __forceinline__ void store_regs(int16_t *dst, const
     }
 }
 
-template <int NP, bool PAD, int MODE>
+// WTA: 0 = store S; 1 = winner-take-all fused (A.5), S not stored; 2 = both (debug: S stays fetchable)
+template <int NP, bool PAD, int MODE, int WTA>
 __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
 {
     constexpr int CH = 128 * NP;                       // bytes of one pixel's d-chunk
@@ -162,41 +168,48 @@ __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
             Ln[i] = __vadd2(L[i], negmin) | padmask[i];
             out[i] = (MODE != AGG_INIT) ? __viaddmin_u16x2(sv[i], L[i], BIG) : L[i]; // saturating accumulate (L >= 0)
         }
-        store_regs<NP>(a.S + ((size_t)y * a.width1 + x) * Dp + lane * 2 * NP, out);
+        if (WTA != 1) store_regs<NP>(a.S + ((size_t)y * a.width1 + x) * Dp + lane * 2 * NP, out);
+        if (WTA != 0) {
+            // this step's stage has been consumed: it doubles as the exchange buffer for the sub-pixel neighbours
+            uint32_t *xch = (uint32_t *)(ring + (k % STAGES) * STAGE_BYTES);
+            wta_pixel<NP>(out, xch, lane, x, y, a.D, a.W, a.minX1, a.minD, a.uniq, a.raw, a.disp2key);
+        }
         advance(x, y);
     }
 }
 
-template <int NP, bool PAD, int MODE> cudaError_t launch_scan(b2s_ctx *c, const AggArgs &a)
+template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *c, const AggArgs &a)
 {
     constexpr int STAGE_BYTES = 128 * NP * (MODE == AGG_ACCUM2 ? 3 : (MODE == AGG_ACCUM ? 2 : 1));
     size_t smem = (size_t)WARPS * Stages<NP>::value * STAGE_BYTES;
     static bool configured = false; // per instantiation
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(agg_scan_kernel<NP, PAD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(agg_scan_kernel<NP, PAD, MODE, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     int nlines = a.my == 0 ? a.H : a.width1;
-    agg_scan_kernel<NP, PAD, MODE><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
+    agg_scan_kernel<NP, PAD, MODE, WTA><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
     c->launches++;
     return cudaGetLastError();
 }
 
-template <int NP, bool PAD> cudaError_t launch_dir(b2s_ctx *c, const AggArgs &a, int mode)
+template <int NP, bool PAD> cudaError_t launch_dir(b2s_ctx *c, const AggArgs &a, int mode, int wta)
 {
-    if (mode == AGG_ACCUM2) return launch_scan<NP, PAD, AGG_ACCUM2>(c, a);
-    return mode == AGG_INIT ? launch_scan<NP, PAD, AGG_INIT>(c, a) : launch_scan<NP, PAD, AGG_ACCUM>(c, a);
+    if (wta == 1) return mode == AGG_ACCUM2 ? launch_scan<NP, PAD, AGG_ACCUM2, 1>(c, a) : launch_scan<NP, PAD, AGG_ACCUM, 1>(c, a);
+    if (wta == 2) return mode == AGG_ACCUM2 ? launch_scan<NP, PAD, AGG_ACCUM2, 2>(c, a) : launch_scan<NP, PAD, AGG_ACCUM, 2>(c, a);
+    if (mode == AGG_ACCUM2) return launch_scan<NP, PAD, AGG_ACCUM2, 0>(c, a);
+    return mode == AGG_INIT ? launch_scan<NP, PAD, AGG_INIT, 0>(c, a) : launch_scan<NP, PAD, AGG_ACCUM, 0>(c, a);
 }
 
-cudaError_t launch_dir_np(b2s_ctx *c, const AggArgs &a, int mode)
+cudaError_t launch_dir_np(b2s_ctx *c, const AggArgs &a, int mode, int wta = 0)
 {
     const bool pad = c->g.D != c->g.Dp;
     switch (c->g.NP) {
-    case 1: return pad ? launch_dir<1, true>(c, a, mode) : launch_dir<1, false>(c, a, mode);
-    case 2: return pad ? launch_dir<2, true>(c, a, mode) : launch_dir<2, false>(c, a, mode);
-    case 3: return pad ? launch_dir<3, true>(c, a, mode) : launch_dir<3, false>(c, a, mode);
-    case 4: return pad ? launch_dir<4, true>(c, a, mode) : launch_dir<4, false>(c, a, mode);
+    case 1: return pad ? launch_dir<1, true>(c, a, mode, wta) : launch_dir<1, false>(c, a, mode, wta);
+    case 2: return pad ? launch_dir<2, true>(c, a, mode, wta) : launch_dir<2, false>(c, a, mode, wta);
+    case 3: return pad ? launch_dir<3, true>(c, a, mode, wta) : launch_dir<3, false>(c, a, mode, wta);
+    case 4: return pad ? launch_dir<4, true>(c, a, mode, wta) : launch_dir<4, false>(c, a, mode, wta);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -645,6 +658,15 @@ int vsweep_cols(const b2s_ctx *c)
     return n <= 32 ? n : 0;
 }
 
+// The strips of a sweep spin on each other, so all CTAs of a launch must become resident.  Two such launches from
+// different streams must not interleave their CTAs (each could hold SMs the other one needs): sweeps of one process
+// are chained per device with an event, which costs nothing because they cannot share the SMs anyway.
+struct SweepChain {
+    std::mutex mu;
+    cudaEvent_t ev[64] = {};
+};
+SweepChain g_chain;
+
 cudaError_t launch_vsweep(b2s_ctx *c, int n, int J)
 {
     const SgbmGeom &g = c->g;
@@ -664,13 +686,20 @@ cudaError_t launch_vsweep(b2s_ctx *c, int n, int J)
     a.err = (int *)((char *)c->agg_ho.p + ho_bytes);
     c->agg_err = a.err;
     const bool pad = g.D != g.Dp;
+    std::lock_guard<std::mutex> lock(g_chain.mu);
+    cudaEvent_t &ev = g_chain.ev[c->device & 63];
+    if (!ev) {
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    } else if ((e = cudaStreamWaitEvent(c->stream, ev, 0)) != cudaSuccess) return e;
     switch (g.NP) {
-    case 1: return pad ? launch_vsweep_j<1, true>(c, a, G, J) : launch_vsweep_j<1, false>(c, a, G, J);
-    case 2: return pad ? launch_vsweep_j<2, true>(c, a, G, J) : launch_vsweep_j<2, false>(c, a, G, J);
-    case 3: return pad ? launch_vsweep_j<3, true>(c, a, G, J) : launch_vsweep_j<3, false>(c, a, G, J);
-    case 4: return pad ? launch_vsweep_j<4, true>(c, a, G, J) : launch_vsweep_j<4, false>(c, a, G, J);
-    default: return cudaErrorInvalidValue;
+    case 1: e = pad ? launch_vsweep_j<1, true>(c, a, G, J) : launch_vsweep_j<1, false>(c, a, G, J); break;
+    case 2: e = pad ? launch_vsweep_j<2, true>(c, a, G, J) : launch_vsweep_j<2, false>(c, a, G, J); break;
+    case 3: e = pad ? launch_vsweep_j<3, true>(c, a, G, J) : launch_vsweep_j<3, false>(c, a, G, J); break;
+    case 4: e = pad ? launch_vsweep_j<4, true>(c, a, G, J) : launch_vsweep_j<4, false>(c, a, G, J); break;
+    default: e = cudaErrorInvalidValue;
     }
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(ev, c->stream);
 }
 
 } // namespace
@@ -703,7 +732,11 @@ cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
     a.S = c->S.as<int16_t>();
     a.S2 = c->S2.as<int16_t>();
     a.H = g.H; a.width1 = g.width1; a.D = g.D; a.P1 = g.P1; a.P2 = g.P2;
+    a.raw = c->raw.as<int16_t>();
+    a.disp2key = c->disp2key.as<unsigned>();
+    a.W = g.W; a.minX1 = g.minX1; a.minD = g.minD; a.uniq = g.uniq;
     cudaError_t e;
+    c->wta_fused = false;
     const int n = vsweep_cols(c);
     if (n > 0) {
         a.mx = 1; a.my = 0;
@@ -712,7 +745,13 @@ cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
         if ((e = launch_vsweep(c, n, g.mode == 1 ? 2 : 1)) != cudaSuccess) return e;
         mark();
         a.mx = -1;
-        if ((e = launch_dir_np(c, a, g.mode == 1 ? AGG_ACCUM2 : AGG_ACCUM)) != cudaSuccess) return e;
+        // B2S_OPT_FUSE_WTA: the last scan also does the winner-take-all (its lanes hold the final S of the pixel) and
+        // stores S only if the volumes are kept.  Off by default: the scan is a latency-bound sequential loop (7 warps
+        // per SM), and the ~60 extra dependent instructions per step cost more than the separate WTA kernel and the
+        // S round trip save (measured 0.86 ms vs 0.37 + 0.41 ms at 1080p/128).
+        const int wta = c->fuse_wta ? (c->keep_volumes ? 2 : 1) : 0;
+        if ((e = launch_dir_np(c, a, g.mode == 1 ? AGG_ACCUM2 : AGG_ACCUM, wta)) != cudaSuccess) return e;
+        c->wta_fused = wta != 0;
         mark();
         if (n_launches) *n_launches = 3;
         return cudaSuccess;

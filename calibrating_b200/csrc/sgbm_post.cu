@@ -241,13 +241,19 @@ __global__ void disp_to_float_kernel(const int16_t *__restrict__ d16, float *__r
 
 } // namespace
 
-cudaError_t launch_wta(b2s_ctx *c)
+cudaError_t launch_wta_prepare(b2s_ctx *c)
 {
     const SgbmGeom &g = c->g;
     size_t n = (size_t)g.H * g.W;
     fill_i16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->raw.as<int16_t>(), n, (int16_t)g.invalid);
-    cudaError_t e = cudaMemsetAsync(c->disp2key.p, 0xFF, (size_t)g.H * (g.W + 2) * sizeof(unsigned), c->stream);
-    if (e != cudaSuccess) return e;
+    c->launches++;
+    return cudaMemsetAsync(c->disp2key.p, 0xFF, (size_t)g.H * (g.W + 2) * sizeof(unsigned), c->stream);
+}
+
+cudaError_t launch_wta(b2s_ctx *c)
+{
+    if (c->wta_fused) return cudaSuccess; // the last aggregation scan already selected the winners (sgbm_agg.cu)
+    const SgbmGeom &g = c->g;
     size_t npix = (size_t)g.H * g.width1;
     size_t want = (npix + 7) / 8;
     unsigned blocks = (unsigned)(want < 148 * 8 * 4 ? want : 148 * 8 * 4);
@@ -261,7 +267,7 @@ cudaError_t launch_wta(b2s_ctx *c)
     case 4: wta_kernel<4><<<blocks, 256, 0, c->stream>>>(S, raw, keys, g); break;
     default: return cudaErrorInvalidValue;
     }
-    c->launches += 2;
+    c->launches++;
     return cudaGetLastError();
 }
 

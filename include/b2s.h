@@ -130,6 +130,12 @@ int b2s_undistort_img(b2s_handle h, const uint8_t *img1, int cn, uint8_t *out);
 #define B2S_FETCH_C 0    /* cost volume (H,width1,Dp) i16 */
 #define B2S_FETCH_S 1    /* aggregated volume (H,width1,Dp) i16 */
 #define B2S_FETCH_RAW 2  /* (H,W) i16 disparity before median/speckle */
+/* Options (all default 0).
+ * B2S_OPT_FUSE_WTA: fuse the winner-take-all step into the last aggregation pass; the aggregated volume S is then never
+ *   written unless B2S_OPT_KEEP_VOLUMES is also set (B2S_FETCH_S fails otherwise).  Results are identical either way. */
+#define B2S_OPT_KEEP_VOLUMES 1
+#define B2S_OPT_FUSE_WTA 2
+int b2s_set_option(b2s_handle h, int option, int value);
 int b2s_volume_dims(b2s_handle h, int *H, int *width1, int *D, int *Dp);
 int b2s_debug_fetch(b2s_handle h, int which, void *dst, size_t bytes);
 int b2s_timings(b2s_handle h, b2s_timing *t);      /* CUDA-event stage times of the last synchronous call */

@@ -47,6 +47,18 @@ def test_stage_parity_random(handle, seed):
     got = m.compute(l, r)
     assert np.array_equal(handle.fetch_volume(0), ref["C"]), "cost volume"
     assert np.array_equal(handle.fetch_volume(1), ref["S"]), "aggregated volume"
+    if seed % 2 == 0:  # the same through the fused winner-take-all (S not stored, then stored on request)
+        handle.fuse_wta(True)
+        try:
+            assert np.array_equal(m.compute(l, r), ref["disp"]), "winner-take-all fused into the last scan"
+            with pytest.raises(Exception, match="not stored"):
+                handle.fetch_volume(1)
+            handle.keep_volumes(True)
+            assert np.array_equal(m.compute(l, r), ref["disp"])
+            assert np.array_equal(handle.fetch_volume(1), ref["S"]), "aggregated volume kept by the fused pass"
+        finally:
+            handle.keep_volumes(False)
+            handle.fuse_wta(False)
     # (the device keeps the pre-L/R-check WTA map; the L/R check is fused into the median kernel's loads)
     assert np.array_equal(got, ref["disp"]), "WTA / uniqueness / subpixel / L-R check / median / speckle"
     f = m.compute_float(l, r)

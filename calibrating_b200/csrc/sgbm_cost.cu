@@ -41,64 +41,100 @@ __global__ void planes_kernel(const uint8_t *__restrict__ img, uchar4 *__restric
     }
 }
 
-// One CTA = one image row y and TX cost columns.  Phase 1: BT pixel cost for TX+2*SW2 columns into shared memory.
+// One CTA = one image row y and TX cost columns.
+// Phase 0: stage the BT operands of the tile in shared memory, already in the form phase 1 consumes:
+//   left  pixel  (column j, plane p): four packed int16x2 constants  (u+B, B-u, B-u1, u0+B), B = 256, both halves equal
+//   right pixels (plane p): v, v0, v1 as packed PAIRS of neighbouring pixels, indexed so that the pair of a lane's two
+//   disparities (d, d+1) is one aligned 32-bit word; two copies (even / odd alignment) cover both parities of the column.
+// Phase 1: a lane owns two adjacent disparities of one column.  With the bias B every difference of the
+//   Birchfield-Tomasi cost is positive, so packed int16x2 differences are plain 32-bit adds/subtracts (no borrow between
+//   the halves), the max(0, ., .) are VIMNMX3.S16x2 against the packed bias, and per plane the cost of two voxels is
+//   5 integer adds + 2 VIMNMX3 + 1 VIMNMX (+ shift/mask for the raw planes, whose cost is >> 2):
+//       c0 + B = max3((u+B) - v1, v0 + (B-u), B)      c1 + B = max3(v + (B-u1), (u0+B) - v, B)      cost + B = min(.,.)
+//   and (cost + B) >> 2 = B/4 + (cost >> 2) exactly, so the biases leave as one constant at the end.
 // Phase 2: horizontal box sum (window clamped in cost-volume coordinates) -> hs.
 constexpr int TX = 64;
 constexpr int COST_THREADS = 256;
+constexpr int BT_BIAS = 256;
 
 template <int CN>
 __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4 *__restrict__ PL, const uchar4 *__restrict__ PR,
                                                                     int16_t *__restrict__ hs, SgbmGeom g)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int NPL = 2 * CN;
+    constexpr int NPL = 2 * CN;
     const int y = blockIdx.y;
     const int x1_0 = blockIdx.x * TX;
     const int TXH = TX + 2 * g.SW2;
-    const int xlo = x1_0 - g.SW2;              // cost column of tile-local index 0
-    const int NR = TXH + g.D - 1;              // right-image columns needed
-    uchar4 *sL = (uchar4 *)smem;               // [NPL][TXH]
-    uchar4 *sR = sL + NPL * TXH;               // [NPL][NR]   index j <-> image column xr0 + j
-    int16_t *pix = (int16_t *)(sR + NPL * NR); // [TXH][Dp]
-    const int xr0 = xlo + g.minX1 - g.minD - (g.D - 1);
+    const int xlo = x1_0 - g.SW2;             // cost column of tile-local index 0
+    const int NR = TXH + g.D - 1;             // right-image columns needed
+    const int NRP = NR / 2 + 2;               // packed pairs per copy
+    const int Dp = g.Dp, DW = Dp / 2;         // 32-bit words per column of pix
+    uint4 *sL = (uint4 *)smem;                // [NPL][TXH]
+    uint32_t *sR = (uint32_t *)(sL + NPL * TXH); // [NPL][3 (v, v0, v1)][2 copies][NRP]
+    uint32_t *pixw = sR + NPL * 3 * 2 * NRP;  // [TXH][DW] packed int16x2
+    // right pixel of reversed index m (m grows with d): image column xr(m) = xrmax - m
+    const int xrmax = xlo + g.minX1 - g.minD + (TXH - 1);
 
     for (int i = threadIdx.x; i < NPL * TXH; i += COST_THREADS) {
         int p = i / TXH, j = i % TXH;
         int x = clampi(xlo + j + g.minX1, 0, g.W - 1);
-        sL[i] = PL[((size_t)y * NPL + p) * g.W + x];
+        uchar4 L = PL[((size_t)y * NPL + p) * g.W + x];
+        uint32_t u = L.x, u0 = L.y, u1 = L.z;
+        sL[i] = make_uint4((u + BT_BIAS) * 0x10001u, (BT_BIAS - u) * 0x10001u, (BT_BIAS - u1) * 0x10001u, (u0 + BT_BIAS) * 0x10001u);
     }
-    for (int i = threadIdx.x; i < NPL * NR; i += COST_THREADS) {
-        int p = i / NR, j = i % NR;
-        int x = clampi(xr0 + j, 0, g.W - 1);
-        sR[i] = PR[((size_t)y * NPL + p) * g.W + x];
+    for (int i = threadIdx.x; i < NPL * 2 * NRP; i += COST_THREADS) {
+        int p = i / (2 * NRP), r = i % (2 * NRP), cp = r / NRP, wd = r % NRP;
+        int m0 = 2 * wd + cp; // copy 0: pairs (2w, 2w+1); copy 1: pairs (2w+1, 2w+2)
+        uchar4 a = PR[((size_t)y * NPL + p) * g.W + clampi(xrmax - m0, 0, g.W - 1)];
+        uchar4 b = PR[((size_t)y * NPL + p) * g.W + clampi(xrmax - m0 - 1, 0, g.W - 1)];
+        uint32_t *dst = sR + (size_t)p * 3 * 2 * NRP + cp * NRP + wd;
+        dst[0] = a.x | ((uint32_t)b.x << 16);
+        dst[2 * NRP] = a.y | ((uint32_t)b.y << 16);
+        dst[4 * NRP] = a.z | ((uint32_t)b.z << 16);
     }
     __syncthreads();
 
-    // phase 1: thread -> (column j, disparity d); consecutive threads = consecutive d
-    const int Dp = g.Dp;
-    for (int i = threadIdx.x; i < TXH * Dp; i += COST_THREADS) {
-        int j = i / Dp, d = i % Dp;
-        int x1 = xlo + j;
-        int cost = 0;
-        if (d < g.D && x1 >= 0 && x1 < g.width1) {
-            int jr = j + (g.D - 1) - d; // image column (x1+minX1) - (d+minD), relative to xr0
+    // phase 1: warp -> column j, lane -> disparity pairs d0 = 2*(lane + 32*i)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t Bp = BT_BIAS * 0x10001u, unbias = (uint32_t)(CN * (BT_BIAS + BT_BIAS / 4)) * 0x10001u;
+    for (int j = wid; j < TXH; j += COST_THREADS / 32) {
+        const int x1 = xlo + j;
+        uint32_t *out = pixw + j * DW;
+        if (x1 < 0 || x1 >= g.width1) {
+            for (int q = lane; q < DW; q += 32) out[q] = 0;
+            continue;
+        }
+        uint4 Lc[NPL];
+#pragma unroll
+        for (int p = 0; p < NPL; p++) Lc[p] = sL[p * TXH + j];
+        const int mj = TXH - 1 - j; // reversed right index of d = 0
+        const uint32_t *rbase = sR + (mj & 1) * NRP + (mj >> 1);
+        for (int q = lane; q < DW; q += 32) { // d0 = 2q
+            if (2 * q >= g.D) { // padded d-lanes are zero in C
+                out[q] = 0;
+                continue;
+            }
+            uint32_t acc = 0;
 #pragma unroll
             for (int p = 0; p < NPL; p++) {
-                uchar4 L = sL[p * TXH + j];
-                uchar4 R = sR[p * NR + jr];
-                int u = L.x, u0 = L.y, u1 = L.z, v = R.x, v0 = R.y, v1 = R.z;
-                int c0 = max(0, max(u - v1, v0 - u));
-                int c1 = max(0, max(v - u1, u0 - v));
-                cost += min(c0, c1) >> (p < CN ? 0 : 2);
+                const uint32_t *rp = rbase + (size_t)p * 3 * 2 * NRP + q;
+                const uint32_t V = rp[0], V0 = rp[2 * NRP], V1 = rp[4 * NRP];
+                uint32_t c0 = __vimax3_s16x2(Lc[p].x - V1, V0 + Lc[p].y, Bp);
+                uint32_t c1 = __vimax3_s16x2(V + Lc[p].z, Lc[p].w - V, Bp);
+                uint32_t c = __vmins2(c0, c1);
+                if (p >= CN) c = (c >> 2) & 0x007F007Fu;
+                acc += c;
             }
+            acc -= unbias;
+            if (2 * q + 1 >= g.D) acc &= 0x0000FFFFu;
+            out[q] = acc;
         }
-        pix[i] = (int16_t)cost;
     }
     __syncthreads();
 
     // phase 2: thread -> (segment of 16 columns, packed d pair); sliding window with wrap arithmetic
-    const int DW = Dp / 2; // 32-bit words per column
-    const uint32_t *pw = (const uint32_t *)pix;
+    const uint32_t *pw = pixw;
     const int SEG = 16;
     for (int i = threadIdx.x; i < (TX / SEG) * DW; i += COST_THREADS) {
         int seg = i / DW, w = i % DW;
@@ -155,8 +191,8 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
         planes_kernel<1><<<pg, pb, 0, c->stream>>>(d_left, PL, g.H, g.W, g.ftzero);
         planes_kernel<1><<<pg, pb, 0, c->stream>>>(d_right, PR, g.H, g.W, g.ftzero);
     }
-    const int TXH = TX + 2 * g.SW2, NR = TXH + g.D - 1;
-    size_t smem = (size_t)NPL * (TXH + NR) * sizeof(uchar4) + (size_t)TXH * g.Dp * sizeof(int16_t);
+    const int TXH = TX + 2 * g.SW2, NR = TXH + g.D - 1, NRP = NR / 2 + 2;
+    size_t smem = (size_t)NPL * TXH * sizeof(uint4) + (size_t)NPL * 3 * 2 * NRP * sizeof(uint32_t) + (size_t)TXH * g.Dp * sizeof(int16_t);
     dim3 cg((g.width1 + TX - 1) / TX, g.H);
     int16_t *hs = c->S.as<int16_t>(); // S is free until aggregation starts
     cudaError_t e;

@@ -160,6 +160,8 @@ static int make_geom(b2s_ctx *c, int H, int W, int cn)
     g.mode = p.mode;
     if (W - g.maxD <= g.SW2) return fail(c, B2S_ESIZE, "input images are too small for your window size and max disparity");
     if (g.ftzero > 127) return fail(c, B2S_EINVAL, "preFilterCap %d too large", p.pre_filter_cap);
+    if ((64 + 2 * g.SW2 + g.D - 1) / 2 + 2 > 168) // shared-memory tile of the cost kernel (sgbm_cost.cu: TX, NRP)
+        return fail(c, B2S_EINVAL, "blockSize %d is too large for numDisparities %d (supported: blockSize + numDisparities <= 269)", bs, g.D);
     c->g = g;
     size_t npx = (size_t)H * W, vol = (size_t)H * g.width1 * g.Dp * sizeof(int16_t);
     CK(c, c->planesL.ensure(npx * 2 * cn * 4));

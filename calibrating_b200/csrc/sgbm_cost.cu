@@ -56,6 +56,7 @@ __global__ void planes_kernel(const uint8_t *__restrict__ img, uchar4 *__restric
 constexpr int TX = 64;
 constexpr int COST_THREADS = 256;
 constexpr int BT_BIAS = 256;
+constexpr int NRP = (TX + 2 * 5 + 256) / 2 + 3; // packed right-pixel pairs per copy: compile-time so that plane offsets are immediates (D <= 256, SW2 <= 5)
 
 template <int CN>
 __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4 *__restrict__ PL, const uchar4 *__restrict__ PR,
@@ -67,8 +68,6 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
     const int x1_0 = blockIdx.x * TX;
     const int TXH = TX + 2 * g.SW2;
     const int xlo = x1_0 - g.SW2;             // cost column of tile-local index 0
-    const int NR = TXH + g.D - 1;             // right-image columns needed
-    const int NRP = NR / 2 + 2;               // packed pairs per copy
     const int Dp = g.Dp, DW = Dp / 2;         // 32-bit words per column of pix
     uint4 *sL = (uint4 *)smem;                // [NPL][TXH]
     uint32_t *sR = (uint32_t *)(sL + NPL * TXH); // [NPL][3 (v, v0, v1)][2 copies][NRP]
@@ -83,8 +82,9 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
         uint32_t u = L.x, u0 = L.y, u1 = L.z;
         sL[i] = make_uint4((u + BT_BIAS) * 0x10001u, (BT_BIAS - u) * 0x10001u, (BT_BIAS - u1) * 0x10001u, (u0 + BT_BIAS) * 0x10001u);
     }
-    for (int i = threadIdx.x; i < NPL * 2 * NRP; i += COST_THREADS) {
-        int p = i / (2 * NRP), r = i % (2 * NRP), cp = r / NRP, wd = r % NRP;
+    const int nrp = (TXH + g.D - 1) / 2 + 2; // pairs actually read by phase 1 (<= NRP, checked by the launcher)
+    for (int i = threadIdx.x; i < NPL * 2 * nrp; i += COST_THREADS) {
+        int p = i / (2 * nrp), r = i % (2 * nrp), cp = r / nrp, wd = r % nrp;
         int m0 = 2 * wd + cp; // copy 0: pairs (2w, 2w+1); copy 1: pairs (2w+1, 2w+2)
         uchar4 a = PR[((size_t)y * NPL + p) * g.W + clampi(xrmax - m0, 0, g.W - 1)];
         uchar4 b = PR[((size_t)y * NPL + p) * g.W + clampi(xrmax - m0 - 1, 0, g.W - 1)];
@@ -191,7 +191,8 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
         planes_kernel<1><<<pg, pb, 0, c->stream>>>(d_left, PL, g.H, g.W, g.ftzero);
         planes_kernel<1><<<pg, pb, 0, c->stream>>>(d_right, PR, g.H, g.W, g.ftzero);
     }
-    const int TXH = TX + 2 * g.SW2, NR = TXH + g.D - 1, NRP = NR / 2 + 2;
+    const int TXH = TX + 2 * g.SW2;
+    if ((TXH + g.D - 1) / 2 + 2 > NRP) return cudaErrorInvalidValue; // (b2s_api.cu rejects such block sizes with a message)
     size_t smem = (size_t)NPL * TXH * sizeof(uint4) + (size_t)NPL * 3 * 2 * NRP * sizeof(uint32_t) + (size_t)TXH * g.Dp * sizeof(int16_t);
     dim3 cg((g.width1 + TX - 1) / TX, g.H);
     int16_t *hs = c->S.as<int16_t>(); // S is free until aggregation starts

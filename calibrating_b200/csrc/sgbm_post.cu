@@ -13,61 +13,77 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v,
 // cv2 visits x1 from width1-1 down to 0 and keeps, per right-image column x2, the candidate with the smallest minS
 // (strict '>' => among equal costs the largest x1 wins).  That order-dependent rule is an atomicMin on the key
 // (minS << 16) | (0xFFFF - x1).
+constexpr int WTA_CHUNK = 32;
 template <int NP>
 __global__ void __launch_bounds__(256) wta_kernel(const int16_t *__restrict__ S, int16_t *__restrict__ raw,
                                                   unsigned *__restrict__ disp2key, SgbmGeom g)
 {
-    const int lane = threadIdx.x & 31;
-    const size_t npix = (size_t)g.H * g.width1;
-    const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    // a warp walks WTA_CHUNK consecutive pixels of one row (no index divisions); blockIdx.y = row
+    const int lane = threadIdx.x & 31, y = blockIdx.y;
+    const int xb = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * WTA_CHUNK, xe = min(xb + WTA_CHUNK, g.width1);
+    if (xb >= xe) return;
     const int Dp = 64 * NP;
-    for (size_t pix = warp0; pix < npix; pix += nwarps) {
-        const int y = (int)(pix / g.width1), x = (int)(pix % g.width1);
-        const int16_t *Sp = S + pix * Dp;
-        uint32_t v[NP];
-        if constexpr (NP == 1) v[0] = *(const uint32_t *)(Sp + lane * 2);
-        else if constexpr (NP == 2) { uint2 t = *(const uint2 *)(Sp + lane * 4); v[0] = t.x; v[1] = t.y; }
-        else if constexpr (NP == 4) { uint4 t = *(const uint4 *)(Sp + lane * 8); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    const int16_t *Srow = S + (size_t)y * g.width1 * Dp;
+    auto load_px = [&](int x, uint32_t (&v)[NP]) {
+        const int16_t *Sp = Srow + (size_t)x * Dp;
+        if constexpr (NP == 1) v[0] = __ldcs((const uint32_t *)(Sp + lane * 2));
+        else if constexpr (NP == 2) { uint2 t = __ldcs((const uint2 *)(Sp + lane * 4)); v[0] = t.x; v[1] = t.y; }
+        else if constexpr (NP == 4) { uint4 t = __ldcs((const uint4 *)(Sp + lane * 8)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
         else {
 #pragma unroll
-            for (int i = 0; i < NP; i++) v[i] = ((const uint32_t *)(Sp + lane * 2 * NP))[i];
+            for (int i = 0; i < NP; i++) v[i] = __ldcs((const uint32_t *)(Sp + lane * 2 * NP) + i);
         }
-        int sv[2 * NP];
-        unsigned key = 0xFFFFFFFFu;
+    };
+    // three pixels in flight per warp: the body is one dependent chain per pixel, and with a single 256-byte load
+    // outstanding per warp the kernel would be bound by DRAM latency, not bandwidth
+    uint32_t buf[3][NP];
 #pragma unroll
-        for (int i = 0; i < NP; i++) {
-            sv[2 * i] = (int)(short)(v[i] & 0xffffu);
-            sv[2 * i + 1] = ((int)v[i]) >> 16;
-        }
+    for (int u = 0; u < 2; u++)
+        if (xb + u < xe) load_px(xb + u, buf[u]);
+    const int thr_mul = 100 - g.uniq;
+    for (int base = xb; base < xe; base += 3) {
 #pragma unroll
-        for (int j = 0; j < 2 * NP; j++) {
-            int d = lane * 2 * NP + j;
-            if (d < g.D) key = min(key, ((unsigned)(sv[j] & 0xffff) << 16) | (unsigned)d);
-        }
-        key = __reduce_min_sync(0xffffffffu, key);
-        const int minS = (int)(key >> 16);
-        int best = (int)(key & 0xffffu);
-        if (minS >= 32767) best = -1; // cv2: strict '<' against MAX_COST never fires
-        bool bad = false;
+        for (int u = 0; u < 3; u++) {
+            const int x = base + u;
+            if (x >= xe) break;
+            if (x + 2 < xe) load_px(x + 2, buf[(u + 2) % 3]);
+            const int16_t *Sp = Srow + (size_t)x * Dp;
+            int sv[2 * NP];
+            unsigned key = 0xFFFFFFFFu;
 #pragma unroll
-        for (int j = 0; j < 2 * NP; j++) {
-            int d = lane * 2 * NP + j;
-            if (d < g.D && sv[j] * (100 - g.uniq) < minS * 100 && abs(best - d) > 1) bad = true;
-        }
-        if (__any_sync(0xffffffffu, bad)) continue;
-        if (lane == 0) {
-            int d = best;
-            int x2 = x + g.minX1 - d - g.minD;
-            if (minS < 32767 && x2 >= 0 && x2 < g.W + 2)
-                atomicMin(&disp2key[(size_t)y * (g.W + 2) + x2], ((unsigned)minS << 16) | (unsigned)(0xFFFF - x));
-            if (0 < d && d < g.D - 1) {
-                int sm = Sp[d - 1], sp = Sp[d + 1], s0 = Sp[d];
-                int den2 = max(sm + sp - 2 * s0, 1);
-                d = d * 16 + ((sm - sp) * 16 + den2) / (den2 * 2);
-            } else
-                d *= 16;
-            raw[(size_t)y * g.W + x + g.minX1] = (int16_t)(d + g.minD * 16);
+            for (int i = 0; i < NP; i++) {
+                sv[2 * i] = (int)(short)(buf[u][i] & 0xffffu);
+                sv[2 * i + 1] = ((int)buf[u][i]) >> 16;
+            }
+#pragma unroll
+            for (int j = 0; j < 2 * NP; j++) {
+                int d = lane * 2 * NP + j;
+                if (d < g.D) key = min(key, ((unsigned)(sv[j] & 0xffff) << 16) | (unsigned)d);
+            }
+            key = __reduce_min_sync(0xffffffffu, key);
+            const int minS = (int)(key >> 16);
+            int best = (int)(key & 0xffffu);
+            if (minS >= 32767) best = -1; // cv2: strict '<' against MAX_COST never fires
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < 2 * NP; j++) {
+                int d = lane * 2 * NP + j;
+                if (d < g.D && sv[j] * thr_mul < minS * 100 && abs(best - d) > 1) bad = true;
+            }
+            if (__any_sync(0xffffffffu, bad)) continue;
+            if (lane == 0) {
+                int d = best;
+                int x2 = x + g.minX1 - d - g.minD;
+                if (minS < 32767 && x2 >= 0 && x2 < g.W + 2)
+                    atomicMin(&disp2key[(size_t)y * (g.W + 2) + x2], ((unsigned)minS << 16) | (unsigned)(0xFFFF - x));
+                if (0 < d && d < g.D - 1) {
+                    int sm = Sp[d - 1], sp = Sp[d + 1], s0 = Sp[d];
+                    int den2 = max(sm + sp - 2 * s0, 1);
+                    d = d * 16 + ((sm - sp) * 16 + den2) / (den2 * 2);
+                } else
+                    d *= 16;
+                raw[(size_t)y * g.W + x + g.minX1] = (int16_t)(d + g.minD * 16);
+            }
         }
     }
 }
@@ -254,9 +270,7 @@ cudaError_t launch_wta(b2s_ctx *c)
 {
     if (c->wta_fused) return cudaSuccess; // the last aggregation scan already selected the winners (sgbm_agg.cu)
     const SgbmGeom &g = c->g;
-    size_t npix = (size_t)g.H * g.width1;
-    size_t want = (npix + 7) / 8;
-    unsigned blocks = (unsigned)(want < 148 * 8 * 4 ? want : 148 * 8 * 4);
+    dim3 blocks((g.width1 + 8 * WTA_CHUNK - 1) / (8 * WTA_CHUNK), g.H);
     const int16_t *S = c->S.as<int16_t>();
     int16_t *raw = c->raw.as<int16_t>();
     unsigned *keys = c->disp2key.as<unsigned>();

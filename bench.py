@@ -237,10 +237,29 @@ def main():
     agg_ms = eng.handles[0].bench_aggregate(10)            # the group back to back
     n_launch = len(agg_parts)
 
+    coll = None
     if world > 1:
-        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+        # the two collectives of the sharded path (calibrating_b200/sharded.py), timed on the device, max over ranks:
+        # one broadcast of a 1080p rig block (maps + mask, ~100 MB) and one all-gather of a step's disparities
+        blk = torch.empty(2 * 4 * 4 * H * W + 2 * 4 * H * W + H * W * 7, dtype=torch.uint8, device="cuda")
+        gat = torch.empty((world * P, H, W), dtype=torch.int16, device="cuda")
+        loc = torch.stack(dout)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        for it in range(3):  # two warm-ups, the third is reported
+            barrier()
+            ev[0].record()
+            dist.broadcast(blk, src=0)
+            ev[1].record()
+            dist.all_gather_into_tensor(gat, loc)
+            ev[2].record()
+            torch.cuda.synchronize()
+        coll = [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])]
+        assert torch.equal(gat[rank * P:(rank + 1) * P], loc)
+        t = torch.tensor([ms, e2e_s] + coll, dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = t.tolist()
+        ms, e2e_s, coll[0], coll[1] = t.tolist()
+        coll = {"rig_broadcast_ms": coll[0], "rig_broadcast_bytes": blk.numel(), "disparity_allgather_ms_per_step": coll[1],
+                "disparity_allgather_bytes_per_rank": loc.numel() * 2, "note": "outside the timed region: once per rig / once per batch"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -280,6 +299,8 @@ def main():
                      "timed": "alone, CUDA events on the engine stream; canonical 8 B/voxel (SURVEY 8(d)), this schedule moves 22 B/voxel"},
         "stage_ms_last_pair": {k: round(v, 3) for k, v in stage.items() if k.endswith("_ms")},
     }
+    if coll:
+        out["collectives"] = coll
     if world == 1 and not args.no_cpu_baseline:
         import cv2
         T = host_threads()

@@ -222,12 +222,12 @@ static int compute_disparity_host(b2s_ctx *c, const uint8_t *left, const uint8_t
     CK(c, c->right.ensure(nb));
     long long l0 = c->launches;
     cudaEventRecord(c->ev[0], c->stream);
-    CK(c, cudaMemcpyAsync(c->left.p, left, nb, cudaMemcpyHostToDevice, c->stream));
-    CK(c, cudaMemcpyAsync(c->right.p, right, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->left.p, left, nb, cudaMemcpyDefault, c->stream));
+    CK(c, cudaMemcpyAsync(c->right.p, right, nb, cudaMemcpyDefault, c->stream));
     rc = matcher_dev(c, c->left.as<uint8_t>(), c->right.as<uint8_t>(), c->disp16.as<int16_t>(), outf ? c->dispf.as<float>() : nullptr, true);
     if (rc) return rc;
-    if (out16) CK(c, cudaMemcpyAsync(out16, c->disp16.p, npx * 2, cudaMemcpyDeviceToHost, c->stream));
-    if (outf) CK(c, cudaMemcpyAsync(outf, c->dispf.p, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out16) CK(c, cudaMemcpyAsync(out16, c->disp16.p, npx * 2, cudaMemcpyDefault, c->stream));
+    if (outf) CK(c, cudaMemcpyAsync(outf, c->dispf.p, npx * 4, cudaMemcpyDefault, c->stream));
     c->timing.total_launches = (int)(c->launches - l0);
     if (sync) {
         CK(c, cudaStreamSynchronize(c->stream));
@@ -274,7 +274,7 @@ int b2s_set_rig(b2s_handle c, const b2s_rig *r)
     for (auto &u : ups) {
         if (!u.src) continue;
         CK(c, u.b->ensure(u.bytes));
-        CK(c, cudaMemcpyAsync(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaMemcpyAsync(u.b->p, u.src, u.bytes, cudaMemcpyDefault, c->stream));
     }
     CK(c, cudaStreamSynchronize(c->stream));
     c->rW = r->W; c->rH = r->H; c->rW1 = r->W1; c->rH1 = r->H1; c->rW2 = r->W2; c->rH2 = r->H2;
@@ -297,8 +297,8 @@ static int rectify_dev(b2s_ctx *c, const uint8_t *img1, const uint8_t *img2, int
     CK(c, c->img2.ensure(n2));
     CK(c, c->rect1.ensure(n));
     CK(c, c->rect2.ensure(n));
-    CK(c, cudaMemcpyAsync(c->img1.p, img1, n1, cudaMemcpyHostToDevice, c->stream));
-    CK(c, cudaMemcpyAsync(c->img2.p, img2, n2, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->img1.p, img1, n1, cudaMemcpyDefault, c->stream));
+    CK(c, cudaMemcpyAsync(c->img2.p, img2, n2, cudaMemcpyDefault, c->stream));
     CK(c, launch_remap_u8(c, c->img1.as<uint8_t>(), c->rH1, c->rW1, cn, c->map1x.as<float>(), c->map1y.as<float>(), c->rH, c->rW, 0,
                           c->r_interp, c->rect1.as<uint8_t>()));
     CK(c, launch_remap_u8(c, c->img2.as<uint8_t>(), c->rH2, c->rW2, cn, c->map2x.as<float>(), c->map2y.as<float>(), c->rH, c->rW,
@@ -318,10 +318,10 @@ static int depth_tail(b2s_ctx *c, const float *d_disp, int add_min, const uint8_
         CK(c, launch_undistort_u8(c, d_img1, c->rH1, c->rW1, cn, c->und_xy.as<int16_t>(), c->und_fxy.as<uint16_t>(), c->und1.as<uint8_t>()));
     }
     cudaEventRecord(c->ev[6], c->stream);
-    if (o->disparity) CK(c, cudaMemcpyAsync(o->disparity, c->dispfinal.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (o->rectify_depth) CK(c, cudaMemcpyAsync(o->rectify_depth, c->rdepth.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (want_unrectify && o->unrectify_depth) CK(c, cudaMemcpyAsync(o->unrectify_depth, c->udepth.p, n1 * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (und) CK(c, cudaMemcpyAsync(o->undistort_img1, c->und1.p, n1 * cn, cudaMemcpyDeviceToHost, c->stream));
+    if (o->disparity) CK(c, cudaMemcpyAsync(o->disparity, c->dispfinal.p, n * 4, cudaMemcpyDefault, c->stream));
+    if (o->rectify_depth) CK(c, cudaMemcpyAsync(o->rectify_depth, c->rdepth.p, n * 8, cudaMemcpyDefault, c->stream));
+    if (want_unrectify && o->unrectify_depth) CK(c, cudaMemcpyAsync(o->unrectify_depth, c->udepth.p, n1 * 8, cudaMemcpyDefault, c->stream));
+    if (und) CK(c, cudaMemcpyAsync(o->undistort_img1, c->und1.p, n1 * cn, cudaMemcpyDefault, c->stream));
     return B2S_OK;
 }
 
@@ -338,9 +338,9 @@ static int get_depth_impl(b2s_ctx *c, const uint8_t *img1, const uint8_t *img2, 
     if ((rc = matcher_dev(c, c->rect1.as<uint8_t>(), c->rect2.as<uint8_t>(), c->disp16.as<int16_t>(), c->dispf.as<float>(), true))) return rc;
     if ((rc = depth_tail(c, c->dispf.as<float>(), 1, c->img1.as<uint8_t>(), cn, want_unrectify, o))) return rc;
     size_t n = (size_t)c->rW * c->rH;
-    if (o->rectify_img1) CK(c, cudaMemcpyAsync(o->rectify_img1, c->rect1.p, n * cn, cudaMemcpyDeviceToHost, c->stream));
-    if (o->rectify_img2) CK(c, cudaMemcpyAsync(o->rectify_img2, c->rect2.p, n * cn, cudaMemcpyDeviceToHost, c->stream));
-    if (o->disp16) CK(c, cudaMemcpyAsync(o->disp16, c->disp16.p, n * 2, cudaMemcpyDeviceToHost, c->stream));
+    if (o->rectify_img1) CK(c, cudaMemcpyAsync(o->rectify_img1, c->rect1.p, n * cn, cudaMemcpyDefault, c->stream));
+    if (o->rectify_img2) CK(c, cudaMemcpyAsync(o->rectify_img2, c->rect2.p, n * cn, cudaMemcpyDefault, c->stream));
+    if (o->disp16) CK(c, cudaMemcpyAsync(o->disp16, c->disp16.p, n * 2, cudaMemcpyDefault, c->stream));
     c->timing.total_launches = (int)(c->launches - l0);
     if (sync) {
         CK(c, cudaStreamSynchronize(c->stream));
@@ -361,8 +361,8 @@ int b2s_rectify(b2s_handle c, const uint8_t *img1, const uint8_t *img2, int cn, 
     int rc = rectify_dev(c, img1, img2, cn);
     if (rc) return rc;
     size_t n = (size_t)c->rW * c->rH * cn;
-    if (out1) CK(c, cudaMemcpyAsync(out1, c->rect1.p, n, cudaMemcpyDeviceToHost, c->stream));
-    if (out2) CK(c, cudaMemcpyAsync(out2, c->rect2.p, n, cudaMemcpyDeviceToHost, c->stream));
+    if (out1) CK(c, cudaMemcpyAsync(out1, c->rect1.p, n, cudaMemcpyDefault, c->stream));
+    if (out2) CK(c, cudaMemcpyAsync(out2, c->rect2.p, n, cudaMemcpyDefault, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return B2S_OK;
 }
@@ -384,10 +384,10 @@ int b2s_depth_from_disparity(b2s_handle c, const float *disparity, const uint8_t
     CK(c, cudaSetDevice(c->device));
     size_t n = (size_t)c->rW * c->rH, n1 = (size_t)c->rW1 * c->rH1;
     CK(c, c->stage_f32.ensure(n * 4));
-    CK(c, cudaMemcpyAsync(c->stage_f32.p, disparity, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->stage_f32.p, disparity, n * 4, cudaMemcpyDefault, c->stream));
     if (img1) {
         CK(c, c->img1.ensure(n1 * cn));
-        CK(c, cudaMemcpyAsync(c->img1.p, img1, n1 * cn, cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaMemcpyAsync(c->img1.p, img1, n1 * cn, cudaMemcpyDefault, c->stream));
     }
     int rc = depth_tail(c, c->stage_f32.as<float>(), 1, img1 ? c->img1.as<uint8_t>() : nullptr, cn, want_unrectify, o);
     if (rc) return rc;
@@ -402,9 +402,9 @@ int b2s_disparity_to_depth(b2s_handle c, const float *disparity, double *depth)
     CK(c, cudaSetDevice(c->device));
     size_t n = (size_t)c->rW * c->rH;
     CK(c, c->stage_f32.ensure(n * 4));
-    CK(c, cudaMemcpyAsync(c->stage_f32.p, disparity, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->stage_f32.p, disparity, n * 4, cudaMemcpyDefault, c->stream));
     CK(c, launch_depth_bare(c, c->stage_f32.as<float>(), c->rdepth.as<double>()));
-    CK(c, cudaMemcpyAsync(depth, c->rdepth.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(depth, c->rdepth.p, n * 8, cudaMemcpyDefault, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return B2S_OK;
 }
@@ -415,9 +415,9 @@ int b2s_unrectify_depth(b2s_handle c, const double *rectify_depth, double *out)
     if (!c->have_rig || !c->umapx.p || !c->umapy.p) return fail(c, B2S_ESTATE, "rig (with unrectify maps) has not been set");
     CK(c, cudaSetDevice(c->device));
     size_t n = (size_t)c->rW * c->rH, n1 = (size_t)c->rW1 * c->rH1;
-    CK(c, cudaMemcpyAsync(c->rdepth.p, rectify_depth, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->rdepth.p, rectify_depth, n * 8, cudaMemcpyDefault, c->stream));
     CK(c, launch_unrectify(c, c->rdepth.as<double>(), c->udepth.as<double>()));
-    CK(c, cudaMemcpyAsync(out, c->udepth.p, n1 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(out, c->udepth.p, n1 * 8, cudaMemcpyDefault, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return B2S_OK;
 }
@@ -431,9 +431,9 @@ int b2s_undistort_img(b2s_handle c, const uint8_t *img1, int cn, uint8_t *out)
     size_t n1 = (size_t)c->rW1 * c->rH1 * cn;
     CK(c, c->img1.ensure(n1));
     CK(c, c->und1.ensure(n1));
-    CK(c, cudaMemcpyAsync(c->img1.p, img1, n1, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->img1.p, img1, n1, cudaMemcpyDefault, c->stream));
     CK(c, launch_undistort_u8(c, c->img1.as<uint8_t>(), c->rH1, c->rW1, cn, c->und_xy.as<int16_t>(), c->und_fxy.as<uint16_t>(), c->und1.as<uint8_t>()));
-    CK(c, cudaMemcpyAsync(out, c->und1.p, n1, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(out, c->und1.p, n1, cudaMemcpyDefault, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return B2S_OK;
 }

@@ -1,0 +1,184 @@
+"""Pair-batch sharding across GPUs: one process per GPU (`torchrun`), `torch.distributed` for the plumbing.
+
+The reference has no multi-device path (one `Stereo.get_depth` per call, calibrating/stereo_camera.py:492-533).  Image
+pairs are independent, so the path shards by pair with no data-path collective; exactly two
+collectives exist, both outside the per-pair kernels:
+
+  * ONE broadcast of the per-rig constant block from rank 0 -- the four rectification map planes, the two unrectify map
+    planes, the valid mask, the undistort maps and the scalars (`Stereo._get_undistort_rectify_map`,
+    stereo_camera.py:125-177; ~100 MB at 1080p) -- so that only rank 0 runs the host-side map generation.  With the
+    NCCL backend the block is broadcast GPU-to-GPU over NVLink and handed to the engine as device pointers
+    (`b2s_set_rig` accepts them), with gloo (CPU tests) it travels as a host tensor.
+  * ONE all-gather of the per-pair results (`unrectify_depth`, float64 (H1,W1) per pair) so that every rank holds the
+    batch result in global pair order.
+
+Pair i of a global batch belongs to rank i % world_size (`shard_indices`).  The compute engine behind a rank is pluggable
+(`engine_factory`) so that the host logic is testable on CPU with the oracle (tests/test_sharded.py, gloo, world_size 2);
+the default engine is the CUDA one and fails loudly without a GPU.
+"""
+import ctypes
+import json
+
+import numpy as np
+
+from . import _ffi
+
+_MAGIC = b"B2SRIG01"
+
+
+def shard_indices(n, rank, world):
+    """Global pair indices handled by `rank`: i % world == rank (static round-robin)."""
+    return list(range(rank, n, world))
+
+
+# ---- the rig block: everything a rank needs to run get_depth, in one contiguous byte buffer ------------------------
+_ARRAYS = [("map1x", np.float32), ("map1y", np.float32), ("map2x", np.float32), ("map2y", np.float32), ("valid_mask1", np.uint8),
+           ("unrect_mapx", np.float32), ("unrect_mapy", np.float32), ("undist_xy", np.int16), ("undist_fxy", np.uint16)]
+
+
+def rig_arrays(stereo):
+    """The per-rig constant arrays and scalars of `stereo` (host side; what `Stereo._push_rig` uploads)."""
+    import cv2
+    m1x, m1y = stereo.undistort_rectify_map1
+    m2x, m2y = stereo.undistort_rectify_map2
+    umx, umy = stereo._unrectify_maps()
+    w1, h1 = stereo.cam1.xy
+    und_xy, und_fxy = cv2.initUndistortRectifyMap(stereo.cam1.K, stereo.cam1.D, None, stereo.cam1.K, (w1, h1), cv2.CV_16SC2)
+    M = stereo.R1.T @ np.linalg.inv(stereo.K)
+    arrays = dict(map1x=m1x, map1y=m1y, map2x=m2x, map2y=m2y, valid_mask1=stereo.rectify_valid_mask1, unrect_mapx=umx, unrect_mapy=umy,
+                  undist_xy=und_xy, undist_fxy=und_fxy)
+    arrays = {k: np.ascontiguousarray(arrays[k], dt) for k, dt in _ARRAYS}
+    scalars = dict(W=int(stereo.xy[0]), H=int(stereo.xy[1]), W1=int(w1), H1=int(h1), W2=int(stereo.cam2.xy[0]), H2=int(stereo.cam2.xy[1]),
+                   unrect_m=[float(v) for v in M[2]], fx_baseline=float(1.0 * stereo.baseline * stereo.K[0, 0]),
+                   max_depth=float(stereo.get_max_depth()),
+                   min_disparity=int(stereo.min_disparity) if getattr(stereo, "translation_rectify_img", None) else 0,
+                   interp={"lanczos4": 0, "linear": 1}[stereo.interp])
+    return arrays, scalars
+
+
+def pack_rig_block(stereo, matcher_cfg=None):
+    """-> uint8 array: magic | u64 header length | JSON header (scalars, matcher cfg, array offsets) | 256-aligned arrays."""
+    arrays, scalars = rig_arrays(stereo)
+    off, table = 0, {}
+    for name, dt in _ARRAYS:
+        a = arrays[name]
+        table[name] = dict(offset=off, shape=list(a.shape), dtype=np.dtype(dt).str)
+        off += (a.nbytes + 255) // 256 * 256
+    header = json.dumps(dict(scalars=scalars, matcher=matcher_cfg or {}, arrays=table)).encode()
+    head_len = (len(_MAGIC) + 8 + len(header) + 255) // 256 * 256
+    buf = np.zeros(head_len + off, np.uint8)
+    buf[:8] = np.frombuffer(_MAGIC, np.uint8)
+    buf[8:16] = np.frombuffer(np.uint64(len(header)).tobytes(), np.uint8)
+    buf[16:16 + len(header)] = np.frombuffer(header, np.uint8)
+    for name, _ in _ARRAYS:
+        a = arrays[name]
+        o = head_len + table[name]["offset"]
+        buf[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+    return buf
+
+
+def unpack_rig_block(buf):
+    """-> (scalars, matcher_cfg, {name: (byte offset into buf, shape, dtype)}); `buf` is the host copy of the header at least."""
+    head = np.asarray(buf[:16]).tobytes()
+    if head[:8] != _MAGIC:
+        raise ValueError("not a rig block")
+    n = int(np.frombuffer(head[8:16], np.uint64)[0])
+    meta = json.loads(np.asarray(buf[16:16 + n]).tobytes().decode())
+    head_len = (16 + n + 255) // 256 * 256
+    table = {k: (head_len + v["offset"], tuple(v["shape"]), np.dtype(v["dtype"])) for k, v in meta["arrays"].items()}
+    return meta["scalars"], meta["matcher"], table
+
+
+def rig_struct(scalars, table, base_address):
+    """ctypes `b2s_rig` whose array pointers are base_address + offset (host or device memory alike)."""
+    rig = _ffi.Rig()
+    for k in ("W", "H", "W1", "H1", "W2", "H2", "min_disparity", "interp"):
+        setattr(rig, k, int(scalars[k]))
+    rig.unrect_m = (ctypes.c_double * 3)(*scalars["unrect_m"])
+    rig.fx_baseline, rig.max_depth = float(scalars["fx_baseline"]), float(scalars["max_depth"])
+    for name, _ in _ARRAYS:
+        setattr(rig, name, base_address + table[name][0])
+    return rig
+
+
+class CudaEngine:
+    """Default per-rank engine: libb2s.so on `device`.  The rig block stays where the broadcast left it (a torch CUDA tensor);
+    results are written straight into the caller's device tensor."""
+
+    def __init__(self, device):
+        self.handle = _ffi.Handle(device)
+        self.device = device
+        self._block = None
+
+    def set_rig_block(self, block, scalars, matcher_cfg, table):
+        from .stereo_matching import SemiGlobalBlockMatching
+        self._block = block  # keep the storage alive
+        base = block.data_ptr() if hasattr(block, "data_ptr") else block.ctypes.data
+        self.handle.call("b2s_set_rig", ctypes.byref(rig_struct(scalars, table, base)))
+        self.matcher = SemiGlobalBlockMatching(dict(matcher_cfg, max_size=1 << 30), handle=self.handle)
+        self.scalars = scalars
+
+    def get_depth_into(self, img1, img2, out):
+        """img1/img2: host uint8 arrays; out: (H1,W1) float64 torch CUDA tensor (or host array) for unrectify_depth."""
+        o = _ffi.DepthOut()
+        o.unrectify_depth = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        img1, img2 = np.ascontiguousarray(img1), np.ascontiguousarray(img2)
+        cn = 1 if img1.ndim == 2 else img1.shape[2]
+        self.handle.call("b2s_get_depth_async", _ffi.ptr(img1), _ffi.ptr(img2), cn, 1, ctypes.byref(o))
+        self.handle.sync()  # (host images are reused by the caller; one pair per call keeps this simple)
+
+
+class ShardedStereo:
+    """Rank-local front end of a pair batch sharded over `torch.distributed` ranks (module docstring)."""
+
+    def __init__(self, stereo=None, engine_factory=None, group=None, device=None):
+        """stereo: a configured `Stereo` (with `set_stereo_matching(SemiGlobalBlockMatching(...))`) on rank 0, None elsewhere."""
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.cuda = dist.get_backend(group) == "nccl"
+        self.device = device if device is not None else (torch.cuda.current_device() if self.cuda else None)
+        self.engine = (engine_factory or (lambda: CudaEngine(self.device)))()
+        self._setup(stereo)
+
+    def _setup(self, stereo):
+        torch, dist = self.torch, self.dist
+        dev = torch.device("cuda", self.device) if self.cuda else torch.device("cpu")
+        if self.rank == 0:
+            if stereo is None:
+                raise ValueError("rank 0 must pass the configured Stereo")
+            sm = getattr(stereo, "stereo_matching", None)
+            host = pack_rig_block(stereo, dict(getattr(sm, "cfg", {}) or {}))
+            size = [int(host.size)]
+        else:
+            host, size = None, [0]
+        dist.broadcast_object_list(size, src=0, group=self.group)  # control plane: the block size (one int)
+        block = torch.empty(size[0], dtype=torch.uint8, device=dev)
+        if self.rank == 0:
+            block.copy_(torch.from_numpy(host))
+        dist.broadcast(block, src=0, group=self.group)  # THE rig broadcast (NVLink with nccl)
+        head = block[:1 << 16].cpu().numpy() if block.numel() > (1 << 16) else block.cpu().numpy()
+        self.scalars, self.matcher_cfg, self.table = unpack_rig_block(head)
+        self.block = block
+        self.rig_bytes = int(size[0])
+        self.engine.set_rig_block(block if self.cuda else block.numpy(), self.scalars, self.matcher_cfg, self.table)
+
+    def shard(self, n):
+        return shard_indices(n, self.rank, self.world)
+
+    def get_depth_batch(self, local_pairs):
+        """local_pairs: this rank's [(img1, img2)] (pair k of this rank is global pair k*world + rank).
+        Returns the gathered `unrectify_depth` of the whole batch, (world * n_local, H1, W1) float64 in global pair order,
+        on every rank (device tensor with nccl, host tensor with gloo).  All ranks must pass the same number of pairs."""
+        torch, dist = self.torch, self.dist
+        n, H1, W1 = len(local_pairs), self.scalars["H1"], self.scalars["W1"]
+        dev = torch.device("cuda", self.device) if self.cuda else torch.device("cpu")
+        local = torch.zeros((n, H1, W1), dtype=torch.float64, device=dev)
+        for k, (a, b) in enumerate(local_pairs):
+            self.engine.get_depth_into(a, b, local[k] if self.cuda else local[k].numpy())
+        gathered = torch.empty((self.world, n, H1, W1), dtype=torch.float64, device=dev)
+        if self.cuda:
+            torch.cuda.current_stream().synchronize()
+        dist.all_gather_into_tensor(gathered.view(self.world * n, H1, W1), local, group=self.group)  # THE depth all-gather
+        return gathered.transpose(0, 1).reshape(self.world * n, H1, W1)  # (rank, k) -> global index k*world + rank

@@ -15,7 +15,10 @@
  * message.  No C++ exception crosses the boundary.  A handle owns one CUDA stream and all device buffers; it
  * is not thread-safe, distinct handles may be driven from distinct threads.  "host" pointers are ordinary
  * (pageable or pinned) caller-owned memory, C-contiguous, alive until the call (or the matching b2s_sync for
- * *_async calls) returns.  Images are (H,W,cn) uint8, cn in {1,3}.  There is no CPU fallback: without a
+ * *_async calls) returns.  Every image / map / result pointer may equally be DEVICE memory of the handle's GPU
+ * (copies use cudaMemcpyDefault): that is how the multi-GPU host layer hands over NCCL-broadcast rig constants
+ * (b2s_set_rig) and collects depth maps for the all-gather (b2s_get_depth_async + b2s_sync) without a host round
+ * trip.  Images are (H,W,cn) uint8, cn in {1,3}.  There is no CPU fallback: without a
  * CUDA device b2s_create fails with B2S_ECUDA.
  */
 #ifndef B2S_H

@@ -250,7 +250,7 @@ def main():
             ev[0].record()
             dist.broadcast(blk, src=0)
             ev[1].record()
-            dist.all_gather_into_tensor(gat, loc)
+            dist.all_gather_into_tensor(gat.view(torch.uint8), loc.view(torch.uint8))  # (NCCL via torch has no int16)
             ev[2].record()
             torch.cuda.synchronize()
         coll = [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])]

@@ -41,13 +41,13 @@ __global__ void __launch_bounds__(256) wta_kernel(const int16_t *__restrict__ S,
     for (int u = 0; u < 2; u++)
         if (xb + u < xe) load_px(xb + u, buf[u]);
     const int thr_mul = 100 - g.uniq;
+    int my_best = -2, my_minS = 0; // lane i keeps the winner of pixel xb+i (-2: rejected by the uniqueness test)
     for (int base = xb; base < xe; base += 3) {
 #pragma unroll
         for (int u = 0; u < 3; u++) {
             const int x = base + u;
             if (x >= xe) break;
             if (x + 2 < xe) load_px(x + 2, buf[(u + 2) % 3]);
-            const int16_t *Sp = Srow + (size_t)x * Dp;
             int sv[2 * NP];
             unsigned key = 0xFFFFFFFFu;
 #pragma unroll
@@ -70,21 +70,29 @@ __global__ void __launch_bounds__(256) wta_kernel(const int16_t *__restrict__ S,
                 int d = lane * 2 * NP + j;
                 if (d < g.D && sv[j] * thr_mul < minS * 100 && abs(best - d) > 1) bad = true;
             }
-            if (__any_sync(0xffffffffu, bad)) continue;
-            if (lane == 0) {
-                int d = best;
-                int x2 = x + g.minX1 - d - g.minD;
-                if (minS < 32767 && x2 >= 0 && x2 < g.W + 2)
-                    atomicMin(&disp2key[(size_t)y * (g.W + 2) + x2], ((unsigned)minS << 16) | (unsigned)(0xFFFF - x));
-                if (0 < d && d < g.D - 1) {
-                    int sm = Sp[d - 1], sp = Sp[d + 1], s0 = Sp[d];
-                    int den2 = max(sm + sp - 2 * s0, 1);
-                    d = d * 16 + ((sm - sp) * 16 + den2) / (den2 * 2);
-                } else
-                    d *= 16;
-                raw[(size_t)y * g.W + x + g.minX1] = (int16_t)(d + g.minD * 16);
+            const bool rej = __any_sync(0xffffffffu, bad);
+            if (lane == x - xb) {
+                my_best = rej ? -2 : best;
+                my_minS = minS;
             }
         }
+    }
+    // the per-pixel tail (right-view candidate, sub-pixel interpolation, store) runs once for the warp's 32 pixels, one per lane
+    const int x = xb + lane;
+    if (x < xe && my_best != -2) {
+        int d = my_best;
+        const int minS = my_minS;
+        const int16_t *Sp = Srow + (size_t)x * Dp;
+        int x2 = x + g.minX1 - d - g.minD;
+        if (minS < 32767 && x2 >= 0 && x2 < g.W + 2)
+            atomicMin(&disp2key[(size_t)y * (g.W + 2) + x2], ((unsigned)minS << 16) | (unsigned)(0xFFFF - x));
+        if (0 < d && d < g.D - 1) {
+            int sm = Sp[d - 1], sp = Sp[d + 1], s0 = Sp[d];
+            int den2 = max(sm + sp - 2 * s0, 1);
+            d = d * 16 + ((sm - sp) * 16 + den2) / (den2 * 2);
+        } else
+            d *= 16;
+        raw[(size_t)y * g.W + x + g.minX1] = (int16_t)(d + g.minD * 16);
     }
 }
 

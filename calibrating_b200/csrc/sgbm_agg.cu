@@ -217,20 +217,19 @@ cudaError_t launch_dir_np(b2s_ctx *c, const AggArgs &a, int mode, int wta = 0)
 
 // ================================================================================================================
 // Fused vertical sweep: the three directions that cross image rows, for the top-down sweep (moves (+1,+1) (0,+1) (-1,+1))
-// and -- MODE_HH -- the bottom-up sweep (moves (+1,-1) (0,-1) (-1,-1)) in ONE kernel that reads C once and
-// read-modify-writes S once per sweep (12 B/voxel for six directions instead of 36 with one kernel per direction).
+// and -- MODE_HH -- the bottom-up sweep (moves (+1,-1) (0,-1) (-1,-1)) in ONE launch that reads C once per sweep
+// (DESIGN.md section 4.1-4.2): the top-down sweep adds its three paths to S, the bottom-up sweep writes the sum of its
+// three to S2, and the last horizontal scan folds S2 in.
 //
-//   * the image is cut into G <= #SM vertical strips of n columns; CTA = strip, warp = column, lane = 2*NP disparities
-//   * step t handles row t of the top-down sweep and row H-1-t of the bottom-up sweep (J = 2 independent recurrences
-//     interleaved in one instruction stream; the same lane touches the same S words for both, so the two
-//     read-modify-writes of a voxel are ordered by program order and need no fence)
+//   * the image is cut into G <= #SM vertical strips of n columns; CTA = strip, warp = (column, sweep), lane = 2*NP disparities
 //   * the vertical state stays in registers; the two diagonal states move one column per row: through a double-buffered
-//     shared-memory slot between warps, and through a 4-deep ring in global memory between neighbouring CTAs.  The ring
-//     carries no flags and needs no fences: states are normalised (L - minL, 15 bits), so bit 15 of every int16 is a
-//     phase bit ((t>>2)&1) written with the data; the consumer lane polls its own words until the phase matches.
-//     A boundary is crossed by one state in each direction every row, so neighbouring CTAs can never be more than one
-//     row apart (lock-step) and a 4-deep ring cannot be overrun.  All G CTAs must be co-resident (G <= #SM, 1 CTA/SM).
-//   * C and S rows are prefetched PF steps ahead into registers (ld.global.cg), ~40 KB in flight per SM.
+//     shared-memory slot and an mbarrier pair per warp between warps, and through a 4-deep ring in global memory between
+//     neighbouring CTAs.  The ring carries no flags and needs no fences: states are normalised (L - minL, 15 bits), so
+//     bit 15 of every int16 is a phase bit ((t>>2)&1) written with the data; the consumer lane polls its own words
+//     until the phase matches.  A boundary is crossed by one state in each direction every row, so neighbouring CTAs
+//     can never be more than one row apart (lock-step) and a 4-deep ring cannot be overrun.  All G CTAs must be
+//     co-resident (G <= #SM, 1 CTA/SM).
+//   * C (and S) rows stream through a private cp.async ring per warp, ~50 KB in flight per SM.
 struct VsArgs {
     const int16_t *C;
     int16_t *S;   // top-down sweep: S += its three paths

@@ -30,6 +30,18 @@ class Rig(ctypes.Structure):
                 ("min_disparity", c_int), ("interp", c_int)]
 
 
+class MapParams(ctypes.Structure):
+    _fields_ = [("W", c_int), ("H", c_int), ("fx", c_double), ("fy", c_double), ("cx", c_double), ("cy", c_double),
+                ("k", c_double * 12), ("iR", c_double * 9)]
+
+
+class RigParams(ctypes.Structure):
+    _fields_ = [("W", c_int), ("H", c_int), ("W1", c_int), ("H1", c_int), ("W2", c_int), ("H2", c_int),
+                ("rect1", MapParams), ("rect2", MapParams), ("unrect", MapParams), ("undist", MapParams),
+                ("unrect_m", c_double * 3), ("fx_baseline", c_double), ("max_depth", c_double),
+                ("min_disparity", c_int), ("interp", c_int)]
+
+
 class DepthOut(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("rectify_img1", "rectify_img2", "disparity", "rectify_depth",
                                         "unrectify_depth", "undistort_img1", "disp16")]
@@ -54,6 +66,7 @@ SIGNATURES = {
     "b2s_compute_disparity_async": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b2s_compute_disparity_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b2s_set_rig": (c_int, [c_void_p, ctypes.POINTER(Rig)]),
+    "b2s_set_rig_params": (c_int, [c_void_p, ctypes.POINTER(RigParams)]),
     "b2s_rectify": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "b2s_get_depth": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(DepthOut)]),
     "b2s_get_depth_async": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(DepthOut)]),
@@ -164,6 +177,14 @@ class Handle:
         """(H, W) int16 disparity before the median / speckle filters."""
         out = np.empty((H, W), np.int16)
         self.call("b2s_debug_fetch", 2, ptr(out), out.nbytes)
+        return out
+
+    RIG_ARRAYS = ["map1x", "map1y", "map2x", "map2y", "valid_mask1", "unrect_mapx", "unrect_mapy", "undist_xy", "undist_fxy"]
+
+    def fetch_rig(self, name, shape, dtype):
+        """Device copy of a rig array (as uploaded by b2s_set_rig or generated by b2s_set_rig_params)."""
+        out = np.empty(shape, dtype)
+        self.call("b2s_debug_fetch", 16 + self.RIG_ARRAYS.index(name), ptr(out), out.nbytes)
         return out
 
     def event_record(self, slot):

@@ -288,6 +288,35 @@ int b2s_set_rig(b2s_handle c, const b2s_rig *r)
     return B2S_OK;
 }
 
+int b2s_set_rig_params(b2s_handle c, const b2s_rig_params *r)
+{
+    if (!c || !r) return B2S_EINVAL;
+    if (r->W <= 0 || r->H <= 0 || r->W1 <= 0 || r->H1 <= 0 || r->W2 <= 0 || r->H2 <= 0) return fail(c, B2S_EINVAL, "b2s_set_rig_params: bad sizes");
+    if (r->interp != 0 && r->interp != 1) return fail(c, B2S_EINVAL, "b2s_set_rig_params: interp must be 0 (LANCZOS4) or 1 (LINEAR)");
+    if (r->rect1.W != r->W || r->rect1.H != r->H || r->rect2.W != r->W || r->rect2.H != r->H || r->unrect.W != r->W1 || r->unrect.H != r->H1 ||
+        r->undist.W != r->W1 || r->undist.H != r->H1)
+        return fail(c, B2S_EINVAL, "b2s_set_rig_params: map sizes do not match the rig sizes");
+    CK(c, cudaSetDevice(c->device));
+    size_t n = (size_t)r->W * r->H, n1 = (size_t)r->W1 * r->H1;
+    CK(c, c->map1x.ensure(n * 4)); CK(c, c->map1y.ensure(n * 4)); CK(c, c->map2x.ensure(n * 4)); CK(c, c->map2y.ensure(n * 4));
+    CK(c, c->vmask.ensure(n)); CK(c, c->umapx.ensure(n1 * 4)); CK(c, c->umapy.ensure(n1 * 4));
+    CK(c, c->und_xy.ensure(n1 * 4)); CK(c, c->und_fxy.ensure(n1 * 2));
+    CK(c, launch_gen_maps(c, r->rect1, c->map1x.as<float>(), c->map1y.as<float>(), c->vmask.as<uint8_t>(), r->W1, r->H1, nullptr, nullptr));
+    CK(c, launch_gen_maps(c, r->rect2, c->map2x.as<float>(), c->map2y.as<float>(), nullptr, 0, 0, nullptr, nullptr));
+    CK(c, launch_gen_maps(c, r->unrect, c->umapx.as<float>(), c->umapy.as<float>(), nullptr, 0, 0, nullptr, nullptr));
+    CK(c, launch_gen_maps(c, r->undist, nullptr, nullptr, nullptr, 0, 0, c->und_xy.as<int16_t>(), c->und_fxy.as<uint16_t>()));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->rW = r->W; c->rH = r->H; c->rW1 = r->W1; c->rH1 = r->H1; c->rW2 = r->W2; c->rH2 = r->H2;
+    c->r_min_disp = r->min_disparity; c->r_interp = r->interp;
+    c->r_m[0] = r->unrect_m[0]; c->r_m[1] = r->unrect_m[1]; c->r_m[2] = r->unrect_m[2];
+    c->r_fxb = r->fx_baseline; c->r_max_depth = r->max_depth;
+    c->have_rig = true;
+    CK(c, c->dispfinal.ensure(n * 4));
+    CK(c, c->rdepth.ensure(n * 8));
+    CK(c, c->udepth.ensure(n1 * 8));
+    return B2S_OK;
+}
+
 } // extern "C"
 
 static int rectify_dev(b2s_ctx *c, const uint8_t *img1, const uint8_t *img2, int cn)
@@ -451,7 +480,7 @@ int b2s_volume_dims(b2s_handle c, int *H, int *width1, int *D, int *Dp)
 int b2s_debug_fetch(b2s_handle c, int which, void *dst, size_t bytes)
 {
     if (!c || !dst) return B2S_EINVAL;
-    if (!c->have_volume) return fail(c, B2S_ESTATE, "no cost volume resident");
+    if (which < B2S_FETCH_RIG && !c->have_volume) return fail(c, B2S_ESTATE, "no cost volume resident");
     CK(c, cudaSetDevice(c->device));
     const SgbmGeom &g = c->g;
     size_t vol = (size_t)g.H * g.width1 * g.Dp * 2, need;
@@ -464,7 +493,16 @@ int b2s_debug_fetch(b2s_handle c, int which, void *dst, size_t bytes)
                                        "call b2s_set_option(h, B2S_OPT_KEEP_VOLUMES, 1) before computing");
         src = c->S.p; need = vol; break;
     case B2S_FETCH_RAW: src = c->raw.p; need = (size_t)g.H * g.W * 2; break;
-    default: return fail(c, B2S_EINVAL, "b2s_debug_fetch: unknown selector %d", which);
+    default:
+        if (which >= B2S_FETCH_RIG && which < B2S_FETCH_RIG + 9 && c->have_rig) {
+            const size_t n = (size_t)c->rW * c->rH, n1 = (size_t)c->rW1 * c->rH1;
+            const DevBuf *bufs[9] = {&c->map1x, &c->map1y, &c->map2x, &c->map2y, &c->vmask, &c->umapx, &c->umapy, &c->und_xy, &c->und_fxy};
+            const size_t sizes[9] = {n * 4, n * 4, n * 4, n * 4, n, n1 * 4, n1 * 4, n1 * 4, n1 * 2};
+            src = bufs[which - B2S_FETCH_RIG]->p; need = sizes[which - B2S_FETCH_RIG];
+            if (!src) return fail(c, B2S_ESTATE, "b2s_debug_fetch: that rig array was not set");
+            break;
+        }
+        return fail(c, B2S_EINVAL, "b2s_debug_fetch: unknown selector %d", which);
     }
     if (bytes != need) return fail(c, B2S_EINVAL, "b2s_debug_fetch: need %zu bytes, got %zu", need, bytes);
     CK(c, cudaStreamSynchronize(c->stream));

@@ -103,6 +103,8 @@ cudaError_t launch_remap_u8(b2s_ctx *c, const uint8_t *src, int sH, int sW, int 
 cudaError_t launch_undistort_u8(b2s_ctx *c, const uint8_t *src, int H, int W, int cn, const int16_t *xy, const uint16_t *fxy,
                                 uint8_t *dst);
 cudaError_t launch_depth(b2s_ctx *c, const float *d_disp_in, int add_min_disp, int want_unrectify);
+cudaError_t launch_gen_maps(b2s_ctx *c, const b2s_map_params &p, float *mapx, float *mapy, uint8_t *mask, int mW, int mH, int16_t *xy16,
+                            uint16_t *fxy16);
 cudaError_t launch_depth_bare(b2s_ctx *c, const float *d_disp, double *d_depth);
 cudaError_t launch_unrectify(b2s_ctx *c, const double *d_depth, double *d_out);
 

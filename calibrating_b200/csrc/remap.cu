@@ -208,6 +208,60 @@ __global__ void unrectify_kernel(const double *__restrict__ depth, int H, int W,
 
 } // namespace
 
+namespace {
+// cv2.initUndistortRectifyMap restated, float64 without fused multiply-add so that every
+// operation rounds exactly where OpenCV's scalar code does; thread = one map pixel.
+__global__ void gen_maps_kernel(b2s_map_params p, float *__restrict__ mapx, float *__restrict__ mapy, uint8_t *__restrict__ mask,
+                                int mW, int mH, short2 *__restrict__ xy16, unsigned short *__restrict__ fxy16)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= p.W) return;
+    const double dj = (double)j, di = (double)i;
+    const double X = __dadd_rn(__dmul_rn(dj, p.iR[0]), __dadd_rn(__dmul_rn(di, p.iR[1]), p.iR[2]));
+    const double Y = __dadd_rn(__dmul_rn(dj, p.iR[3]), __dadd_rn(__dmul_rn(di, p.iR[4]), p.iR[5]));
+    const double Wh = __dadd_rn(__dmul_rn(dj, p.iR[6]), __dadd_rn(__dmul_rn(di, p.iR[7]), p.iR[8]));
+    const double w = __ddiv_rn(1.0, Wh), x = __dmul_rn(X, w), y = __dmul_rn(Y, w);
+    const double x2 = __dmul_rn(x, x), y2 = __dmul_rn(y, y), r2 = __dadd_rn(x2, y2), _2xy = __dmul_rn(__dmul_rn(2.0, x), y);
+    const double k1 = p.k[0], k2 = p.k[1], p1 = p.k[2], p2 = p.k[3], k3 = p.k[4], k4 = p.k[5], k5 = p.k[6], k6 = p.k[7];
+    const double s1 = p.k[8], s2 = p.k[9], s3 = p.k[10], s4 = p.k[11];
+    auto poly = [&](double a, double b, double c) { // 1 + ((a*r2 + b)*r2 + c)*r2
+        return __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(a, r2), b), r2), c), r2));
+    };
+    const double kr = __ddiv_rn(poly(k3, k2, k1), poly(k6, k5, k4));
+    double xd = __dadd_rn(__dmul_rn(x, kr), __dmul_rn(p1, _2xy));
+    xd = __dadd_rn(xd, __dmul_rn(p2, __dadd_rn(r2, __dmul_rn(2.0, x2))));
+    xd = __dadd_rn(xd, __dmul_rn(s1, r2));
+    xd = __dadd_rn(xd, __dmul_rn(__dmul_rn(s2, r2), r2));
+    double yd = __dadd_rn(__dmul_rn(y, kr), __dmul_rn(p1, __dadd_rn(r2, __dmul_rn(2.0, y2))));
+    yd = __dadd_rn(yd, __dmul_rn(p2, _2xy));
+    yd = __dadd_rn(yd, __dmul_rn(s3, r2));
+    yd = __dadd_rn(yd, __dmul_rn(__dmul_rn(s4, r2), r2));
+    const double u = __dadd_rn(__dmul_rn(p.fx, xd), p.cx), v = __dadd_rn(__dmul_rn(p.fy, yd), p.cy);
+    const size_t o = (size_t)i * p.W + j;
+    if (mapx) {
+        const float fu = (float)u, fv = (float)v;
+        mapx[o] = fu;
+        mapy[o] = fv;
+        // rectify_valid_mask1 (stereo_camera.py:167-176), on the float32 maps like the reference
+        if (mask) mask[o] = (-0.5f < fu) && (fu < (float)mW - 0.5f) && (-0.5f < fv) && (fv < (float)mH - 0.5f);
+    }
+    if (xy16) { // CV_16SC2 + interpolation-table index, as cv2 builds them for cv2.undistort (from the float64 values)
+        const int iu = __double2int_rn(__dmul_rn(u, 32.0)), iv = __double2int_rn(__dmul_rn(v, 32.0));
+        xy16[o] = make_short2((short)sat_short(iu >> 5), (short)sat_short(iv >> 5));
+        fxy16[o] = (unsigned short)((iv & 31) * 32 + (iu & 31));
+    }
+}
+} // namespace
+
+cudaError_t launch_gen_maps(b2s_ctx *c, const b2s_map_params &p, float *mapx, float *mapy, uint8_t *mask, int mW, int mH, int16_t *xy16,
+                            uint16_t *fxy16)
+{
+    dim3 b(128), g((p.W + 127) / 128, p.H);
+    gen_maps_kernel<<<g, b, 0, c->stream>>>(p, mapx, mapy, mask, mW, mH, (short2 *)xy16, fxy16);
+    c->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_remap_u8(b2s_ctx *c, const uint8_t *src, int sH, int sW, int cn, const float *mapx, const float *mapy, int dH,
                             int dW, int xshift, int interp, uint8_t *dst)
 {

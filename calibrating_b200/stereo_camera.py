@@ -82,12 +82,15 @@ class Stereo:
     MAX_DEPTH = 1000
     DUMP_ATTRS = ["R", "t", "retval"]
 
-    def __init__(self, cam1=None, cam2=None, xy_target=None, K_target=1, R=None, t=None, device=0, interp="lanczos4"):
-        """interp: "lanczos4" (what the reference's rectify uses) or "linear" (north_star's fast bilinear mode)."""
+    def __init__(self, cam1=None, cam2=None, xy_target=None, K_target=1, R=None, t=None, device=0, interp="lanczos4", maps="host"):
+        """interp: "lanczos4" (what the reference's rectify uses) or "linear" (north_star's fast bilinear mode).
+        maps: "host" uploads the cv2.initUndistortRectifyMap results (stereo_camera.py:159-165); "device" sends only the
+        calibration parameters and the engine generates the same maps itself (b2s_set_rig_params)."""
         self.xy_target = xy_target
         self.K_target = K_target
         self.device = device
         self.interp = interp
+        self.maps = maps
         self._handle = None
         self._rig_dirty = True
         if cam1 is None:
@@ -143,7 +146,7 @@ class Stereo:
         return self
 
     def copy(self):
-        new = type(self)(device=self.device, interp=self.interp)
+        new = type(self)(device=self.device, interp=self.interp, maps=self.maps)
         new.load(self.dump(return_dict=True))
         return new
 
@@ -229,9 +232,43 @@ class Stereo:
                                                                      tuple(self.cam1.xy), cv2.CV_32FC1)
         return self._unrectify_depth_maps
 
+    @staticmethod
+    def _map_params(K, D, R, Knew, size):
+        """Inputs of one cv2.initUndistortRectifyMap(K, D, R, Knew, size) call as a b2s_map_params struct."""
+        D = np.zeros(0) if D is None else np.float64(D).ravel()
+        if D.size > 12 and np.any(D[12:] != 0):
+            raise NotImplementedError("tilted sensor model (tauX, tauY) is not supported by the device-side map generation")
+        k = np.zeros(12)
+        k[:min(D.size, 12)] = D[:12]
+        iR = np.linalg.inv(np.float64(Knew) @ (np.eye(3) if R is None else np.float64(R)))
+        K = np.float64(K)
+        return _ffi.MapParams(int(size[0]), int(size[1]), K[0, 0], K[1, 1], K[0, 2], K[1, 2], (ctypes.c_double * 12)(*k),
+                              (ctypes.c_double * 9)(*iR.ravel()))
+
+    def _push_rig_params(self):
+        w1, h1 = self.cam1.xy
+        rp = _ffi.RigParams()
+        rp.W, rp.H = self.xy
+        rp.W1, rp.H1 = w1, h1
+        rp.W2, rp.H2 = self.cam2.xy
+        rp.rect1 = self._map_params(self.cam1.K, self.cam1.D, self.R1, self.K, self.xy)
+        rp.rect2 = self._map_params(self.cam2.K, self.cam2.D, self.R2, self.K, self.xy)
+        rp.unrect = self._map_params(self.K, None, self.R1.T, self.cam1.K, (w1, h1))
+        rp.undist = self._map_params(self.cam1.K, self.cam1.D, None, self.cam1.K, (w1, h1))
+        M = self.R1.T @ np.linalg.inv(self.K)
+        rp.unrect_m = (ctypes.c_double * 3)(*M[2])
+        rp.fx_baseline = float(1.0 * self.baseline * self.K[0, 0])
+        rp.max_depth = float(self.get_max_depth())
+        rp.min_disparity = int(self.min_disparity) if getattr(self, "translation_rectify_img", None) else 0
+        rp.interp = {"lanczos4": 0, "linear": 1}[self.interp]
+        self.handle.call("b2s_set_rig_params", ctypes.byref(rp))
+        self._rig_dirty = False
+
     def _push_rig(self):
         if not self._rig_dirty:
             return
+        if self.maps == "device":
+            return self._push_rig_params()
         h = self.handle
         m1x, m1y = (np.ascontiguousarray(m, np.float32) for m in self.undistort_rectify_map1)
         m2x, m2y = (np.ascontiguousarray(m, np.float32) for m in self.undistort_rectify_map2)

@@ -66,6 +66,29 @@ typedef struct {
     int interp;                 /* 0 = INTER_LANCZOS4 (reference), 1 = INTER_LINEAR (fast mode)          */
 } b2s_rig;
 
+/* One cv2.initUndistortRectifyMap(cameraMatrix, distCoeffs, R, newCameraMatrix, (W,H)) call described by its inputs, for
+ * device-side map generation (b2s_set_rig_params): pixel (j,i) of the map -> [X Y Wh] = iR*[j i 1], x = X/Wh, y = Y/Wh,
+ * OpenCV distortion model k = (k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4), u = fx*xd + cx, v = fy*yd + cy, evaluated in
+ * float64 in cv2's operation order (no fused multiply-add) and rounded to float32 once. */
+typedef struct {
+    int W, H;              /* map size */
+    double fx, fy, cx, cy; /* cameraMatrix: intrinsics of the image the map samples */
+    double k[12];          /* distortion coefficients, zero-padded (the tilt terms tauX/tauY are not supported) */
+    double iR[9];          /* inv(newCameraMatrix * R), row-major */
+} b2s_map_params;
+
+/* The rig of b2s_rig described by parameters instead of arrays: the engine generates the four rectification map planes,
+ * the valid mask (stereo_camera.py:167-176), the unrectify maps (utils.py:184-191) and the CV_16SC2 undistort maps on
+ * the device.  SURVEY.md section 8(f) rank 1. */
+typedef struct {
+    int W, H, W1, H1, W2, H2;
+    b2s_map_params rect1, rect2; /* (cam1.K, cam1.D, R1, K), (cam2.K, cam2.D, R2, K) at (W,H)            */
+    b2s_map_params unrect;       /* (K, none, R1^T, cam1.K) at (W1,H1)                                  */
+    b2s_map_params undist;       /* (cam1.K, cam1.D, I, cam1.K) at (W1,H1)                              */
+    double unrect_m[3], fx_baseline, max_depth;
+    int min_disparity, interp;
+} b2s_rig_params;
+
 /* Which arrays b2s_get_depth copies back; NULL pointers are skipped. */
 typedef struct {
     uint8_t *rectify_img1, *rectify_img2; /* (H,W,cn) u8 */
@@ -108,6 +131,10 @@ int b2s_compute_disparity_dev(b2s_handle h, const uint8_t *d_left, const uint8_t
 
 /* ---- full chain: replaces Stereo.rectify / get_depth / unrectify_depth / undistort_img ------------------- */
 int b2s_set_rig(b2s_handle h, const b2s_rig *rig);
+/* Same rig, maps generated on the device from the calibration parameters (bit-identical to cv2's maps wherever
+ * float64 arithmetic is: tests/test_gpu_chain.py); replaces the cv2.initUndistortRectifyMap calls of
+ * stereo_camera.py:159-165, utils.py:184-191 and the ~100 MB upload / broadcast of their results. */
+int b2s_set_rig_params(b2s_handle h, const b2s_rig_params *rig);
 /* Stereo.rectify (stereo_camera.py:216-242): img1 (H1,W1,cn), img2 (H2,W2,cn) host -> out1/out2 (H,W,cn). */
 int b2s_rectify(b2s_handle h, const uint8_t *img1, const uint8_t *img2, int cn, uint8_t *out1, uint8_t *out2);
 /* Stereo.get_depth with the built-in matcher (stereo_camera.py:492-533). want_unrectify: also run
@@ -133,6 +160,7 @@ int b2s_undistort_img(b2s_handle h, const uint8_t *img1, int cn, uint8_t *out);
 #define B2S_FETCH_C 0    /* cost volume (H,width1,Dp) i16 */
 #define B2S_FETCH_S 1    /* aggregated volume (H,width1,Dp) i16 */
 #define B2S_FETCH_RAW 2  /* (H,W) i16 disparity before median/speckle */
+#define B2S_FETCH_RIG 16 /* + k: k-th rig array in b2s_rig order: map1x map1y map2x map2y valid_mask1 unrect_mapx unrect_mapy undist_xy undist_fxy */
 /* Options (all default 0).
  * B2S_OPT_FUSE_WTA: fuse the winner-take-all step into the last aggregation pass; the aggregated volume S is then never
  *   written unless B2S_OPT_KEEP_VOLUMES is also set (B2S_FETCH_S fails otherwise).  Results are identical either way. */

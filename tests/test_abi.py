@@ -37,6 +37,22 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_ffi.Rig) == 6 * 4 + 9 * 8 + 5 * 8 + 2 * 4
 
 
+def test_struct_sizes_against_the_c_compiler(tmp_path):
+    """sizeof of every struct of include/b2s.h as gcc sees it == the ctypes mirror."""
+    import ctypes
+    import subprocess
+    names = {"b2s_sgbm_params": _ffi.SgbmParams, "b2s_rig": _ffi.Rig, "b2s_map_params": _ffi.MapParams, "b2s_rig_params": _ffi.RigParams,
+             "b2s_depth_out": _ffi.DepthOut, "b2s_timing": _ffi.Timing}
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "b2s.h"\nint main(void){' +
+                   "".join('printf("%s %%zu\\n", sizeof(%s));' % (n, n) for n in names) + "return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for n, t in names.items():
+        assert int(out[n]) == ctypes.sizeof(t), n
+
+
 def test_no_cpu_fallback(lib):
     if lib.b2s_device_count() > 0:
         pytest.skip("a GPU is present")

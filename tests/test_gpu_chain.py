@@ -101,3 +101,36 @@ def test_chain_1080p_vs_cv2_restatement(interp):
     v = res["unrectify_depth"] > 0
     assert v.mean() > 0.5
     assert np.median(np.abs(res["unrectify_depth"][v] - gt[v]) / gt[v]) < 0.01
+
+
+@pytest.mark.parametrize("size", [(320, 240), (1920, 1080)])
+def test_device_side_map_generation(size, golden):
+    """the rig described by parameters only (`maps="device"`, b2s_set_rig_params).  The
+    generated maps equal cv2.initUndistortRectifyMap's bit for bit (float64 in cv2's operation order, no FMA), so the
+    whole chain gives the same arrays as with uploaded maps."""
+    import cv2
+    rig = synth.rig_dict(size)
+    host = cb.Stereo.load(rig).set_stereo_matching(cb.SemiGlobalBlockMatching({"max_size": 4000, "num_disparities": 64}), max_depth=3.5)
+    dev = cb.Stereo.load(rig, maps="device").set_stereo_matching(cb.SemiGlobalBlockMatching({"max_size": 4000, "num_disparities": 64}),
+                                                                 max_depth=3.5)
+    img1, img2 = synth.render_rig(rig, seed=3)
+    a, b = host.get_depth(img1, img2), dev.get_depth(img1, img2)
+    w, h = dev.xy
+    w1, h1 = dev.cam1.xy
+    exp = dict(zip(["map1x", "map1y"], dev.undistort_rectify_map1))
+    exp.update(zip(["map2x", "map2y"], dev.undistort_rectify_map2))
+    exp.update(zip(["unrect_mapx", "unrect_mapy"], dev._unrectify_maps()))
+    for name, e in exp.items():
+        got = dev.handle.fetch_rig(name, e.shape, np.float32)
+        same = (got == e).mean()
+        assert same >= 0.9999 and np.abs(got - e).max() <= 2e-4, (name, same)  # (100 % on these rigs; cv2's SIMD path may differ by an ulp)
+    und_xy, und_fxy = cv2.initUndistortRectifyMap(dev.cam1.K, dev.cam1.D, None, dev.cam1.K, (w1, h1), cv2.CV_16SC2)
+    assert (dev.handle.fetch_rig("undist_xy", (h1, w1, 2), np.int16) == und_xy).mean() >= 0.9999
+    assert (dev.handle.fetch_rig("undist_fxy", (h1, w1), np.uint16) == und_fxy).mean() >= 0.9999
+    assert np.array_equal(dev.handle.fetch_rig("valid_mask1", (h, w), np.uint8).astype(bool), dev.rectify_valid_mask1)
+    for k in a:
+        if a[k].dtype == np.uint8:
+            assert (a[k] == b[k]).mean() >= 0.9999, k
+        else:
+            assert _close_depth(np.float64(b[k]), np.float64(a[k]), 1e-3).mean() >= 0.9999 if "depth" in k else \
+                (a[k] == b[k]).mean() >= 0.999, k

@@ -44,7 +44,7 @@ class RigParams(ctypes.Structure):
 
 class DepthOut(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("rectify_img1", "rectify_img2", "disparity", "rectify_depth",
-                                        "unrectify_depth", "undistort_img1", "disp16")]
+                                        "unrectify_depth", "undistort_img1", "disp16", "distort_depth")]
 
 
 class Timing(ctypes.Structure):
@@ -74,6 +74,8 @@ SIGNATURES = {
     "b2s_disparity_to_depth": (c_int, [c_void_p, c_void_p, c_void_p]),
     "b2s_unrectify_depth": (c_int, [c_void_p, c_void_p, c_void_p]),
     "b2s_undistort_img": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "b2s_set_cam1_model": (c_int, [c_void_p, c_double, c_double, c_double, c_double, ctypes.POINTER(c_double)]),
+    "b2s_distort_depth": (c_int, [c_void_p, c_void_p, c_void_p]),
     "b2s_set_option": (c_int, [c_void_p, c_int, c_int]),
     "b2s_volume_dims": (c_int, [c_void_p] + [ctypes.POINTER(c_int)] * 4),
     "b2s_debug_fetch": (c_int, [c_void_p, c_int, c_void_p, c_size_t]),

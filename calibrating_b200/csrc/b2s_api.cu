@@ -80,7 +80,7 @@ int b2s_destroy(b2s_handle c)
     DevBuf *bufs[] = {&c->left, &c->right, &c->planesL, &c->planesR, &c->C, &c->S, &c->S2, &c->raw, &c->disp16, &c->disp2key, &c->labels,
                       &c->sizes, &c->med, &c->dispf, &c->agg_ho, &c->map1x, &c->map1y, &c->map2x, &c->map2y, &c->vmask, &c->umapx, &c->umapy,
                       &c->und_xy, &c->und_fxy, &c->img1, &c->img2, &c->rect1, &c->rect2, &c->und1, &c->dispfinal, &c->rdepth,
-                      &c->udepth, &c->lanczos_tab, &c->stage_f32};
+                      &c->udepth, &c->lanczos_tab, &c->stage_f32, &c->dkey, &c->ddepth};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -311,9 +311,37 @@ int b2s_set_rig_params(b2s_handle c, const b2s_rig_params *r)
     c->r_m[0] = r->unrect_m[0]; c->r_m[1] = r->unrect_m[1]; c->r_m[2] = r->unrect_m[2];
     c->r_fxb = r->fx_baseline; c->r_max_depth = r->max_depth;
     c->have_rig = true;
+    c->cam1_f[0] = r->undist.fx; c->cam1_f[1] = r->undist.fy; c->cam1_f[2] = r->undist.cx; c->cam1_f[3] = r->undist.cy;
+    memcpy(c->cam1_k, r->undist.k, sizeof c->cam1_k);
+    c->have_cam1 = true;
     CK(c, c->dispfinal.ensure(n * 4));
     CK(c, c->rdepth.ensure(n * 8));
     CK(c, c->udepth.ensure(n1 * 8));
+    return B2S_OK;
+}
+
+int b2s_set_cam1_model(b2s_handle c, double fx, double fy, double cx, double cy, const double k[12])
+{
+    if (!c || !k) return B2S_EINVAL;
+    if (fx == 0 || fy == 0) return fail(c, B2S_EINVAL, "b2s_set_cam1_model: zero focal length");
+    c->cam1_f[0] = fx; c->cam1_f[1] = fy; c->cam1_f[2] = cx; c->cam1_f[3] = cy;
+    memcpy(c->cam1_k, k, sizeof c->cam1_k);
+    c->have_cam1 = true;
+    return B2S_OK;
+}
+
+int b2s_distort_depth(b2s_handle c, const double *depth, double *out)
+{
+    if (!c || !depth || !out) return B2S_EINVAL;
+    if (!c->have_rig || !c->have_cam1) return fail(c, B2S_ESTATE, "rig and cam1 model (b2s_set_cam1_model) have not been set");
+    CK(c, cudaSetDevice(c->device));
+    size_t n1 = (size_t)c->rW1 * c->rH1;
+    CK(c, c->udepth.ensure(n1 * 8));
+    CK(c, c->ddepth.ensure(n1 * 8));
+    CK(c, cudaMemcpyAsync(c->udepth.p, depth, n1 * 8, cudaMemcpyDefault, c->stream));
+    CK(c, launch_distort_depth(c, c->udepth.as<double>(), c->ddepth.as<double>()));
+    CK(c, cudaMemcpyAsync(out, c->ddepth.p, n1 * 8, cudaMemcpyDefault, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
     return B2S_OK;
 }
 
@@ -346,7 +374,14 @@ static int depth_tail(b2s_ctx *c, const float *d_disp, int add_min, const uint8_
         CK(c, c->und1.ensure(n1 * cn));
         CK(c, launch_undistort_u8(c, d_img1, c->rH1, c->rW1, cn, c->und_xy.as<int16_t>(), c->und_fxy.as<uint16_t>(), c->und1.as<uint8_t>()));
     }
+    const bool dist = want_unrectify && o->distort_depth;
+    if (dist) {
+        if (!c->have_cam1) return fail(c, B2S_ESTATE, "distort_depth needs b2s_set_cam1_model");
+        CK(c, c->ddepth.ensure(n1 * 8));
+        CK(c, launch_distort_depth(c, c->udepth.as<double>(), c->ddepth.as<double>()));
+    }
     cudaEventRecord(c->ev[6], c->stream);
+    if (dist) CK(c, cudaMemcpyAsync(o->distort_depth, c->ddepth.p, n1 * 8, cudaMemcpyDefault, c->stream));
     if (o->disparity) CK(c, cudaMemcpyAsync(o->disparity, c->dispfinal.p, n * 4, cudaMemcpyDefault, c->stream));
     if (o->rectify_depth) CK(c, cudaMemcpyAsync(o->rectify_depth, c->rdepth.p, n * 8, cudaMemcpyDefault, c->stream));
     if (want_unrectify && o->unrectify_depth) CK(c, cudaMemcpyAsync(o->unrectify_depth, c->udepth.p, n1 * 8, cudaMemcpyDefault, c->stream));

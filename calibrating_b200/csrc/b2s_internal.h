@@ -77,6 +77,9 @@ struct b2s_ctx {
     DevBuf img1, img2, rect1, rect2, und1; // raw inputs and remapped outputs
     DevBuf dispfinal, rdepth, udepth;      // (H,W) f32, (H,W) f64, (H1,W1) f64
     DevBuf lanczos_tab;                    // (1024, 8, 8) int16
+    DevBuf dkey, ddepth;                   // distort_depth: winner index per target pixel (+ the 12 coefficients); (H1,W1) f64 result
+    bool have_cam1 = false;
+    double cam1_f[4] = {0, 0, 0, 0}, cam1_k[12] = {0};
     DevBuf stage_f32;                      // upload scratch for b2s_depth_from_disparity
 
     cudaEvent_t ev[8] = {};
@@ -103,6 +106,7 @@ cudaError_t launch_remap_u8(b2s_ctx *c, const uint8_t *src, int sH, int sW, int 
 cudaError_t launch_undistort_u8(b2s_ctx *c, const uint8_t *src, int H, int W, int cn, const int16_t *xy, const uint16_t *fxy,
                                 uint8_t *dst);
 cudaError_t launch_depth(b2s_ctx *c, const float *d_disp_in, int add_min_disp, int want_unrectify);
+cudaError_t launch_distort_depth(b2s_ctx *c, const double *d_depth, double *d_out);
 cudaError_t launch_gen_maps(b2s_ctx *c, const b2s_map_params &p, float *mapx, float *mapy, uint8_t *mask, int mW, int mH, int16_t *xy16,
                             uint16_t *fxy16);
 cudaError_t launch_depth_bare(b2s_ctx *c, const float *d_disp, double *d_depth);

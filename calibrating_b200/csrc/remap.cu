@@ -253,6 +253,56 @@ __global__ void gen_maps_kernel(b2s_map_params p, float *__restrict__ mapx, floa
 }
 } // namespace
 
+namespace {
+// cv2.undistortPoints(points f32, K, None) then cv2.projectPoints(., 0, 0, K, D) restated: float64 in OpenCV's
+// operation order without FMA, rounded to float32 where OpenCV stores float32 (the normalised point and the image point),
+// then the reference's astype(int32) truncation.  Winner per target = smallest source index (atomicMin).
+__global__ void distort_scatter_kernel(int W, int H, double fx, double fy, double cx, double cy, const double *__restrict__ kk,
+                                       unsigned *__restrict__ key)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+    if (u >= W) return;
+    const double ifx = __ddiv_rn(1.0, fx), ify = __ddiv_rn(1.0, fy);
+    const double x = (double)(float)__dmul_rn(__dadd_rn((double)u, -cx), ifx), y = (double)(float)__dmul_rn(__dadd_rn((double)v, -cy), ify);
+    const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), r4 = __dmul_rn(r2, r2), r6 = __dmul_rn(r4, r2);
+    const double a1 = __dmul_rn(__dmul_rn(2.0, x), y), a2 = __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x)),
+                 a3 = __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y));
+    const double cdist = __dadd_rn(__dadd_rn(__dadd_rn(1.0, __dmul_rn(kk[0], r2)), __dmul_rn(kk[1], r4)), __dmul_rn(kk[4], r6));
+    const double icdist2 = __ddiv_rn(1.0, __dadd_rn(__dadd_rn(__dadd_rn(1.0, __dmul_rn(kk[5], r2)), __dmul_rn(kk[6], r4)), __dmul_rn(kk[7], r6)));
+    double xd = __dadd_rn(__dmul_rn(__dmul_rn(x, cdist), icdist2), __dmul_rn(kk[2], a1));
+    xd = __dadd_rn(__dadd_rn(__dadd_rn(xd, __dmul_rn(kk[3], a2)), __dmul_rn(kk[8], r2)), __dmul_rn(kk[9], r4));
+    double yd = __dadd_rn(__dmul_rn(__dmul_rn(y, cdist), icdist2), __dmul_rn(kk[2], a3));
+    yd = __dadd_rn(__dadd_rn(__dadd_rn(yd, __dmul_rn(kk[3], a1)), __dmul_rn(kk[10], r2)), __dmul_rn(kk[11], r4));
+    const float mx = (float)__dadd_rn(__dmul_rn(xd, fx), cx), my = (float)__dadd_rn(__dmul_rn(yd, fy), cy);
+    const int tx = (int)mx, ty = (int)my; // astype(np.int32): truncation toward zero
+    if (mx <= -1.f || my <= -1.f || tx < 0 || ty < 0 || tx >= W || ty >= H) return;
+    atomicMin(&key[(size_t)ty * W + tx], (unsigned)(v * W + u));
+}
+__global__ void distort_gather_kernel(const double *__restrict__ depth, const unsigned *__restrict__ key, double *__restrict__ out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned k = key[i];
+    out[i] = k == 0xFFFFFFFFu ? 0.0 : depth[k];
+}
+} // namespace
+
+cudaError_t launch_distort_depth(b2s_ctx *c, const double *d_depth, double *d_out)
+{
+    const int W = c->rW1, H = c->rH1;
+    const size_t n = (size_t)W * H;
+    cudaError_t e = c->dkey.ensure(n * 4 + 12 * 8 + 8);
+    if (e != cudaSuccess) return e;
+    double *kk = (double *)((char *)c->dkey.p + n * 4 + (8 - (n * 4) % 8) % 8);
+    if ((e = cudaMemsetAsync(c->dkey.p, 0xFF, n * 4, c->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(kk, c->cam1_k, 12 * 8, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return e;
+    dim3 b(128), g((W + 127) / 128, H);
+    distort_scatter_kernel<<<g, b, 0, c->stream>>>(W, H, c->cam1_f[0], c->cam1_f[1], c->cam1_f[2], c->cam1_f[3], kk, c->dkey.as<unsigned>());
+    distort_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_depth, c->dkey.as<unsigned>(), d_out, n);
+    c->launches += 2;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gen_maps(b2s_ctx *c, const b2s_map_params &p, float *mapx, float *mapy, uint8_t *mask, int mW, int mH, int16_t *xy16,
                             uint16_t *fxy16)
 {

@@ -264,6 +264,13 @@ class Stereo:
         self.handle.call("b2s_set_rig_params", ctypes.byref(rp))
         self._rig_dirty = False
 
+    def _push_cam1_model(self):
+        D = np.float64(self.cam1.D).ravel()
+        k = np.zeros(12)
+        k[:min(D.size, 12)] = D[:12]
+        K = self.cam1.K
+        self.handle.call("b2s_set_cam1_model", float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), (ctypes.c_double * 12)(*k))
+
     def _push_rig(self):
         if not self._rig_dirty:
             return
@@ -291,6 +298,7 @@ class Stereo:
         rig.min_disparity = int(self.min_disparity) if getattr(self, "translation_rectify_img", None) else 0
         rig.interp = {"lanczos4": 0, "linear": 1}[self.interp]
         h.call("b2s_set_rig", ctypes.byref(rig))
+        self._push_cam1_model()
         self._rig_dirty = False
 
     @staticmethod
@@ -360,6 +368,17 @@ class Stereo:
         self.handle.call("b2s_undistort_img", _ffi.ptr(img1), cn, _ffi.ptr(out))
         return out
 
+    def distort_depth(self, depth):
+        """stereo_camera.py:433-464 on the device (the reference's version is documented as "OOM warning and very slow")."""
+        self._push_rig()
+        depth = np.ascontiguousarray(depth, np.float64)
+        w1, h1 = self.cam1.xy
+        if depth.shape != (h1, w1):
+            raise ValueError("depth must be cam1-sized %s" % ((h1, w1),))
+        out = np.empty((h1, w1), np.float64)
+        self.handle.call("b2s_distort_depth", _ffi.ptr(depth), _ffi.ptr(out))
+        return out
+
     def set_stereo_matching(self, stereo_matching, max_depth=None, translation_rectify_img=None):
         """stereo_camera.py:466-489."""
         self.stereo_matching = stereo_matching
@@ -374,8 +393,6 @@ class Stereo:
         in one C-ABI call (one upload, one stream of kernels, one download); with a foreign `MetaStereoMatching` plugin
         the rectify half and the depth half run on the device around the plugin's host call."""
         assert hasattr(self, "stereo_matching"), "Please stereo.set_stereo_matching(stereo_matching)"
-        if return_distort_depth:
-            raise NotImplementedError("distort_depth (stereo_camera.py:433-464) is a 'next' row (SURVEY.md section 8(f))")
         img1, cn = self._prep(img1)
         img2, cn2 = self._prep(img2)
         if cn != cn2:
@@ -383,7 +400,7 @@ class Stereo:
         self._check_raw(img1, img2)
         w, h = self.xy
         w1, h1 = self.cam1.xy
-        want = bool(return_unrectify_depth)
+        want = bool(return_unrectify_depth or return_distort_depth)
         sm = self.stereo_matching
         fused = (isinstance(sm, SemiGlobalBlockMatching) and sm.stereo_sgbm.handle is self.handle and sm.max_size >= max(h, w))
         self._push_rig()
@@ -397,6 +414,9 @@ class Stereo:
             unrectify_depth = np.empty((h1, w1), np.float64)
             undistort_img1 = np.empty(img1.shape, np.uint8)
             out.unrectify_depth, out.undistort_img1 = unrectify_depth.ctypes.data, undistort_img1.ctypes.data
+        if return_distort_depth:
+            distort_depth = np.empty((h1, w1), np.float64)
+            out.distort_depth = distort_depth.ctypes.data
         if fused:
             rectify_img1, rectify_img2 = np.empty(ishape, np.uint8), np.empty(ishape, np.uint8)
             out.rectify_img1, out.rectify_img2 = rectify_img1.ctypes.data, rectify_img2.ctypes.data
@@ -412,6 +432,8 @@ class Stereo:
         result.update(rectify_img1=rectify_img1, rectify_depth=rectify_depth, disparity=disparity, rectify_img2=rectify_img2)
         if want:
             result.update(unrectify_depth=unrectify_depth, undistort_img1=undistort_img1)
+        if return_distort_depth:
+            result.update(distort_img1=img1, distort_depth=distort_depth)
         return result
 
 

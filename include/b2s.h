@@ -97,6 +97,8 @@ typedef struct {
     double *unrectify_depth;              /* (H1,W1) f64 */
     uint8_t *undistort_img1;              /* (H1,W1,cn) u8 */
     int16_t *disp16;                      /* (H,W) i16: raw StereoSGBM output (debug / parity) */
+    double *distort_depth;                /* (H1,W1) f64: Stereo.distort_depth(unrectify_depth) (return_distort_depth);
+                                             needs b2s_set_cam1_model and want_unrectify */
 } b2s_depth_out;
 
 typedef struct {
@@ -153,6 +155,15 @@ int b2s_depth_from_disparity(b2s_handle h, const float *disparity, const uint8_t
 int b2s_disparity_to_depth(b2s_handle h, const float *disparity, double *depth);
 /* Stereo.unrectify_depth (stereo_camera.py:415-428): (H,W) f64 -> (H1,W1) f64. */
 int b2s_unrectify_depth(b2s_handle h, const double *rectify_depth, double *out);
+/* cam1's own intrinsics and distortion model (fx fy cx cy; k = k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4, zero-padded), used by
+ * b2s_distort_depth.  b2s_set_rig_params sets it implicitly (its `undist` map describes the same camera). */
+int b2s_set_cam1_model(b2s_handle h, double fx, double fy, double cx, double cy, const double k[12]);
+/* Stereo.distort_depth (stereo_camera.py:433-464): forward splat of the undistorted (H1,W1) f64 depth image into the raw
+ * distorted cam1 image: every pixel is projected through the distortion model exactly as cv2.undistortPoints +
+ * cv2.projectPoints do (float64, float32 where they round to float32), truncated to int; of the pixels landing on the
+ * same target the smallest source index wins (np.unique(..., return_index=True)); targets nobody hits are 0.  Source
+ * pixels that project outside the image are dropped (the reference would raise IndexError or wrap around). */
+int b2s_distort_depth(b2s_handle h, const double *unrectify_depth, double *out);
 /* Stereo.undistort_img (stereo_camera.py:430-431): (H1,W1,cn) u8 -> (H1,W1,cn) u8. */
 int b2s_undistort_img(b2s_handle h, const uint8_t *img1, int cn, uint8_t *out);
 

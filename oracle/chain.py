@@ -116,12 +116,32 @@ class RefStereo:
     def undistort_img(self, img1):
         return cv2.undistort(img1, self.K1, self.D1)
 
-    def get_depth(self, img1, img2, interp=cv2.INTER_LANCZOS4):
+    def distort_depth(self, depth):
+        """stereo_camera.py:433-464: forward splat of the undistorted depth image into the raw (distorted) cam1 image.  Every
+        pixel is projected through the distortion model (cv2.undistortPoints with no distortion, then cv2.projectPoints
+        with D), truncated to int, and of the pixels that land on the same target the one with the smallest source index
+        wins (np.unique(..., return_index=True))."""
+        w, h = self.cam1["xy"]
+        res = np.zeros((h, w), dtype=depth.dtype)
+        u, v = np.meshgrid(np.arange(w, dtype=np.int32), np.arange(h, dtype=np.int32))
+        pts = np.stack([u.ravel(), v.ravel()], -1).astype(np.float32)
+        zero = np.zeros(3, np.float32)
+        und = cv2.undistortPoints(pts, self.K1, None)
+        img_pts, _ = cv2.projectPoints(cv2.convertPointsToHomogeneous(und), zero, zero, self.K1, self.D1, und)
+        img_pts = img_pts.reshape(-1, 2).astype(np.int32)
+        uniq, index = np.unique(img_pts, axis=0, return_index=True)
+        res[uniq[:, 1], uniq[:, 0]] = depth.ravel()[index]
+        return res
+
+    def get_depth(self, img1, img2, interp=cv2.INTER_LANCZOS4, return_distort_depth=False):
         r1, r2 = self.rectify(img1, img2, interp)
         disparity = self.plugin(r1, r2)
         if self.translate:
             disparity += self.min_disparity
         disparity = self.valid1 * disparity
         depth = self.disparity_to_depth(disparity)
-        return dict(rectify_img1=r1, rectify_img2=r2, disparity=disparity, rectify_depth=depth,
-                    unrectify_depth=self.unrectify_depth(depth), undistort_img1=self.undistort_img(img1))
+        res = dict(rectify_img1=r1, rectify_img2=r2, disparity=disparity, rectify_depth=depth,
+                   unrectify_depth=self.unrectify_depth(depth), undistort_img1=self.undistort_img(img1))
+        if return_distort_depth:
+            res.update(distort_img1=img1, distort_depth=self.distort_depth(res["unrectify_depth"]))
+        return res

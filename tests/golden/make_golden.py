@@ -99,6 +99,11 @@ def main():
     np.savez_compressed(os.path.join(HERE, "rig320_d64.npz"), min_disparity=st.min_disparity,
                         **{k: (v.astype(np.float32) if v.dtype == np.float64 else v) for k, v in res.items()
                            if k in ("disparity", "rectify_depth", "unrectify_depth", "undistort_img1")})
+    # --- case D: distort_depth (stereo_camera.py:433-464) of case B's unrectify_depth, from the real reference
+    with np.errstate(all="ignore"):
+        res = st.get_depth(img1, img2, return_distort_depth=True)
+    np.savez_compressed(os.path.join(HERE, "rig320_distort.npz"), unrectify_depth=res["unrectify_depth"],
+                        distort_depth=res["distort_depth"])
     # --- case C: raw cv2.StereoSGBM outputs on a small rectified pair, both modes (pins oracle/sgbm_ref.c)
     l, r, _ = synth.rectified_pair(96, 200, 48, seed=3)
     for mode, name in ((0, "sgbm"), (1, "hh")):

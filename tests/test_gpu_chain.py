@@ -134,3 +134,25 @@ def test_device_side_map_generation(size, golden):
         else:
             assert _close_depth(np.float64(b[k]), np.float64(a[k]), 1e-3).mean() >= 0.9999 if "depth" in k else \
                 (a[k] == b[k]).mean() >= 0.999, k
+
+
+def test_distort_depth(golden_dir):
+    """Stereo.distort_depth on the device, bit-exact against the real reference's output
+    (golden), stand-alone and inside get_depth(return_distort_depth=True); 1080p against the oracle restatement."""
+    from oracle import chain
+    g = np.load(os.path.join(golden_dir, "rig320_distort.npz"))
+    rig = synth.rig_dict((320, 240))
+    for maps in ("host", "device"):
+        st = cb.Stereo.load(rig, maps=maps).set_stereo_matching(cb.SemiGlobalBlockMatching({"max_size": 4000, "num_disparities": 64}), max_depth=3.5)
+        got = st.distort_depth(g["unrectify_depth"])
+        assert got.dtype == np.float64 and np.array_equal(got, g["distort_depth"]), maps
+    img1, img2 = synth.render_rig(rig, seed=1)
+    res = st.get_depth(img1, img2, return_distort_depth=True)
+    assert set(res) >= {"distort_img1", "distort_depth", "unrectify_depth", "undistort_img1"} and res["distort_img1"] is not None
+    assert np.array_equal(res["distort_depth"], chain.RefStereo(rig).distort_depth(res["unrectify_depth"]))
+    with pytest.raises(ValueError):
+        st.distort_depth(np.zeros((10, 10)))
+    rig = synth.rig_dict((1920, 1080))
+    depth = np.random.default_rng(5).random((1080, 1920)) * 4
+    depth[depth < 0.5] = 0
+    assert np.array_equal(cb.Stereo.load(rig).distort_depth(depth), chain.RefStereo(rig).distort_depth(depth))

@@ -41,3 +41,12 @@ def test_chain_d64_matches_reference(golden_dir):
     for k in ("disparity", "rectify_depth", "unrectify_depth"):
         assert np.array_equal(res[k].astype(np.float32), g[k]), k
     assert np.array_equal(res["undistort_img1"], g["undistort_img1"])
+
+
+def test_distort_depth_matches_reference(golden_dir):
+    """oracle.chain.RefStereo.distort_depth against the real reference's Stereo.distort_depth (stereo_camera.py:433-464)."""
+    from calibrating_b200 import synth
+    from oracle import chain
+    g = np.load(os.path.join(golden_dir, "rig320_distort.npz"))
+    got = chain.RefStereo(synth.rig_dict((320, 240))).distort_depth(g["unrectify_depth"])
+    assert got.dtype == np.float64 and np.array_equal(got, g["distort_depth"])

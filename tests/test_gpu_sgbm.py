@@ -168,3 +168,24 @@ def test_textureless_and_saturated(handle):
                      speckle_window_size=200, speckle_range=2, mode=mode)
             ref = osgbm.sgbm_compute(l, r, **p)
             assert np.array_equal(cb.StereoSGBM(handle=handle, **p).compute(l, r), ref)
+
+
+def test_full_size_4k_256(handle):
+    """BASELINE config 4's geometry (3840x2160 gray, 256 disparities, 8 paths) with the BT cost (the census cost named there
+    has no oracle in this OpenCV build): strips of 25 columns, one sweep per launch, NP = 4 registers per lane.
+    Size-independent properties, and bit-exact against cv2 when it is available on the box (~25 s of CPU)."""
+    l, r, gt = synth.rectified_pair(2160, 3840, 256, seed=1, cn=1)
+    kw = dict(minDisparity=0, numDisparities=256, blockSize=5, P1=8 * 25, P2=32 * 25, disp12MaxDiff=1, uniquenessRatio=5,
+              speckleWindowSize=200, speckleRange=2, mode=1)
+    m = cb.StereoSGBM_create(handle=handle, **kw)
+    got = m.compute(l, r)
+    assert (got[:, :256] == -16).all()
+    valid = got >= 0
+    assert valid.mean() > 0.6
+    assert (np.abs(got[valid] / 16.0 - gt[valid]) <= 1).mean() > 0.95
+    assert np.array_equal(m.compute(l[::-1].copy(), r[::-1].copy()), got[::-1]), "vertical flip equivariance"
+    try:
+        import cv2
+    except ImportError:
+        return
+    assert np.array_equal(cv2.StereoSGBM_create(**kw).compute(l, r), got)

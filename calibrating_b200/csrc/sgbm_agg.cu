@@ -56,6 +56,82 @@ template <int NP> __device__ __forceinline__ void store_regs(int16_t *dst, const
     }
 }
 
+template <int NP> __device__ __forceinline__ void ldcg_regs(const int16_t *src, uint32_t (&v)[NP])
+{
+    if constexpr (NP == 1) v[0] = __ldcg((const uint32_t *)src);
+    else if constexpr (NP == 2) { uint2 t = __ldcg((const uint2 *)src); v[0] = t.x; v[1] = t.y; }
+    else if constexpr (NP == 4) { uint4 t = __ldcg((const uint4 *)src); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) v[i] = __ldcg((const uint32_t *)src + i);
+    }
+}
+template <int NP> __device__ __forceinline__ void stcg_regs(int16_t *dst, const uint32_t (&v)[NP])
+{
+    if constexpr (NP == 1) __stcg((uint32_t *)dst, v[0]);
+    else if constexpr (NP == 2) __stcg((uint2 *)dst, make_uint2(v[0], v[1]));
+    else if constexpr (NP == 4) __stcg((uint4 *)dst, make_uint4(v[0], v[1], v[2], v[3]));
+    else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) __stcg((uint32_t *)dst + i, v[i]);
+    }
+}
+// shared memory through 32-bit shared-window addresses (keeps generic->shared conversions out of the loop)
+template <int NP> __device__ __forceinline__ void lds_s(uint32_t addr, uint32_t (&v)[NP])
+{
+    if constexpr (NP == 2) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(addr) : "memory");
+    else if constexpr (NP == 4)
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr) : "memory");
+    else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[i]) : "r"(addr + 4 * i) : "memory");
+    }
+}
+template <int NP> __device__ __forceinline__ void sts_s(uint32_t addr, const uint32_t (&v)[NP])
+{
+    if constexpr (NP == 2) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(v[0]), "r"(v[1]) : "memory");
+    else if constexpr (NP == 4)
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+    else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + 4 * i), "r"(v[i]) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t saddr, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gsrc) : "memory");
+}
+
+// one step of one path: T = normalised state of the predecessor pixel (in/out), c = C of this pixel, L = L_r of this pixel
+template <int NP, bool PAD>
+__device__ __forceinline__ void sgm_step(uint32_t (&T)[NP], const uint32_t (&c)[NP], uint32_t (&L)[NP], const uint32_t (&padmask)[NP],
+                                         uint32_t P1v, uint32_t P2mP1v, int lane)
+{
+    const uint32_t BIG = 0x7FFF7FFFu;
+    uint32_t up = __shfl_up_sync(0xffffffffu, T[NP - 1], 1);
+    uint32_t dn = __shfl_down_sync(0xffffffffu, T[0], 1);
+    if (lane == 0) up = BIG;
+    if (lane == 31) dn = BIG;
+    uint32_t m = BIG;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        uint32_t lft = __byte_perm(i == 0 ? up : T[i - 1], T[i], 0x5432);      // L(d-1)
+        uint32_t rgt = __byte_perm(T[i], i == NP - 1 ? dn : T[i + 1], 0x5432); // L(d+1)
+        uint32_t t = __vimin3_s16x2(lft, rgt, P2mP1v);
+        t = __viaddmin_s16x2(t, P1v, T[i]);
+        L[i] = __vadd2(c[i], t);
+        if (PAD) L[i] |= padmask[i];
+        m = __vmins2(m, L[i]);
+    }
+    m = __vmins2(m, __byte_perm(m, m, 0x1032));                 // both halves = min over this lane's disparities
+    m = (uint32_t)__reduce_min_sync(0xffffffffu, (int)m);       // signed 32-bit min of (v,v) pairs = (min,min)
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        T[i] = L[i] - m; // both halves of L are >= their half of m: the 32-bit difference has no borrow = packed difference
+        if (PAD) T[i] |= padmask[i];
+    }
+}
+
 // WTA: 0 = store S; 1 = winner-take-all fused (A.5), S not stored; 2 = both (debug: S stays fetchable)
 template <int NP, bool PAD, int MODE, int WTA>
 __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
@@ -178,6 +254,96 @@ __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
     }
 }
 
+// Horizontal lines only (my == 0), the two scans of the production schedule: same arithmetic as agg_scan_kernel, but the
+// per-step overhead is cut to the bone (a scan line is ONE warp's in-order instruction stream of 1792 dependent steps, so
+// its length is the kernel's duration): incremental 64-bit pointers, 32-bit shared addresses, the step of sgm_step.
+template <int NP, bool PAD, int MODE, int WTA>
+__global__ void __launch_bounds__(WARPS * 32) agg_hscan_kernel(AggArgs a)
+{
+    constexpr int CH = 128 * NP;                       // bytes of one pixel's d-chunk
+    constexpr int NSRC = MODE == AGG_ACCUM2 ? 3 : (MODE == AGG_ACCUM ? 2 : 1); // C only; C and S; C, S and S2
+    constexpr int STAGE_BYTES = CH * NSRC;
+    constexpr int STAGES = Stages<NP>::value;
+    constexpr int NSEG = STAGE_BYTES / 16, NLD = (NSEG + 31) / 32;
+    extern __shared__ __align__(16) unsigned char smem[];
+
+    const int lane = threadIdx.x & 31;
+    const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int y = blockIdx.x * WARPS + wid;
+    if (y >= a.H) return;
+    const int Dp = 64 * NP, nsteps = a.width1;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem) + wid * (STAGES * STAGE_BYTES);
+    const long long stepE = (long long)a.mx * Dp; // int16 elements to the next pixel of the line
+    const long long o0 = ((long long)y * a.width1 + (a.mx > 0 ? 0 : a.width1 - 1)) * Dp;
+    const int16_t *src[NLD];
+    uint32_t dsto[NLD];
+#pragma unroll
+    for (int q = 0; q < NLD; q++) {
+        const int seg = lane + 32 * q;
+        const int which = seg / (CH / 16), r = seg % (CH / 16);
+        src[q] = (which == 0 ? a.C : (which == 1 ? (const int16_t *)a.S : a.S2)) + o0 + r * 8;
+        dsto[q] = ring + seg * 16;
+    }
+    auto issue = [&](int stage) {
+#pragma unroll
+        for (int q = 0; q < NLD; q++) {
+            if (lane + 32 * q < NSEG) cp_async16_s(dsto[q] + stage * STAGE_BYTES, src[q]);
+            src[q] += stepE;
+        }
+    };
+    uint32_t padmask[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        int d0 = (lane * NP + i) * 2;
+        padmask[i] = PAD ? ((d0 >= a.D ? 0x00007FFFu : 0u) | (d0 + 1 >= a.D ? 0x7FFF0000u : 0u)) : 0u;
+    }
+    const uint32_t P1v = (uint32_t)a.P1 * 0x10001u, P2mP1v = (uint32_t)(a.P2 - a.P1) * 0x10001u;
+    const uint32_t BIG = 0x7FFF7FFFu;
+#pragma unroll 1
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nsteps) issue(s);
+        cp_async_commit();
+    }
+    uint32_t T[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) T[i] = padmask[i];
+    int16_t *sp = a.S + o0 + lane * 2 * NP;
+    int x = a.mx > 0 ? 0 : a.width1 - 1;
+    int stage = 0, pstage = STAGES - 1;
+    const uint32_t cur0 = ring + lane * NP * 4;
+#pragma unroll 1
+    for (int k = 0; k < nsteps; k++) {
+        __syncwarp();
+        if (k + STAGES - 1 < nsteps) issue(pstage);
+        cp_async_commit();
+        cp_async_wait<STAGES - 1>();
+        __syncwarp();
+        const uint32_t cur = cur0 + stage * STAGE_BYTES;
+        uint32_t c[NP], sv[NP], L[NP], out[NP];
+        lds_s<NP>(cur, c);
+        if (MODE != AGG_INIT) lds_s<NP>(cur + CH, sv);
+        if (MODE == AGG_ACCUM2) {
+            uint32_t s2[NP];
+            lds_s<NP>(cur + 2 * CH, s2);
+#pragma unroll
+            for (int i = 0; i < NP; i++) sv[i] = __viaddmin_u16x2(sv[i], s2[i], BIG);
+        }
+        sgm_step<NP, PAD>(T, c, L, padmask, P1v, P2mP1v, lane);
+#pragma unroll
+        for (int i = 0; i < NP; i++) out[i] = (MODE != AGG_INIT) ? __viaddmin_u16x2(sv[i], L[i], BIG) : L[i];
+        if (WTA != 1) stcg_regs<NP>(sp, out);
+        if (WTA != 0) {
+            // this step's stage has been consumed: it doubles as the exchange buffer for the sub-pixel neighbours
+            uint32_t *xch = (uint32_t *)(smem + wid * (STAGES * STAGE_BYTES) + stage * STAGE_BYTES);
+            wta_pixel<NP>(out, xch, lane, x, y, a.D, a.W, a.minX1, a.minD, a.uniq, a.raw, a.disp2key);
+        }
+        sp += stepE;
+        x += a.mx;
+        pstage = stage;
+        stage = stage + 1 == STAGES ? 0 : stage + 1;
+    }
+}
+
 template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *c, const AggArgs &a)
 {
     constexpr int STAGE_BYTES = 128 * NP * (MODE == AGG_ACCUM2 ? 3 : (MODE == AGG_ACCUM ? 2 : 1));
@@ -189,7 +355,16 @@ template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *
         configured = true;
     }
     int nlines = a.my == 0 ? a.H : a.width1;
-    agg_scan_kernel<NP, PAD, MODE, WTA><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
+    if (a.my == 0 && !c->agg_legacy) {
+        static bool configured_h = false;
+        if (!configured_h) {
+            cudaError_t e = cudaFuncSetAttribute(agg_hscan_kernel<NP, PAD, MODE, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured_h = true;
+        }
+        agg_hscan_kernel<NP, PAD, MODE, WTA><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
+    } else
+        agg_scan_kernel<NP, PAD, MODE, WTA><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
     c->launches++;
     return cudaGetLastError();
 }
@@ -243,26 +418,6 @@ struct VsArgs {
 constexpr int HO_SLOTS = 4;
 constexpr int HO_SPIN_LIMIT = 1 << 18;
 
-template <int NP> __device__ __forceinline__ void ldcg_regs(const int16_t *src, uint32_t (&v)[NP])
-{
-    if constexpr (NP == 1) v[0] = __ldcg((const uint32_t *)src);
-    else if constexpr (NP == 2) { uint2 t = __ldcg((const uint2 *)src); v[0] = t.x; v[1] = t.y; }
-    else if constexpr (NP == 4) { uint4 t = __ldcg((const uint4 *)src); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-    else {
-#pragma unroll
-        for (int i = 0; i < NP; i++) v[i] = __ldcg((const uint32_t *)src + i);
-    }
-}
-template <int NP> __device__ __forceinline__ void stcg_regs(int16_t *dst, const uint32_t (&v)[NP])
-{
-    if constexpr (NP == 1) __stcg((uint32_t *)dst, v[0]);
-    else if constexpr (NP == 2) __stcg((uint2 *)dst, make_uint2(v[0], v[1]));
-    else if constexpr (NP == 4) __stcg((uint4 *)dst, make_uint4(v[0], v[1], v[2], v[3]));
-    else {
-#pragma unroll
-        for (int i = 0; i < NP; i++) __stcg((uint32_t *)dst + i, v[i]);
-    }
-}
 template <int NP> __device__ __forceinline__ void lds_regs(const uint32_t *src, uint32_t (&v)[NP])
 {
     if constexpr (NP == 2) { uint2 t = *(const uint2 *)src; v[0] = t.x; v[1] = t.y; }
@@ -329,62 +484,6 @@ template <int NP> __device__ __forceinline__ void ho_write(uint32_t *p, uint32_t
 #pragma unroll
         for (int i = 0; i < NP; i++) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p + i), "r"(v[i]) : "memory");
     }
-}
-
-// one step of one path: T = normalised state of the predecessor pixel (in/out), c = C of this pixel, L = L_r of this pixel
-template <int NP, bool PAD>
-__device__ __forceinline__ void sgm_step(uint32_t (&T)[NP], const uint32_t (&c)[NP], uint32_t (&L)[NP], const uint32_t (&padmask)[NP],
-                                         uint32_t P1v, uint32_t P2mP1v, int lane)
-{
-    const uint32_t BIG = 0x7FFF7FFFu;
-    uint32_t up = __shfl_up_sync(0xffffffffu, T[NP - 1], 1);
-    uint32_t dn = __shfl_down_sync(0xffffffffu, T[0], 1);
-    if (lane == 0) up = BIG;
-    if (lane == 31) dn = BIG;
-    uint32_t m = BIG;
-#pragma unroll
-    for (int i = 0; i < NP; i++) {
-        uint32_t lft = __byte_perm(i == 0 ? up : T[i - 1], T[i], 0x5432);      // L(d-1)
-        uint32_t rgt = __byte_perm(T[i], i == NP - 1 ? dn : T[i + 1], 0x5432); // L(d+1)
-        uint32_t t = __vimin3_s16x2(lft, rgt, P2mP1v);
-        t = __viaddmin_s16x2(t, P1v, T[i]);
-        L[i] = __vadd2(c[i], t);
-        if (PAD) L[i] |= padmask[i];
-        m = __vmins2(m, L[i]);
-    }
-    m = __vmins2(m, __byte_perm(m, m, 0x1032));                 // both halves = min over this lane's disparities
-    m = (uint32_t)__reduce_min_sync(0xffffffffu, (int)m);       // signed 32-bit min of (v,v) pairs = (min,min)
-#pragma unroll
-    for (int i = 0; i < NP; i++) {
-        T[i] = L[i] - m; // both halves of L are >= their half of m: the 32-bit difference has no borrow = packed difference
-        if (PAD) T[i] |= padmask[i];
-    }
-}
-
-// shared memory through 32-bit shared-window addresses (keeps generic->shared conversions out of the loop)
-template <int NP> __device__ __forceinline__ void lds_s(uint32_t addr, uint32_t (&v)[NP])
-{
-    if constexpr (NP == 2) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(addr) : "memory");
-    else if constexpr (NP == 4)
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr) : "memory");
-    else {
-#pragma unroll
-        for (int i = 0; i < NP; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[i]) : "r"(addr + 4 * i) : "memory");
-    }
-}
-template <int NP> __device__ __forceinline__ void sts_s(uint32_t addr, const uint32_t (&v)[NP])
-{
-    if constexpr (NP == 2) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(v[0]), "r"(v[1]) : "memory");
-    else if constexpr (NP == 4)
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
-    else {
-#pragma unroll
-        for (int i = 0; i < NP; i++) asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + 4 * i), "r"(v[i]) : "memory");
-    }
-}
-__device__ __forceinline__ void cp_async16_s(uint32_t saddr, const void *gsrc)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gsrc) : "memory");
 }
 
 __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count)
@@ -737,6 +836,7 @@ cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
     cudaError_t e;
     c->wta_fused = false;
     const int n = vsweep_cols(c);
+    c->agg_legacy = n == 0; // the legacy path keeps the generic scan kernel for every direction (it is the cross-check)
     if (n > 0) {
         a.mx = 1; a.my = 0;
         if ((e = launch_dir_np(c, a, AGG_INIT)) != cudaSuccess) return e;

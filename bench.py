@@ -145,8 +145,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs-per-step", type=int, default=4)
-    ap.add_argument("--streams", type=int, default=2)
+    ap.add_argument("--pairs-per-step", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -44,32 +44,44 @@ class DisparityBatchEngine:
         16*disparity when as_float=False.  H2D copy, kernels and D2H copy of different pairs overlap across streams."""
         n, S = len(pairs), len(self.handles)
         results = [None] * n
-        for base in range(0, n, S):
-            chunk = list(range(base, min(base + S, n)))
-            for slot, i in enumerate(chunk):
-                left, right, H, W, cn = StereoSGBM._check_pair(*pairs[i])
-                if left.ctypes.data not in _ffi._PINNED:
-                    buf = self._pinned(("l", slot), left.shape, np.uint8)
-                    np.copyto(buf, left)
-                    left = buf
-                if right.ctypes.data not in _ffi._PINNED:
-                    buf = self._pinned(("r", slot), right.shape, np.uint8)
-                    np.copyto(buf, right)
-                    right = buf
-                if out is not None:
-                    o = out[i]
-                else:
-                    o = self._pinned(("o", slot, i // S % 2), (H, W), np.float32 if as_float else np.int16)
-                h = self.handles[slot]
-                if as_float:
-                    h.call("b2s_compute_disparity_async", _ffi.ptr(left), _ffi.ptr(right), H, W, cn, None, _ffi.ptr(o))
-                else:
-                    h.call("b2s_compute_disparity_async", _ffi.ptr(left), _ffi.ptr(right), H, W, cn, _ffi.ptr(o), None)
-                results[i] = o
-            for slot, i in enumerate(chunk):
-                self.handles[slot].sync()
-                if out is None:
-                    results[i] = results[i].copy()
+        busy = [False] * S  # handle has calls in flight that use its staging buffers
+        copy_back = []
+        for i in range(n):
+            slot = i % S
+            h = self.handles[slot]
+            left, right, H, W, cn = StereoSGBM._check_pair(*pairs[i])
+            staged = left.ctypes.data not in _ffi._PINNED or right.ctypes.data not in _ffi._PINNED or out is None
+            if staged and busy[slot]:
+                h.sync()  # the previous call of this handle still reads / writes the per-slot staging buffers
+                busy[slot] = False
+                for j, o in copy_back:
+                    if j % S == slot and results[j] is o:
+                        results[j] = o.copy()
+            if left.ctypes.data not in _ffi._PINNED:
+                buf = self._pinned(("l", slot), left.shape, np.uint8)
+                np.copyto(buf, left)
+                left = buf
+            if right.ctypes.data not in _ffi._PINNED:
+                buf = self._pinned(("r", slot), right.shape, np.uint8)
+                np.copyto(buf, right)
+                right = buf
+            if out is not None:
+                o = out[i]
+            else:
+                o = self._pinned(("o", slot), (H, W), np.float32 if as_float else np.int16)
+                copy_back.append((i, o))
+            # calls on one handle are stream-ordered (upload, kernels, download), so pinned caller buffers need no sync in between
+            if as_float:
+                h.call("b2s_compute_disparity_async", _ffi.ptr(left), _ffi.ptr(right), H, W, cn, None, _ffi.ptr(o))
+            else:
+                h.call("b2s_compute_disparity_async", _ffi.ptr(left), _ffi.ptr(right), H, W, cn, _ffi.ptr(o), None)
+            results[i] = o
+            busy[slot] = busy[slot] or staged
+        for h in self.handles:
+            h.sync()
+        for j, o in copy_back:
+            if results[j] is o:
+                results[j] = o.copy()
         return results
 
     def compute_batch_dev(self, dev_pairs, H, W, cn, dev_out16):

@@ -6,9 +6,9 @@ Public surface mirrors the reference's names for this path:
     StereoSGBM_create                (keyword-compatible with cv2.StereoSGBM_create, MODE_SGBM / MODE_HH)
 Everything numeric runs in libb2s.so (hand-written sm_100a CUDA behind the C-ABI of include/b2s.h).
 """
-from .stereo_matching import (MODE_HH, MODE_SGBM, B200StereoMatching, MetaStereoMatching, SemiGlobalBlockMatching,
+from .stereo_matching import (COST_BT, COST_CENSUS, MODE_HH, MODE_SGBM, B200StereoMatching, MetaStereoMatching, SemiGlobalBlockMatching,
                               StereoSGBM, StereoSGBM_create)
 from .stereo_camera import Cam, Stereo
 
 __all__ = ["Stereo", "Cam", "MetaStereoMatching", "SemiGlobalBlockMatching", "B200StereoMatching", "StereoSGBM",
-           "StereoSGBM_create", "MODE_SGBM", "MODE_HH"]
+           "StereoSGBM_create", "MODE_SGBM", "MODE_HH", "COST_BT", "COST_CENSUS"]

@@ -18,7 +18,7 @@ class B2SError(RuntimeError):
 class SgbmParams(ctypes.Structure):
     _fields_ = [(n, c_int) for n in (
         "min_disparity", "num_disparities", "block_size", "P1", "P2", "disp12_max_diff", "pre_filter_cap",
-        "uniqueness_ratio", "speckle_window_size", "speckle_range", "mode")]
+        "uniqueness_ratio", "speckle_window_size", "speckle_range", "mode", "cost")]
 
 
 class Rig(ctypes.Structure):

@@ -118,6 +118,7 @@ int b2s_set_sgbm_params(b2s_handle c, const b2s_sgbm_params *p)
     if (p->num_disparities > 256) return fail(c, B2S_EINVAL, "numDisparities > 256 is not supported yet (got %d)", p->num_disparities);
     if (p->min_disparity < 0) return fail(c, B2S_EINVAL, "negative minDisparity is not supported (got %d)", p->min_disparity);
     if (p->mode != 0 && p->mode != 1) return fail(c, B2S_EINVAL, "mode must be 0 (MODE_SGBM) or 1 (MODE_HH), got %d", p->mode);
+    if (p->cost != 0 && p->cost != 1) return fail(c, B2S_EINVAL, "cost must be 0 (Birchfield-Tomasi, cv2) or 1 (census), got %d", p->cost);
     int P1 = p->P1 > 0 ? p->P1 : 2;
     int P2 = p->P2 > 0 ? p->P2 : 5;
     if (P2 < P1 + 1) P2 = P1 + 1;
@@ -135,6 +136,7 @@ static int make_geom(b2s_ctx *c, int H, int W, int cn)
 {
     if (!c->have_prm) return fail(c, B2S_ESTATE, "b2s_set_sgbm_params has not been called");
     if (cn != 1 && cn != 3) return fail(c, B2S_EINVAL, "images must have 1 or 3 channels (got %d)", cn);
+    if (c->prm.cost == 1 && cn != 1) return fail(c, B2S_EINVAL, "the census cost takes gray images (got %d channels)", cn);
     if (H <= 0 || W <= 0 || W > 65535) return fail(c, B2S_EINVAL, "bad image size %dx%d", W, H);
     const b2s_sgbm_params &p = c->prm;
     SgbmGeom g;

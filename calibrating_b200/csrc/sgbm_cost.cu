@@ -155,6 +155,46 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
     }
 }
 
+// ---- census cost (b2s_sgbm_params.cost = 1; this engine's own definition, see oracle/sgbm_ref.c: census_desc) --------------
+// descriptor = 62 bits, one per neighbour of the 9 (wide) x 7 (tall) window except the centre, row-major, bit = neighbour <
+// centre, coordinates clamped to the image.
+__global__ void census_kernel(const uint8_t *__restrict__ img, unsigned long long *__restrict__ desc, int H, int W)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const int c = img[(size_t)y * W + x];
+    unsigned long long bits = 0;
+#pragma unroll
+    for (int dy = -3; dy <= 3; dy++) {
+        const uint8_t *row = img + (size_t)clampi(y + dy, 0, H - 1) * W;
+#pragma unroll
+        for (int dx = -4; dx <= 4; dx++) {
+            if (dy == 0 && dx == 0) continue;
+            bits = (bits << 1) | (unsigned long long)(row[clampi(x + dx, 0, W - 1)] < c);
+        }
+    }
+    desc[(size_t)y * W + x] = bits;
+}
+// C(y, x1, d) = popcount(descL(x) ^ descR(x - d)); warp = cost column, lane = disparity pairs, written as packed int16x2
+__global__ void __launch_bounds__(256) census_cost_kernel(const unsigned long long *__restrict__ dl, const unsigned long long *__restrict__ dr,
+                                                          uint32_t *__restrict__ C, SgbmGeom g)
+{
+    const int lane = threadIdx.x & 31, y = blockIdx.y;
+    const int x1 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (x1 >= g.width1) return;
+    const int x = x1 + g.minX1, DW = g.Dp / 2;
+    const unsigned long long l = dl[(size_t)y * g.W + x];
+    const unsigned long long *rrow = dr + (size_t)y * g.W;
+    uint32_t *out = C + ((size_t)y * g.width1 + x1) * DW;
+    for (int q = lane; q < DW; q += 32) {
+        const int d0 = 2 * q;
+        uint32_t v = 0;
+        if (d0 < g.D) v = __popcll(l ^ rrow[x - (d0 + g.minD)]);
+        if (d0 + 1 < g.D) v |= (uint32_t)__popcll(l ^ rrow[x - (d0 + 1 + g.minD)]) << 16;
+        out[q] = v; // padded d-lanes are zero in C
+    }
+}
+
 // C[y] = sum_{k=-SH2..SH2} hs[clamp(y+k, 0, H-1)]; thread = 8 consecutive int16 (uint4), band of rows per blockIdx.y
 constexpr int VBAND = 32;
 __global__ void vsum_kernel(const uint4 *__restrict__ hs, uint4 *__restrict__ C, int H, size_t row_vec, int SH2)
@@ -181,6 +221,16 @@ __global__ void vsum_kernel(const uint4 *__restrict__ hs, uint4 *__restrict__ C,
 cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t *d_right)
 {
     const SgbmGeom &g = c->g;
+    if (c->prm.cost == 1) { // census: descriptors live in the (8 bytes per gray pixel) plane buffers
+        dim3 b(128), gd((g.W + 127) / 128, g.H);
+        unsigned long long *DL = c->planesL.as<unsigned long long>(), *DR = c->planesR.as<unsigned long long>();
+        census_kernel<<<gd, b, 0, c->stream>>>(d_left, DL, g.H, g.W);
+        census_kernel<<<gd, b, 0, c->stream>>>(d_right, DR, g.H, g.W);
+        dim3 gc((g.width1 + 7) / 8, g.H);
+        census_cost_kernel<<<gc, 256, 0, c->stream>>>(DL, DR, c->C.as<uint32_t>(), g);
+        c->launches += 3;
+        return cudaGetLastError();
+    }
     const int NPL = 2 * g.cn;
     dim3 pb(128), pg((g.W + 127) / 128, g.H);
     uchar4 *PL = c->planesL.as<uchar4>(), *PR = c->planesR.as<uchar4>();

@@ -18,7 +18,8 @@ MODE_SGBM, MODE_HH = 0, 1
 # calibrating/stereo_matching.py:29-58
 REFERENCE_DEFAULTS = dict(min_disparity=2, num_disparities=218, block_size=11, uniqueness_ratio=5, speckle_window_size=200,
                           speckle_range=2, disp12_max_diff=0, P1=8 * 1 * 11 * 11, P2=32 * 1 * 11 * 11, pre_filter_cap=0,
-                          mode=MODE_SGBM)
+                          mode=MODE_SGBM, cost=0)
+COST_BT, COST_CENSUS = 0, 1  # cost: 0 = cv2's Birchfield-Tomasi + block sum; 1 = 9x7 census / Hamming (extension, gray images)
 
 
 class MetaStereoMatching:
@@ -39,7 +40,7 @@ class StereoSGBM:
         if unknown:
             raise TypeError("unknown StereoSGBM parameters: %s" % sorted(unknown))
         self.params = dict(min_disparity=0, num_disparities=16, block_size=3, P1=0, P2=0, disp12_max_diff=0, pre_filter_cap=0,
-                           uniqueness_ratio=0, speckle_window_size=0, speckle_range=0, mode=MODE_SGBM)
+                           uniqueness_ratio=0, speckle_window_size=0, speckle_range=0, mode=MODE_SGBM, cost=0)
         self.params.update(params)
         self.handle = handle or _ffi.Handle(device)
         self._push()
@@ -80,11 +81,11 @@ class StereoSGBM:
 
 
 def StereoSGBM_create(minDisparity=0, numDisparities=16, blockSize=3, P1=0, P2=0, disp12MaxDiff=0, preFilterCap=0,
-                      uniquenessRatio=0, speckleWindowSize=0, speckleRange=0, mode=MODE_SGBM, device=0, handle=None):
-    """Keyword-compatible with cv2.StereoSGBM_create (MODE_SGBM=0 and MODE_HH=1 only)."""
+                      uniquenessRatio=0, speckleWindowSize=0, speckleRange=0, mode=MODE_SGBM, device=0, handle=None, cost=0):
+    """Keyword-compatible with cv2.StereoSGBM_create (MODE_SGBM=0 and MODE_HH=1 only); cost=COST_CENSUS is an extension."""
     return StereoSGBM(device=device, handle=handle, min_disparity=minDisparity, num_disparities=numDisparities, block_size=blockSize,
                       P1=P1, P2=P2, disp12_max_diff=disp12MaxDiff, pre_filter_cap=preFilterCap, uniqueness_ratio=uniquenessRatio,
-                      speckle_window_size=speckleWindowSize, speckle_range=speckleRange, mode=mode)
+                      speckle_window_size=speckleWindowSize, speckle_range=speckleRange, mode=mode, cost=cost)
 
 
 def _resize(img, arg):

@@ -45,6 +45,10 @@ typedef struct {
     int min_disparity, num_disparities, block_size;
     int P1, P2, disp12_max_diff, pre_filter_cap, uniqueness_ratio;
     int speckle_window_size, speckle_range, mode;
+    /* Extension (not in cv2, parity unpinned: BASELINE config 4): 0 = cv2's Birchfield-Tomasi cost + block sum,
+     * 1 = 9x7 census transform / Hamming distance, gray images only, block_size unused.  Everything after the cost volume
+     * (aggregation, winner-take-all, L/R check, median, speckle) is the same code. */
+    int cost;
 } b2s_sgbm_params;
 
 /* Per-rig constants produced once on the host by Stereo._get_undistort_rectify_map

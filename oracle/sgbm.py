@@ -14,7 +14,7 @@ MODE_SGBM, MODE_HH = 0, 1
 class SgbmParams(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in (
         "min_disparity", "num_disparities", "block_size", "P1", "P2", "disp12_max_diff",
-        "pre_filter_cap", "uniqueness_ratio", "speckle_window_size", "speckle_range", "mode")]
+        "pre_filter_cap", "uniqueness_ratio", "speckle_window_size", "speckle_range", "mode", "cost")]
 
 
 _lib = None
@@ -34,8 +34,9 @@ def _p(a):
 
 def sgbm_compute(left, right, *, min_disparity=0, num_disparities=16, block_size=3, P1=0, P2=0,
                  disp12_max_diff=0, pre_filter_cap=0, uniqueness_ratio=0, speckle_window_size=0,
-                 speckle_range=0, mode=MODE_SGBM, want_volumes=False, want_raw=False):
-    """Same keyword meaning as cv2.StereoSGBM_create.  Returns int16 (H,W) disparity*16, or a dict
+                 speckle_range=0, mode=MODE_SGBM, cost=0, want_volumes=False, want_raw=False):
+    """Same keyword meaning as cv2.StereoSGBM_create (cost=1: 9x7 census / Hamming cost, this engine's own definition,
+    not in cv2 -- parity unpinned).  Returns int16 (H,W) disparity*16, or a dict
     with the C / S volumes (H, width1, D) and the pre-median disparity when asked."""
     left = np.ascontiguousarray(left, np.uint8)
     right = np.ascontiguousarray(right, np.uint8)
@@ -43,7 +44,7 @@ def sgbm_compute(left, right, *, min_disparity=0, num_disparities=16, block_size
     H, W = left.shape[:2]
     cn = 1 if left.ndim == 2 else left.shape[2]
     prm = SgbmParams(min_disparity, num_disparities, block_size, P1, P2, disp12_max_diff,
-                     pre_filter_cap, uniqueness_ratio, speckle_window_size, speckle_range, mode)
+                     pre_filter_cap, uniqueness_ratio, speckle_window_size, speckle_range, mode, cost)
     disp = np.empty((H, W), np.int16)
     width1 = W - (min_disparity + num_disparities)
     C = S = raw = None

@@ -22,6 +22,7 @@ typedef struct {
     int min_disparity, num_disparities, block_size;
     int P1, P2, disp12_max_diff, pre_filter_cap, uniqueness_ratio;
     int speckle_window_size, speckle_range, mode; /* 0 = MODE_SGBM (5 paths), 1 = MODE_HH (8 paths) */
+    int cost; /* 0 = Birchfield-Tomasi + box sum (cv2); 1 = 9x7 census / Hamming (BASELINE config 4; NOT in cv2: parity unpinned) */
 } sgbm_params;
 
 static inline int imin(int a, int b) { return a < b ? a : b; }
@@ -57,6 +58,22 @@ static void build_planes(const uint8_t *img, int H, int W, int cn, int y, int ft
             hi[(size_t)p * W + x] = (uint8_t)imax(imax(ul, ur), u);
         }
     }
+}
+
+/* Census cost (cost = 1), this engine's own definition (there is no reference implementation: parity unpinned):
+ * descriptor of a gray pixel = 62 bits, one per neighbour of the 9 (wide) x 7 (tall) window except the centre, row-major,
+ * bit = neighbour < centre, coordinates clamped to the image; C(x, d) = popcount(descL(x) ^ descR(x - d)), no box sum. */
+static uint64_t census_desc(const uint8_t *img, int H, int W, int y, int x)
+{
+    uint64_t bits = 0;
+    int c = img[(size_t)y * W + x];
+    for (int dy = -3; dy <= 3; dy++)
+        for (int dx = -4; dx <= 4; dx++) {
+            if (dy == 0 && dx == 0) continue;
+            int v = img[(size_t)clampi(y + dy, 0, H - 1) * W + clampi(x + dx, 0, W - 1)];
+            bits = (bits << 1) | (uint64_t)(v < c);
+        }
+    return bits;
 }
 
 /* A.4 one step of the path recurrence.  Lp/Ln are D-long; minLp is min over Lp. returns min over Ln. */
@@ -150,9 +167,21 @@ int oracle_sgbm_compute(const uint8_t *left, const uint8_t *right, int H, int W,
     if (W - maxD <= SW2 || D <= 0) return -1;
 
     size_t row = (size_t)width1 * D, vol = row * H;
-    cost_t *hs = (cost_t *)malloc(vol * sizeof(cost_t));
     cost_t *Cv = (cost_t *)malloc(vol * sizeof(cost_t));
     cost_t *Sv = (cost_t *)calloc(vol, sizeof(cost_t));
+    if (prm->cost == 1) {
+        if (cn != 1) { free(Cv); free(Sv); return -2; }
+        uint64_t *cl = (uint64_t *)malloc((size_t)W * 8), *cr = (uint64_t *)malloc((size_t)W * 8);
+        for (int y = 0; y < H; y++) {
+            for (int x = 0; x < W; x++) { cl[x] = census_desc(left, H, W, y, x); cr[x] = census_desc(right, H, W, y, x); }
+            for (int x = minX1; x < maxX1; x++)
+                for (int d = minD; d < maxD; d++)
+                    Cv[(size_t)y * row + (size_t)(x - minX1) * D + (d - minD)] = (cost_t)__builtin_popcountll(cl[x] ^ cr[x - d]);
+        }
+        free(cl); free(cr);
+    } else if (prm->cost != 0) { free(Cv); free(Sv); return -2; }
+    else {
+    cost_t *hs = (cost_t *)malloc(vol * sizeof(cost_t));
     int np = 2 * cn;
     uint8_t *lv = (uint8_t *)malloc((size_t)np * W * 3), *rv = (uint8_t *)malloc((size_t)np * W * 3);
     uint8_t *llo = lv + (size_t)np * W, *lhi = llo + (size_t)np * W;
@@ -196,6 +225,7 @@ int oracle_sgbm_compute(const uint8_t *left, const uint8_t *right, int H, int W,
         }
     }
     free(hs); free(pix); free(lv); free(rv);
+    }
 
     /* A.4 aggregation */
     int16_t *raw = (int16_t *)malloc((size_t)H * W * sizeof(int16_t));

@@ -31,7 +31,7 @@ def test_header_symbols_exported(lib):
 
 def test_struct_layouts_match_header():
     import ctypes
-    assert ctypes.sizeof(_ffi.SgbmParams) == 11 * 4
+    assert ctypes.sizeof(_ffi.SgbmParams) == 12 * 4
     assert ctypes.sizeof(_ffi.DepthOut) == 8 * 8
     assert ctypes.sizeof(_ffi.Timing) == 7 * 4 + 2 * 4
     assert ctypes.sizeof(_ffi.Rig) == 6 * 4 + 9 * 8 + 5 * 8 + 2 * 4

@@ -217,3 +217,39 @@ def test_batch_engine_streams():
             assert np.array_equal(g, f)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_census_cost_vs_own_restatement(handle, seed):
+    """cost=COST_CENSUS (BASELINE config 4's cost function).  cv2 has no census matcher, so parity is UNPINNED: the CUDA path is
+    compared bit for bit with this repo's own C restatement (oracle/sgbm_ref.c, cost = 1), and with the ground truth."""
+    rng = np.random.default_rng(500 + seed)
+    D = int(rng.choice([16, 48, 64, 100, 128, 256]))
+    minD = int(rng.choice([0, 3]))
+    h, w = int(rng.integers(12, 60)), int(rng.integers(D + minD + 12, D + minD + 120))
+    p = dict(min_disparity=minD, num_disparities=D, block_size=5, P1=10, P2=120, disp12_max_diff=1, uniqueness_ratio=int(rng.choice([0, 5, 10])),
+             speckle_window_size=int(rng.choice([0, 50])), speckle_range=2, mode=seed % 2, cost=cb.COST_CENSUS)
+    l, r, _ = synth.rectified_pair(h, w, D, seed, 1)
+    ref = osgbm.sgbm_compute(l, r, want_volumes=True, **p)
+    got = cb.StereoSGBM(handle=handle, **p).compute(l, r)
+    assert np.array_equal(handle.fetch_volume(0), ref["C"]), "census cost volume"
+    assert np.array_equal(handle.fetch_volume(1), ref["S"]), "aggregated volume"
+    assert np.array_equal(got, ref["disp"])
+    with pytest.raises(ValueError, match="gray"):
+        cb.StereoSGBM(handle=handle, **p).compute(np.zeros((h, w, 3), np.uint8), np.zeros((h, w, 3), np.uint8))
+
+
+def test_census_4k_256_accuracy(handle):
+    """BASELINE config 4 as named: 3840x2160 gray, 256 disparities, census cost, 8 paths; accuracy against the synthetic
+    ground truth (parity unpinned, see above) and the size-independent properties."""
+    l, r, gt = synth.rectified_pair(2160, 3840, 256, seed=2, cn=1)
+    m = cb.StereoSGBM_create(minDisparity=0, numDisparities=256, blockSize=5, P1=10, P2=120, disp12MaxDiff=1, uniquenessRatio=5,
+                             speckleWindowSize=200, speckleRange=2, mode=cb.MODE_HH, cost=cb.COST_CENSUS, handle=handle)
+    got = m.compute(l, r)
+    assert (got[:, :256] == -16).all()
+    valid = got >= 0
+    assert valid.mean() > 0.6
+    assert (np.abs(got[valid] / 16.0 - gt[valid]) <= 1).mean() > 0.97
+    assert np.array_equal(m.compute(l[::-1].copy(), r[::-1].copy()), got[::-1]), "vertical flip equivariance"
+    t = handle.timings()
+    print("census 4K/256 stage ms:", {k: round(v, 3) for k, v in t.items() if k.endswith("_ms")})

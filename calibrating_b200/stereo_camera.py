@@ -245,7 +245,7 @@ class Stereo:
         return _ffi.MapParams(int(size[0]), int(size[1]), K[0, 0], K[1, 1], K[0, 2], K[1, 2], (ctypes.c_double * 12)(*k),
                               (ctypes.c_double * 9)(*iR.ravel()))
 
-    def _push_rig_params(self):
+    def _push_rig_params(self, handle=None):
         w1, h1 = self.cam1.xy
         rp = _ffi.RigParams()
         rp.W, rp.H = self.xy
@@ -261,22 +261,27 @@ class Stereo:
         rp.max_depth = float(self.get_max_depth())
         rp.min_disparity = int(self.min_disparity) if getattr(self, "translation_rectify_img", None) else 0
         rp.interp = {"lanczos4": 0, "linear": 1}[self.interp]
-        self.handle.call("b2s_set_rig_params", ctypes.byref(rp))
-        self._rig_dirty = False
+        (handle or self.handle).call("b2s_set_rig_params", ctypes.byref(rp))
+        if handle is None:
+            self._rig_dirty = False
 
-    def _push_cam1_model(self):
+    def _push_cam1_model(self, handle=None):
         D = np.float64(self.cam1.D).ravel()
         k = np.zeros(12)
         k[:min(D.size, 12)] = D[:12]
         K = self.cam1.K
-        self.handle.call("b2s_set_cam1_model", float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), (ctypes.c_double * 12)(*k))
+        (handle or self.handle).call("b2s_set_cam1_model", float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]),
+                                     (ctypes.c_double * 12)(*k))
 
-    def _push_rig(self):
-        if not self._rig_dirty:
-            return
+    def _push_rig(self, handle=None):
+        """Upload the per-rig constants to the engine (once per rig and handle)."""
+        if handle is None:
+            if not self._rig_dirty:
+                return
+            self._batch = None  # (the handles of get_depth_batch carry the old rig)
         if self.maps == "device":
-            return self._push_rig_params()
-        h = self.handle
+            return self._push_rig_params(handle)
+        h = handle or self.handle
         m1x, m1y = (np.ascontiguousarray(m, np.float32) for m in self.undistort_rectify_map1)
         m2x, m2y = (np.ascontiguousarray(m, np.float32) for m in self.undistort_rectify_map2)
         mask = np.ascontiguousarray(self.rectify_valid_mask1, np.uint8)
@@ -298,8 +303,9 @@ class Stereo:
         rig.min_disparity = int(self.min_disparity) if getattr(self, "translation_rectify_img", None) else 0
         rig.interp = {"lanczos4": 0, "linear": 1}[self.interp]
         h.call("b2s_set_rig", ctypes.byref(rig))
-        self._push_cam1_model()
-        self._rig_dirty = False
+        self._push_cam1_model(handle)
+        if handle is None:
+            self._rig_dirty = False
 
     @staticmethod
     def _get_img(path_or_np):
@@ -435,6 +441,81 @@ class Stereo:
         if return_distort_depth:
             result.update(distort_img1=img1, distort_depth=distort_depth)
         return result
+
+
+    # ---- throughput: several pairs in flight (not in the reference) -------------------------------
+    def get_depth_batch(self, pairs, streams=4, keys=("unrectify_depth",)):
+        """`get_depth` for a list of (img1, img2) with `streams` engine handles (= CUDA streams) in flight: upload, the ~20
+        kernels and the download of different pairs overlap.  Needs the built-in `SemiGlobalBlockMatching` at full resolution
+        (the one-call path of `get_depth`).  keys: which result arrays to return, any of rectify_img1, rectify_img2, disparity,
+        rectify_depth, unrectify_depth, undistort_img1, distort_depth.  Returns a list of dicts."""
+        assert hasattr(self, "stereo_matching"), "Please stereo.set_stereo_matching(stereo_matching)"
+        sm = self.stereo_matching
+        w, h = self.xy
+        w1, h1 = self.cam1.xy
+        if not (isinstance(sm, SemiGlobalBlockMatching) and sm.max_size >= max(h, w)):
+            raise ValueError("get_depth_batch needs the built-in SemiGlobalBlockMatching at full resolution (max_size >= image size)")
+        self._push_rig()
+        batch = getattr(self, "_batch", None)
+        if batch is None or len(batch) != streams:
+            from .stereo_matching import StereoSGBM
+            batch = []
+            for _ in range(int(streams)):
+                hd = _ffi.Handle(self.device)
+                StereoSGBM(handle=hd, **sm.stereo_sgbm.params)
+                self._push_rig(hd)
+                batch.append(dict(handle=hd, pin={}, pending=None))
+            self._batch = batch
+        want = int(any(k in keys for k in ("unrectify_depth", "undistort_img1", "distort_depth")))
+        results = [None] * len(pairs)
+
+        def collect(slot):
+            b = batch[slot]
+            if b["pending"] is None:
+                return
+            b["handle"].sync()
+            i, bufs = b["pending"]
+            results[i] = {k: v.copy() for k, v in bufs.items()}
+            if "distort_depth" in keys:
+                results[i]["distort_img1"] = pairs[i][0]
+            b["pending"] = None
+
+        for i, (img1, img2) in enumerate(pairs):
+            slot = i % len(batch)
+            collect(slot)
+            b = batch[slot]
+            img1, cn = self._prep(img1)
+            img2, cn2 = self._prep(img2)
+            if cn != cn2:
+                raise ValueError("img1/img2 channel counts differ")
+            self._check_raw(img1, img2)
+            ishape = (h, w) if img1.ndim == 2 else (h, w, cn)
+            spec = dict(rectify_img1=(ishape, np.uint8), rectify_img2=(ishape, np.uint8), disparity=((h, w), np.float32),
+                        rectify_depth=((h, w), np.float64), unrectify_depth=((h1, w1), np.float64), undistort_img1=(img1.shape, np.uint8),
+                        distort_depth=((h1, w1), np.float64))
+            out, bufs = _ffi.DepthOut(), {}
+
+            def pinned(name, shape, dtype):
+                a = b["pin"].get(name)
+                if a is None or a.shape != tuple(shape) or a.dtype != np.dtype(dtype):
+                    if a is not None:
+                        _ffi.pinned_free(a)
+                    a = b["pin"][name] = _ffi.pinned_empty(shape, dtype)
+                return a
+
+            for k in keys:
+                if k not in spec:
+                    raise ValueError("unknown result key %r" % (k,))
+                bufs[k] = pinned(k, *spec[k])
+                setattr(out, k, bufs[k].ctypes.data)
+            in1, in2 = pinned("_in1", img1.shape, np.uint8), pinned("_in2", img2.shape, np.uint8)
+            np.copyto(in1, img1)
+            np.copyto(in2, img2)
+            b["handle"].call("b2s_get_depth_async", _ffi.ptr(in1), _ffi.ptr(in2), cn, want, ctypes.byref(out))
+            b["pending"] = (i, bufs)
+        for slot in range(len(batch)):
+            collect(slot)
+        return results
 
 
 __all__ = ["Stereo", "Cam", "MetaStereoMatching", "SemiGlobalBlockMatching"]

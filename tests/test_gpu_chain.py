@@ -156,3 +156,23 @@ def test_distort_depth(golden_dir):
     depth = np.random.default_rng(5).random((1080, 1920)) * 4
     depth[depth < 0.5] = 0
     assert np.array_equal(cb.Stereo.load(rig).distort_depth(depth), chain.RefStereo(rig).distort_depth(depth))
+
+
+@pytest.mark.parametrize("maps", ["host", "device"])
+def test_get_depth_batch(maps):
+    """Stereo.get_depth_batch: several pairs in flight on several handles give exactly get_depth's arrays, in order."""
+    rig = synth.rig_dict((320, 240))
+    st = cb.Stereo.load(rig, maps=maps).set_stereo_matching(cb.SemiGlobalBlockMatching({"max_size": 4000, "num_disparities": 64}), max_depth=3.5)
+    pairs = [synth.render_rig(rig, seed=s) for s in range(5)]
+    keys = ("disparity", "unrectify_depth", "undistort_img1", "rectify_img2", "distort_depth")
+    got = st.get_depth_batch(pairs, streams=3, keys=keys)
+    assert len(got) == 5
+    for (a, b), g in zip(pairs, got):
+        ref = st.get_depth(a, b, return_distort_depth=True)
+        for k in keys:
+            assert g[k].dtype == ref[k].dtype and np.array_equal(g[k], ref[k]), k
+    st.set_stereo_matching(cb.SemiGlobalBlockMatching({"max_size": 4000, "num_disparities": 48}), max_depth=3.0)  # new rig constants
+    g2 = st.get_depth_batch(pairs[:2], streams=3, keys=("unrectify_depth",))
+    assert np.array_equal(g2[1]["unrectify_depth"], st.get_depth(*pairs[1])["unrectify_depth"])
+    with pytest.raises(ValueError):
+        st.get_depth_batch(pairs[:1], keys=("nope",))

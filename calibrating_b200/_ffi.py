@@ -76,6 +76,8 @@ SIGNATURES = {
     "b2s_undistort_img": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "b2s_set_cam1_model": (c_int, [c_void_p, c_double, c_double, c_double, c_double, ctypes.POINTER(c_double)]),
     "b2s_distort_depth": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "b2s_project_depth": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, ctypes.POINTER(c_double), ctypes.POINTER(c_double),
+                                  ctypes.POINTER(c_double), c_int, c_int, c_void_p]),
     "b2s_set_option": (c_int, [c_void_p, c_int, c_int]),
     "b2s_volume_dims": (c_int, [c_void_p] + [ctypes.POINTER(c_int)] * 4),
     "b2s_debug_fetch": (c_int, [c_void_p, c_int, c_void_p, c_size_t]),

@@ -80,7 +80,7 @@ int b2s_destroy(b2s_handle c)
     DevBuf *bufs[] = {&c->left, &c->right, &c->planesL, &c->planesR, &c->C, &c->S, &c->S2, &c->raw, &c->disp16, &c->disp2key, &c->labels,
                       &c->sizes, &c->med, &c->dispf, &c->agg_ho, &c->map1x, &c->map1y, &c->map2x, &c->map2y, &c->vmask, &c->umapx, &c->umapy,
                       &c->und_xy, &c->und_fxy, &c->img1, &c->img2, &c->rect1, &c->rect2, &c->und1, &c->dispfinal, &c->rdepth,
-                      &c->udepth, &c->lanczos_tab, &c->stage_f32, &c->dkey, &c->ddepth};
+                      &c->udepth, &c->lanczos_tab, &c->stage_f32, &c->dkey, &c->ddepth, &c->pkey, &c->pin, &c->pout};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -319,6 +319,23 @@ int b2s_set_rig_params(b2s_handle c, const b2s_rig_params *r)
     CK(c, c->dispfinal.ensure(n * 4));
     CK(c, c->rdepth.ensure(n * 8));
     CK(c, c->udepth.ensure(n1 * 8));
+    return B2S_OK;
+}
+
+int b2s_project_depth(b2s_handle c, const double *depth2, int W2, int H2, double rate, const double K2inv[9], const double T[16],
+                      const double K1[9], int W1, int H1, double *out)
+{
+    if (!c || !depth2 || !K2inv || !T || !K1 || !out) return B2S_EINVAL;
+    if (W2 <= 0 || H2 <= 0 || W1 <= 0 || H1 <= 0 || !(rate > 0) || rate > 64) return fail(c, B2S_EINVAL, "b2s_project_depth: bad sizes or rate");
+    CK(c, cudaSetDevice(c->device));
+    const size_t n2 = (size_t)W2 * H2, n1 = (size_t)W1 * H1;
+    CK(c, c->pin.ensure(n2 * 8));
+    CK(c, c->pout.ensure(n1 * 8));
+    CK(c, c->pkey.ensure(n1 * 8));
+    CK(c, cudaMemcpyAsync(c->pin.p, depth2, n2 * 8, cudaMemcpyDefault, c->stream));
+    CK(c, launch_project_depth(c, c->pin.as<double>(), W2, H2, rate, K2inv, T, K1, W1, H1, c->pkey.as<unsigned long long>(), c->pout.as<double>()));
+    CK(c, cudaMemcpyAsync(out, c->pout.p, n1 * 8, cudaMemcpyDefault, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
     return B2S_OK;
 }
 

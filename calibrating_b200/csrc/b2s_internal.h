@@ -78,6 +78,7 @@ struct b2s_ctx {
     DevBuf img1, img2, rect1, rect2, und1; // raw inputs and remapped outputs
     DevBuf dispfinal, rdepth, udepth;      // (H,W) f32, (H,W) f64, (H1,W1) f64
     DevBuf lanczos_tab;                    // (1024, 8, 8) int16
+    DevBuf pkey, pin, pout;                // project_depth: winner key per target pixel, staged input / output
     DevBuf dkey, ddepth;                   // distort_depth: winner index per target pixel (+ the 12 coefficients); (H1,W1) f64 result
     bool have_cam1 = false;
     double cam1_f[4] = {0, 0, 0, 0}, cam1_k[12] = {0};
@@ -108,6 +109,8 @@ cudaError_t launch_undistort_u8(b2s_ctx *c, const uint8_t *src, int H, int W, in
                                 uint8_t *dst);
 cudaError_t launch_depth(b2s_ctx *c, const float *d_disp_in, int add_min_disp, int want_unrectify);
 cudaError_t launch_distort_depth(b2s_ctx *c, const double *d_depth, double *d_out);
+cudaError_t launch_project_depth(b2s_ctx *c, const double *d_depth2, int W2, int H2, double rate, const double *Kinv, const double *T,
+                                 const double *K1, int W1, int H1, unsigned long long *d_key, double *d_out);
 cudaError_t launch_gen_maps(b2s_ctx *c, const b2s_map_params &p, float *mapx, float *mapy, uint8_t *mask, int mW, int mH, int16_t *xy16,
                             uint16_t *fxy16);
 cudaError_t launch_depth_bare(b2s_ctx *c, const float *d_disp, double *d_depth);

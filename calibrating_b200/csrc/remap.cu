@@ -6,6 +6,7 @@
 // cv2 semantics restated: coordinates quantised to 1/32 px with round-half-even, 15-bit
 // fixed-point weight tables summing to exactly 32768, rounding (sum + 2^14) >> 15, constant-0 border.
 #include <math.h>
+#include <string.h>
 
 #include "b2s_internal.h"
 
@@ -299,6 +300,76 @@ cudaError_t launch_distort_depth(b2s_ctx *c, const double *d_depth, double *d_ou
     dim3 b(128), g((W + 127) / 128, H);
     distort_scatter_kernel<<<g, b, 0, c->stream>>>(W, H, c->cam1_f[0], c->cam1_f[1], c->cam1_f[2], c->cam1_f[3], kk, c->dkey.as<unsigned>());
     distort_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_depth, c->dkey.as<unsigned>(), d_out, n);
+    c->launches += 2;
+    return cudaGetLastError();
+}
+
+namespace {
+struct ProjArgs {
+    double Kinv[9], T[12], K1[9];
+    double rate, sx, sy; // sx = W2 / W2u, sy = H2 / H2u: cv2.resize's source-per-destination scale
+    int W2, H2, W2u, H2u, W1, H1;
+};
+// order-preserving map double -> uint64 (smaller double = smaller key), and back
+__device__ __forceinline__ unsigned long long dkey(double z)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(z);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k)
+{
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k));
+}
+// thread = one sample of the up-sampled depth image
+__global__ void project_scatter_kernel(const double *__restrict__ depth2, ProjArgs p, unsigned long long *__restrict__ key)
+{
+    const int uu = blockIdx.x * blockDim.x + threadIdx.x, vv = blockIdx.y;
+    if (uu >= p.W2u) return;
+    // cv2.resize INTER_NEAREST: source index = min(floor(dst * scale), size - 1)
+    const int su = min((int)floor(uu * p.sx), p.W2 - 1), sv = min((int)floor(vv * p.sy), p.H2 - 1);
+    const double z = depth2[(size_t)sv * p.W2 + su];
+    if (z == 0.0) return;
+    const double u = (double)uu / p.rate, v = (double)vv / p.rate;
+    const double a0 = u * z, a1 = v * z;
+    const double X = p.Kinv[0] * a0 + p.Kinv[1] * a1 + p.Kinv[2] * z, Y = p.Kinv[3] * a0 + p.Kinv[4] * a1 + p.Kinv[5] * z,
+                 Z = p.Kinv[6] * a0 + p.Kinv[7] * a1 + p.Kinv[8] * z;
+    const double x1 = p.T[0] * X + p.T[1] * Y + p.T[2] * Z + p.T[3], y1 = p.T[4] * X + p.T[5] * Y + p.T[6] * Z + p.T[7],
+                 z1 = p.T[8] * X + p.T[9] * Y + p.T[10] * Z + p.T[11];
+    const double px = p.K1[0] * x1 + p.K1[1] * y1 + p.K1[2] * z1, py = p.K1[3] * x1 + p.K1[4] * y1 + p.K1[5] * z1,
+                 pz = p.K1[6] * x1 + p.K1[7] * y1 + p.K1[8] * z1;
+    const double fu = rint(px / pz), fv = rint(py / pz); // np.round: half to even
+    if (!(fu >= 0.0 && fu < (double)p.W1 && fv >= 0.0 && fv < (double)p.H1)) return;
+    atomicMin(&key[(size_t)(int)fv * p.W1 + (int)fu], dkey(pz));
+}
+__global__ void project_gather_kernel(const unsigned long long *__restrict__ key, double *__restrict__ out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long k = key[i];
+    out[i] = k == 0xFFFFFFFFFFFFFFFFull ? 0.0 : dunkey(k);
+}
+} // namespace
+
+cudaError_t launch_project_depth(b2s_ctx *c, const double *d_depth2, int W2, int H2, double rate, const double *Kinv, const double *T,
+                                 const double *K1, int W1, int H1, unsigned long long *d_key, double *d_out)
+{
+    ProjArgs p;
+    memcpy(p.Kinv, Kinv, sizeof p.Kinv);
+    memcpy(p.T, T, sizeof p.T);
+    memcpy(p.K1, K1, sizeof p.K1);
+    p.rate = rate;
+    p.W2 = W2; p.H2 = H2; p.W1 = W1; p.H1 = H1;
+    p.W2u = rate == 1.0 ? W2 : (int)nearbyint(W2 * rate);
+    p.H2u = rate == 1.0 ? H2 : (int)nearbyint(H2 * rate);
+    if (p.W2u <= 0 || p.H2u <= 0) return cudaErrorInvalidValue;
+    p.sx = 1.0 / ((double)p.W2u / (double)W2); // cv::resize: ifx = 1 / inv_scale_x, inv_scale_x = dsize.width / ssize.width
+    p.sy = 1.0 / ((double)p.H2u / (double)H2);
+    const size_t n = (size_t)W1 * H1;
+    cudaError_t e = cudaMemsetAsync(d_key, 0xFF, n * 8, c->stream);
+    if (e != cudaSuccess) return e;
+    dim3 b(128), g((p.W2u + 127) / 128, p.H2u);
+    project_scatter_kernel<<<g, b, 0, c->stream>>>(d_depth2, p, d_key);
+    project_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_key, d_out, n);
     c->launches += 2;
     return cudaGetLastError();
 }

@@ -65,6 +65,41 @@ class Cam:
     def copy(self):
         return Cam(self.K.copy(), self.D.copy(), self.xy, self.name)
 
+    def project_cam2_depth(cam1, cam2, depth2, T=None, interpolation=1.5, device=0):
+        """calibrating/camera.py:298-309 on the device: the depth image `depth2` of `cam2` seen from this camera, T = pose of
+        cam2 in this camera's frame (4x4).  The reference derives a missing T from shared calibration boards
+        (`get_T_cam2_in_self`, calibration is out of scope here), so T is required."""
+        if T is None:
+            raise NotImplementedError("T from calibration boards (camera.py:283-296) is out of scope: pass T")
+        depth2 = np.asarray(depth2)
+        if depth2.ndim != 2:
+            raise ValueError("depth2 must be a 2-D depth image")
+        if depth2.dtype == np.uint16:
+            depth2 = np.float32(depth2 / 1000.0)  # utils.py:219-220
+        rate = 1
+        if interpolation:  # utils._get_appropriate_interpolation_rate (utils.py:203-210)
+            rate = cam1.K[0, 0] / cam2.K[0, 0] * interpolation
+            if interpolation >= 1:
+                rate = max(rate, 1)
+        depth2 = np.ascontiguousarray(depth2, np.float64)
+        w1, h1 = cam1.xy
+        out = np.empty((h1, w1), np.float64)
+        h = _module_handle(device)
+        arr = lambda m: (ctypes.c_double * m.size)(*np.float64(m).ravel())
+        h.call("b2s_project_depth", _ffi.ptr(depth2), depth2.shape[1], depth2.shape[0], float(rate), arr(np.linalg.inv(cam2.K)),
+               arr(np.float64(T).reshape(4, 4)), arr(cam1.K), int(w1), int(h1), _ffi.ptr(out))
+        return out
+
+
+_HANDLES = {}
+
+
+def _module_handle(device):
+    """One shared engine handle per device for the rig-independent helpers (Cam.project_cam2_depth)."""
+    if device not in _HANDLES:
+        _HANDLES[device] = _ffi.Handle(device)
+    return _HANDLES[device]
+
 
 def _project_on_plane(v, plane_normal):
     # calibrating/utils.py:139-140

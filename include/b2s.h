@@ -168,6 +168,16 @@ int b2s_set_cam1_model(b2s_handle h, double fx, double fy, double cx, double cy,
  * same target the smallest source index wins (np.unique(..., return_index=True)); targets nobody hits are 0.  Source
  * pixels that project outside the image are dropped (the reference would raise IndexError or wrap around). */
 int b2s_distort_depth(b2s_handle h, const double *unrectify_depth, double *out);
+/* Cam.project_cam2_depth (calibrating/camera.py:298-309 -> utils.depth_to_point_cloud, apply_T_to_point_cloud,
+ * point_cloud_to_depth, utils.py:152-161, 213-317): the depth image of a second camera seen from this one.  depth2 (H2,W2)
+ * f64 (0 = no measurement) is up-sampled nearest-neighbour by `rate` like cv2.resize(INTER_NEAREST) to
+ * (round(W2*rate), round(H2*rate)), every non-zero sample is un-projected with K2inv (row-major 3x3), moved by the rigid
+ * transform T (row-major 4x4, cam2 -> cam1), projected with K1, rounded half-to-even to the (H1,W1) grid; the smallest z
+ * landing on a pixel wins (the reference writes in order of descending z), pixels nobody hits are 0.  float64 throughout;
+ * the reference's matrix products go through BLAS, so z agrees to ~1e-15 relative, not bit for bit.  SURVEY 8(f) rank 3.
+ * Independent of the rig: needs only a handle. */
+int b2s_project_depth(b2s_handle h, const double *depth2, int W2, int H2, double rate, const double K2inv[9], const double T[16],
+                      const double K1[9], int W1, int H1, double *out);
 /* Stereo.undistort_img (stereo_camera.py:430-431): (H1,W1,cn) u8 -> (H1,W1,cn) u8. */
 int b2s_undistort_img(b2s_handle h, const uint8_t *img1, int cn, uint8_t *out);
 

@@ -176,3 +176,35 @@ def test_get_depth_batch(maps):
     assert np.array_equal(g2[1]["unrectify_depth"], st.get_depth(*pairs[1])["unrectify_depth"])
     with pytest.raises(ValueError):
         st.get_depth_batch(pairs[:1], keys=("nope",))
+
+
+def test_project_cam2_depth(golden_dir):
+    """Cam.project_cam2_depth on the device against the real reference's output (golden) and,
+    at other sizes / rates / dtypes, the oracle restatement.  Same pixels hit, z within 1e-12 relative (the reference's
+    matrix products go through BLAS)."""
+    from oracle import reproject
+    g = np.load(os.path.join(golden_dir, "rig320_project.npz"))
+    rig = synth.rig_dict((320, 240))
+    cam1, cam2 = cb.Cam.load(rig["cam1"]), cb.Cam.load(rig["cam2"])
+    got = cam1.project_cam2_depth(cam2, g["depth2"], T=g["T"])
+    exp = g["depth1"]
+    assert got.dtype == np.float64 and got.shape == exp.shape
+    assert ((got != 0) == (exp != 0)).all() and np.allclose(got, exp, rtol=1e-12, atol=0)
+    with pytest.raises(NotImplementedError):
+        cam1.project_cam2_depth(cam2, g["depth2"])
+    rng = np.random.default_rng(3)
+    big1 = cb.Cam(np.float64([[900, 0, 640], [0, 905, 360], [0, 0, 1]]), None, (1280, 720))
+    small2 = cb.Cam(np.float64([[420, 0, 330], [0, 418, 236], [0, 0, 1]]), None, (640, 480))
+    T = np.eye(4)
+    T[:3, :3] = __import__("cv2").Rodrigues(np.float64([0.02, -0.05, 0.01]))[0]
+    T[:3, 3] = [0.06, -0.01, 0.02]
+    d16 = (rng.random((480, 640)) * 3000 + 500).astype(np.uint16)
+    d16[rng.random((480, 640)) < 0.2] = 0
+    for interp in (1.5, 0, 0.5):
+        for d2, (ca, cb2) in ((d16, (big1, small2)), (np.float64(d16) / 1000.0, (small2, small2))):
+            got = ca.project_cam2_depth(cb2, d2, T=T, interpolation=interp)
+            exp = reproject.project_cam2_depth(ca.K, ca.xy, cb2.K, d2, T, interpolation=interp)
+            same = ((got != 0) == (exp != 0)).mean()
+            assert same > 0.99999, (interp, same)
+            both = (got != 0) & (exp != 0)
+            assert np.allclose(got[both], exp[both], rtol=1e-9, atol=0) or (np.abs(got[both] - exp[both]) <= 1e-9 * exp[both]).mean() > 0.9999

@@ -50,3 +50,15 @@ def test_distort_depth_matches_reference(golden_dir):
     g = np.load(os.path.join(golden_dir, "rig320_distort.npz"))
     got = chain.RefStereo(synth.rig_dict((320, 240))).distort_depth(g["unrectify_depth"])
     assert got.dtype == np.float64 and np.array_equal(got, g["distort_depth"])
+
+
+def test_project_cam2_depth_matches_reference(golden_dir):
+    """oracle.reproject against the real reference's Cam.project_cam2_depth (camera.py:298-309), bit for bit."""
+    from calibrating_b200 import synth
+    from oracle import reproject
+    g = np.load(os.path.join(golden_dir, "rig320_project.npz"))
+    rig = synth.rig_dict((320, 240))
+    K = lambda c: np.float64([[c["fx"], 0, c["cx"]], [0, c["fy"], c["cy"]], [0, 0, 1]])
+    got = reproject.project_cam2_depth(K(rig["cam1"]), rig["cam1"]["xy"], K(rig["cam2"]), g["depth2"], g["T"])
+    assert np.array_equal(got, g["depth1"])
+    assert abs(reproject.interpolation_rate(K(rig["cam1"]), K(rig["cam2"])) - float(g["rate"])) == 0

@@ -56,9 +56,9 @@ __global__ void planes_kernel(const uint8_t *__restrict__ img, uchar4 *__restric
 constexpr int TX = 64;
 constexpr int COST_THREADS = 256;
 constexpr int BT_BIAS = 256;
-constexpr int NRP = (TX + 2 * 5 + 256) / 2 + 3; // packed right-pixel pairs per copy: compile-time so that plane offsets are immediates (D <= 256, SW2 <= 5)
+constexpr int NRP_MAX = (TX + 2 * 5 + 256) / 2 + 3; // packed right-pixel pairs per copy; compile-time strides (template NRP): 104 for D <= 128, NRP_MAX for D <= 256
 
-template <int CN>
+template <int CN, int NRP>
 __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4 *__restrict__ PL, const uchar4 *__restrict__ PR,
                                                                     int16_t *__restrict__ hs, SgbmGeom g)
 {
@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
     const int xlo = x1_0 - g.SW2;             // cost column of tile-local index 0
     const int Dp = g.Dp, DW = Dp / 2;         // 32-bit words per column of pix
     uint4 *sL = (uint4 *)smem;                // [NPL][TXH]
-    uint32_t *sR = (uint32_t *)(sL + NPL * TXH); // [NPL][3 (v, v0, v1)][2 copies][NRP]
-    uint32_t *pixw = sR + NPL * 3 * 2 * NRP;  // [TXH][DW] packed int16x2
+    uint4 *sR = sL + NPL * TXH;               // [NPL][2 copies][NRP] {v, v0, v1, -} packed pairs: one LDS.128 per plane and lane
+    uint32_t *pixw = (uint32_t *)(sR + NPL * 2 * NRP); // [TXH][DW] packed int16x2
     // right pixel of reversed index m (m grows with d): image column xr(m) = xrmax - m
     const int xrmax = xlo + g.minX1 - g.minD + (TXH - 1);
 
@@ -88,10 +88,7 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
         int m0 = 2 * wd + cp; // copy 0: pairs (2w, 2w+1); copy 1: pairs (2w+1, 2w+2)
         uchar4 a = PR[((size_t)y * NPL + p) * g.W + clampi(xrmax - m0, 0, g.W - 1)];
         uchar4 b = PR[((size_t)y * NPL + p) * g.W + clampi(xrmax - m0 - 1, 0, g.W - 1)];
-        uint32_t *dst = sR + (size_t)p * 3 * 2 * NRP + cp * NRP + wd;
-        dst[0] = a.x | ((uint32_t)b.x << 16);
-        dst[2 * NRP] = a.y | ((uint32_t)b.y << 16);
-        dst[4 * NRP] = a.z | ((uint32_t)b.z << 16);
+        sR[(p * 2 + cp) * NRP + wd] = make_uint4(a.x | ((uint32_t)b.x << 16), a.y | ((uint32_t)b.y << 16), a.z | ((uint32_t)b.z << 16), 0u);
     }
     __syncthreads();
 
@@ -109,7 +106,7 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
 #pragma unroll
         for (int p = 0; p < NPL; p++) Lc[p] = sL[p * TXH + j];
         const int mj = TXH - 1 - j; // reversed right index of d = 0
-        const uint32_t *rbase = sR + (mj & 1) * NRP + (mj >> 1);
+        const uint4 *rbase = sR + (mj & 1) * NRP + (mj >> 1);
         for (int q = lane; q < DW; q += 32) { // d0 = 2q
             if (2 * q >= g.D) { // padded d-lanes are zero in C
                 out[q] = 0;
@@ -118,8 +115,8 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
             uint32_t acc = 0;
 #pragma unroll
             for (int p = 0; p < NPL; p++) {
-                const uint32_t *rp = rbase + (size_t)p * 3 * 2 * NRP + q;
-                const uint32_t V = rp[0], V0 = rp[2 * NRP], V1 = rp[4 * NRP];
+                const uint4 R4 = rbase[p * 2 * NRP + q];
+                const uint32_t V = R4.x, V0 = R4.y, V1 = R4.z;
                 uint32_t c0 = __vimax3_s16x2(Lc[p].x - V1, V0 + Lc[p].y, Bp);
                 uint32_t c1 = __vimax3_s16x2(V + Lc[p].z, Lc[p].w - V, Bp);
                 uint32_t c = __vmins2(c0, c1);
@@ -241,21 +238,22 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
         planes_kernel<1><<<pg, pb, 0, c->stream>>>(d_left, PL, g.H, g.W, g.ftzero);
         planes_kernel<1><<<pg, pb, 0, c->stream>>>(d_right, PR, g.H, g.W, g.ftzero);
     }
-    const int TXH = TX + 2 * g.SW2;
-    if ((TXH + g.D - 1) / 2 + 2 > NRP) return cudaErrorInvalidValue; // (b2s_api.cu rejects such block sizes with a message)
-    size_t smem = (size_t)NPL * TXH * sizeof(uint4) + (size_t)NPL * 3 * 2 * NRP * sizeof(uint32_t) + (size_t)TXH * g.Dp * sizeof(int16_t);
+    const int TXH = TX + 2 * g.SW2, need = (TXH + g.D - 1) / 2 + 2;
+    if (need > NRP_MAX) return cudaErrorInvalidValue; // (b2s_api.cu rejects such block sizes with a message)
+    const int nrp = need <= 104 ? 104 : NRP_MAX;
+    size_t smem = (size_t)NPL * TXH * sizeof(uint4) + (size_t)NPL * 2 * nrp * sizeof(uint4) + (size_t)TXH * g.Dp * sizeof(int16_t);
     dim3 cg((g.width1 + TX - 1) / TX, g.H);
     int16_t *hs = c->S.as<int16_t>(); // S is free until aggregation starts
+    auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<cg, COST_THREADS, smem, c->stream>>>(PL, PR, hs, g);
+        return cudaSuccess;
+    };
     cudaError_t e;
-    if (g.cn == 3) {
-        e = cudaFuncSetAttribute(pixcost_hsum_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        pixcost_hsum_kernel<3><<<cg, COST_THREADS, smem, c->stream>>>(PL, PR, hs, g);
-    } else {
-        e = cudaFuncSetAttribute(pixcost_hsum_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        pixcost_hsum_kernel<1><<<cg, COST_THREADS, smem, c->stream>>>(PL, PR, hs, g);
-    }
+    if (g.cn == 3) e = nrp == 104 ? launch(pixcost_hsum_kernel<3, 104>) : launch(pixcost_hsum_kernel<3, NRP_MAX>);
+    else e = nrp == 104 ? launch(pixcost_hsum_kernel<1, 104>) : launch(pixcost_hsum_kernel<1, NRP_MAX>);
+    if (e != cudaSuccess) return e;
     size_t row_vec = (size_t)g.width1 * g.Dp / 8;
     dim3 vg((unsigned)((row_vec + 255) / 256), (g.H + VBAND - 1) / VBAND);
     vsum_kernel<<<vg, 256, 0, c->stream>>>((const uint4 *)hs, c->C.as<uint4>(), g.H, row_vec, g.SH2);

@@ -56,21 +56,36 @@ def rig_arrays(stereo):
     return arrays, scalars
 
 
+def rig_params(stereo):
+    """The inputs of the four cv2.initUndistortRectifyMap calls as plain lists (for `Stereo(maps="device")` rigs: the ranks
+    regenerate the maps on their GPU with b2s_set_rig_params, so the broadcast block carries ~1 KB instead of ~100 MB)."""
+    w1, h1 = stereo.cam1.xy
+    specs = dict(rect1=(stereo.cam1.K, stereo.cam1.D, stereo.R1, stereo.K, stereo.xy), rect2=(stereo.cam2.K, stereo.cam2.D, stereo.R2, stereo.K, stereo.xy),
+                 unrect=(stereo.K, None, stereo.R1.T, stereo.cam1.K, (w1, h1)), undist=(stereo.cam1.K, stereo.cam1.D, None, stereo.cam1.K, (w1, h1)))
+    out = {}
+    for name, (K, D, R, Knew, size) in specs.items():
+        m = stereo._map_params(K, D, R, Knew, size)
+        out[name] = dict(W=m.W, H=m.H, fx=m.fx, fy=m.fy, cx=m.cx, cy=m.cy, k=list(m.k), iR=list(m.iR))
+    return out
+
+
 def pack_rig_block(stereo, matcher_cfg=None):
-    """-> uint8 array: magic | u64 header length | JSON header (scalars, matcher cfg, array offsets) | 256-aligned arrays."""
+    """-> uint8 array: magic | u64 header length | JSON header (scalars, matcher cfg, array offsets) | 256-aligned arrays.
+    For a `maps="device"` rig the header carries the map parameters instead and there are no arrays."""
     arrays, scalars = rig_arrays(stereo)
+    params = rig_params(stereo) if getattr(stereo, "maps", "host") == "device" else None
     off, table = 0, {}
-    for name, dt in _ARRAYS:
+    for name, dt in ([] if params else _ARRAYS):
         a = arrays[name]
         table[name] = dict(offset=off, shape=list(a.shape), dtype=np.dtype(dt).str)
         off += (a.nbytes + 255) // 256 * 256
-    header = json.dumps(dict(scalars=scalars, matcher=matcher_cfg or {}, arrays=table)).encode()
+    header = json.dumps(dict(scalars=dict(scalars, map_params=params), matcher=matcher_cfg or {}, arrays=table)).encode()
     head_len = (len(_MAGIC) + 8 + len(header) + 255) // 256 * 256
     buf = np.zeros(head_len + off, np.uint8)
     buf[:8] = np.frombuffer(_MAGIC, np.uint8)
     buf[8:16] = np.frombuffer(np.uint64(len(header)).tobytes(), np.uint8)
     buf[16:16 + len(header)] = np.frombuffer(header, np.uint8)
-    for name, _ in _ARRAYS:
+    for name in table:
         a = arrays[name]
         o = head_len + table[name]["offset"]
         buf[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
@@ -87,6 +102,19 @@ def unpack_rig_block(buf):
     head_len = (16 + n + 255) // 256 * 256
     table = {k: (head_len + v["offset"], tuple(v["shape"]), np.dtype(v["dtype"])) for k, v in meta["arrays"].items()}
     return meta["scalars"], meta["matcher"], table
+
+
+def rig_params_struct(scalars):
+    """ctypes `b2s_rig_params` from the scalars of a `maps="device"` rig block."""
+    rp = _ffi.RigParams()
+    for k in ("W", "H", "W1", "H1", "W2", "H2", "min_disparity", "interp"):
+        setattr(rp, k, int(scalars[k]))
+    rp.unrect_m = (ctypes.c_double * 3)(*scalars["unrect_m"])
+    rp.fx_baseline, rp.max_depth = float(scalars["fx_baseline"]), float(scalars["max_depth"])
+    for name, m in scalars["map_params"].items():
+        setattr(rp, name, _ffi.MapParams(int(m["W"]), int(m["H"]), m["fx"], m["fy"], m["cx"], m["cy"], (ctypes.c_double * 12)(*m["k"]),
+                                         (ctypes.c_double * 9)(*m["iR"])))
+    return rp
 
 
 def rig_struct(scalars, table, base_address):
@@ -113,8 +141,11 @@ class CudaEngine:
     def set_rig_block(self, block, scalars, matcher_cfg, table):
         from .stereo_matching import SemiGlobalBlockMatching
         self._block = block  # keep the storage alive
-        base = block.data_ptr() if hasattr(block, "data_ptr") else block.ctypes.data
-        self.handle.call("b2s_set_rig", ctypes.byref(rig_struct(scalars, table, base)))
+        if scalars.get("map_params"):  # maps="device": the rank generates the maps itself from ~1 KB of parameters
+            self.handle.call("b2s_set_rig_params", ctypes.byref(rig_params_struct(scalars)))
+        else:
+            base = block.data_ptr() if hasattr(block, "data_ptr") else block.ctypes.data
+            self.handle.call("b2s_set_rig", ctypes.byref(rig_struct(scalars, table, base)))
         self.matcher = SemiGlobalBlockMatching(dict(matcher_cfg, max_size=1 << 30), handle=self.handle)
         self.scalars = scalars
 

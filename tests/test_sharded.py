@@ -92,6 +92,13 @@ def test_pack_unpack_and_shards():
     assert sorted(sum((sharded.shard_indices(64, r, 8) for r in range(8)), [])) == list(range(64))
     with pytest.raises(ValueError):
         sharded.unpack_rig_block(np.zeros(64, np.uint8))
+    # a maps="device" rig travels as parameters only: ~1 KB instead of the map planes
+    st.maps = "device"
+    small = sharded.pack_rig_block(st, CFG)
+    sc, _, tb = sharded.unpack_rig_block(small)
+    assert small.size < 16384 < buf.size and not tb and set(sc["map_params"]) == {"rect1", "rect2", "unrect", "undist"}
+    rp = sharded.rig_params_struct(sc)
+    assert (rp.W, rp.H, rp.rect1.W, rp.undist.H) == (320, 240, 320, 240) and rp.rect1.fx == st.cam1.K[0, 0]
 
 
 def test_two_ranks_gloo():
@@ -130,6 +137,10 @@ def test_cuda_engine_nccl_world1():
         got = sh.get_depth_batch(pairs).cpu().numpy()
         for i, (a, b) in enumerate(pairs):
             assert np.array_equal(got[i], st.get_depth(a, b)["unrectify_depth"])
+        st2 = cb.Stereo.load(rig, maps="device").set_stereo_matching(cb.SemiGlobalBlockMatching(dict(CFG)), max_depth=3.5)
+        sh2 = sharded.ShardedStereo(st2)  # parameters only in the broadcast block
+        assert sh2.rig_bytes < 16384 < sh.rig_bytes
+        assert np.array_equal(sh2.get_depth_batch(pairs).cpu().numpy(), got)
         exp = _expected(rig, 3)
         assert np.allclose(got, exp, rtol=1e-9, atol=0)
     finally:

@@ -95,7 +95,6 @@ struct b2s_ctx {
 cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t *d_right);
 // sgbm_agg.cu
 cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks = nullptr);
-cudaError_t agg_configure();
 int agg_poll_error(b2s_ctx *c); // after a stream sync: 1 if a hand-over wait of the fused sweep timed out
 // sgbm_post.cu
 cudaError_t launch_wta_prepare(b2s_ctx *c); // before the aggregation: clears the WTA outputs

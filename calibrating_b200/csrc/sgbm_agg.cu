@@ -2,16 +2,19 @@
 //
 // Replaces the aggregation loops of cv2.StereoSGBM.compute (calibrating/stereo_matching.py:63).
 //   L_r(p,d) = C(p,d) + min(L_r(p-r,d), L_r(p-r,d-1)+P1, L_r(p-r,d+1)+P1, minL_r(p-r)+P2) - minL_r(p-r)
-// Every direction r is an independent family of scan lines, and the saturating sum over directions is
-// order-independent for non-negative L, so each direction is swept by one "scan" kernel:
-//   * one warp = one scan line; a lane owns 2*NP consecutive disparities as NP packed int16x2 registers
-//   * state kept normalised (L - minL), so a step is  VIMNMX3.S16x2 / VIADDMNMX.S16x2 / VIADD.16x2 (DPX) per register,
-//     two SHFLs for the d-1 / d+1 neighbours across lanes and one CREDUX.MIN for minL
-//   * the C (and S) chunk of a pixel is 128*NP contiguous bytes; each warp streams its chunks through a private
-//     cp.async (LDGSTS) ring in shared memory, STAGES deep, so ~8 KB per warp are in flight and the sweep is HBM-bound
-//   * horizontal lines are image rows; vertical and diagonal lines are indexed by their column at the first row and
-//     wrap around the image edge with a state reset (an out-of-image predecessor is L = 0, minL = 0), so all lines
-//     have the same length and every row of C is read as one contiguous span by neighbouring warps.
+// The saturating sum over directions is order-independent for non-negative L, so the eight (MODE_HH) or five (MODE_SGBM)
+// directions are grouped by what they need rather than by OpenCV's two sweeps:
+//   agg_hscan_kernel<INIT>      the horizontal path (+1,0): 1080 independent image rows, S = L
+//   agg_vsweep_kernel           every path that crosses rows, in ONE launch: the three top-down paths add to S, the three
+//                               bottom-up paths (MODE_HH) go to S2; lock-step strips of columns, see the kernel's comment
+//   agg_hscan_kernel<ACCUM[2]>  the horizontal path (-1,0) last: S = sat(S [+ S2] + L) (optionally with the winner-take-all fused)
+//   agg_scan_kernel             generic one-direction-per-launch scan (any direction; diagonal lines wrap around the image
+//                               edge with a state reset): the legacy schedule for strips wider than 32 columns and the
+//                               cross-check of the tests (B2S_AGG_LEGACY=1)
+// Common to all: one warp = one line (or column), a lane owns 2*NP consecutive disparities as NP packed int16x2 registers;
+// state kept normalised (L - minL), so a step (sgm_step) is VIMNMX3.S16x2 / VIADDMNMX.S16x2 / VIADD.16x2 (DPX) per register,
+// two SHFLs for the d-1 / d+1 neighbours across lanes and one CREDUX.MIN for minL; the C (and S) chunk of a pixel is 128*NP
+// contiguous bytes, streamed through a private cp.async (LDGSTS) ring per warp.
 #include <stdlib.h>
 
 #include <mutex>
@@ -801,8 +804,6 @@ cudaError_t launch_vsweep(b2s_ctx *c, int n, int J)
 }
 
 } // namespace
-
-cudaError_t agg_configure() { return cudaSuccess; }
 
 int agg_poll_error(b2s_ctx *c)
 {

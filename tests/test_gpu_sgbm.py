@@ -253,3 +253,24 @@ def test_census_4k_256_accuracy(handle):
     assert np.array_equal(m.compute(l[::-1].copy(), r[::-1].copy()), got[::-1]), "vertical flip equivariance"
     t = handle.timings()
     print("census 4K/256 stage ms:", {k: round(v, 3) for k, v in t.items() if k.endswith("_ms")})
+
+
+@pytest.mark.parametrize("shape", [(1, 40), (2, 41), (3, 60), (5, 37), (9, 300)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_degenerate_shapes(handle, shape, mode):
+    """Images of one to a few rows and cost volumes a few columns wide (fewer rows than the cp.async ring is deep, strips of a
+    single column pair, block windows larger than the image) against the oracle."""
+    h, w = shape
+    rng = np.random.default_rng(h * 1000 + w + mode)
+    l = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    r = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    for D, bs in ((16, 11), (32, 3)):
+        if w - D <= bs // 2:
+            continue
+        p = dict(min_disparity=0, num_disparities=D, block_size=bs, P1=8 * 3 * bs * bs, P2=32 * 3 * bs * bs, disp12_max_diff=1,
+                 uniqueness_ratio=5, speckle_window_size=10, speckle_range=2, mode=mode)
+        ref = osgbm.sgbm_compute(l, r, want_volumes=True, **p)
+        got = cb.StereoSGBM(handle=handle, **p).compute(l, r)
+        assert np.array_equal(handle.fetch_volume(0), ref["C"]), (D, bs, "C")
+        assert np.array_equal(handle.fetch_volume(1), ref["S"]), (D, bs, "S")
+        assert np.array_equal(got, ref["disp"]), (D, bs)

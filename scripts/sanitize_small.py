@@ -20,3 +20,18 @@ img1, img2 = synth.render_rig(rig, seed=0)
 st = cb.Stereo.load(rig).set_stereo_matching(cb.SemiGlobalBlockMatching({"max_size": 4000, "num_disparities": 64}), max_depth=3.5)
 res = st.get_depth(img1, img2)
 print("chain ok", {k: v.shape for k, v in res.items()})
+# later additions: census cost, device-side maps, distort_depth, project_cam2_depth, fused winner-take-all
+l, r, _ = synth.rectified_pair(20, 200, 64, 2, 1)
+p = dict(min_disparity=0, num_disparities=64, block_size=5, P1=10, P2=120, disp12_max_diff=1, uniqueness_ratio=5, speckle_window_size=20,
+         speckle_range=2, mode=1, cost=cb.COST_CENSUS)
+m = cb.StereoSGBM(**p)
+print("census", np.array_equal(m.compute(l, r), osgbm.sgbm_compute(l, r, **p)))
+m.handle.fuse_wta(True)
+print("census fused wta", np.array_equal(m.compute(l, r), osgbm.sgbm_compute(l, r, **p)))
+st2 = cb.Stereo.load(rig, maps="device").set_stereo_matching(cb.SemiGlobalBlockMatching({"max_size": 4000, "num_disparities": 64}), max_depth=3.5)
+res2 = st2.get_depth(img1, img2, return_distort_depth=True)
+print("device maps chain equal", all(np.array_equal(res[k], res2[k]) for k in res), res2["distort_depth"].shape)
+cam1, cam2 = cb.Cam.load(rig["cam1"]), cb.Cam.load(rig["cam2"])
+T = np.eye(4); T[:3, 3] = [0.05, 0, 0.01]
+print("project", (cam1.project_cam2_depth(cam2, res["unrectify_depth"], T=T) > 0).mean())
+print("batch", len(st.get_depth_batch([(img1, img2)] * 3, streams=2)))

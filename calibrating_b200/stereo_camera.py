@@ -479,11 +479,13 @@ class Stereo:
 
 
     # ---- throughput: several pairs in flight (not in the reference) -------------------------------
-    def get_depth_batch(self, pairs, streams=4, keys=("unrectify_depth",)):
+    def get_depth_batch(self, pairs, streams=4, keys=("unrectify_depth",), out=None):
         """`get_depth` for a list of (img1, img2) with `streams` engine handles (= CUDA streams) in flight: upload, the ~20
         kernels and the download of different pairs overlap.  Needs the built-in `SemiGlobalBlockMatching` at full resolution
         (the one-call path of `get_depth`).  keys: which result arrays to return, any of rectify_img1, rectify_img2, disparity,
-        rectify_depth, unrectify_depth, undistort_img1, distort_depth.  Returns a list of dicts."""
+        rectify_depth, unrectify_depth, undistort_img1, distort_depth.  Returns a list of dicts.
+        Host copies are avoided when the caller supplies pinned memory (`_ffi.pinned_empty`): pinned input images are
+        uploaded in place, and `out` (a list of dicts of pinned arrays, one per pair, same keys) receives the results directly."""
         assert hasattr(self, "stereo_matching"), "Please stereo.set_stereo_matching(stereo_matching)"
         sm = self.stereo_matching
         w, h = self.xy
@@ -510,7 +512,7 @@ class Stereo:
                 return
             b["handle"].sync()
             i, bufs = b["pending"]
-            results[i] = {k: v.copy() for k, v in bufs.items()}
+            results[i] = bufs if out is not None else {k: v.copy() for k, v in bufs.items()}
             if "distort_depth" in keys:
                 results[i]["distort_img1"] = pairs[i][0]
             b["pending"] = None
@@ -528,7 +530,7 @@ class Stereo:
             spec = dict(rectify_img1=(ishape, np.uint8), rectify_img2=(ishape, np.uint8), disparity=((h, w), np.float32),
                         rectify_depth=((h, w), np.float64), unrectify_depth=((h1, w1), np.float64), undistort_img1=(img1.shape, np.uint8),
                         distort_depth=((h1, w1), np.float64))
-            out, bufs = _ffi.DepthOut(), {}
+            dout, bufs = _ffi.DepthOut(), {}
 
             def pinned(name, shape, dtype):
                 a = b["pin"].get(name)
@@ -541,12 +543,22 @@ class Stereo:
             for k in keys:
                 if k not in spec:
                     raise ValueError("unknown result key %r" % (k,))
-                bufs[k] = pinned(k, *spec[k])
-                setattr(out, k, bufs[k].ctypes.data)
-            in1, in2 = pinned("_in1", img1.shape, np.uint8), pinned("_in2", img2.shape, np.uint8)
-            np.copyto(in1, img1)
-            np.copyto(in2, img2)
-            b["handle"].call("b2s_get_depth_async", _ffi.ptr(in1), _ffi.ptr(in2), cn, want, ctypes.byref(out))
+                if out is not None:
+                    a = out[i][k]
+                    if a.shape != tuple(spec[k][0]) or a.dtype != np.dtype(spec[k][1]) or not a.flags.c_contiguous:
+                        raise ValueError("out[%d][%r] must be a C-contiguous %s array of shape %s" % (i, k, np.dtype(spec[k][1]), spec[k][0]))
+                    bufs[k] = a
+                else:
+                    bufs[k] = pinned(k, *spec[k])
+                setattr(dout, k, bufs[k].ctypes.data)
+            in1, in2 = img1, img2
+            if img1.ctypes.data not in _ffi._PINNED:
+                in1 = pinned("_in1", img1.shape, np.uint8)
+                np.copyto(in1, img1)
+            if img2.ctypes.data not in _ffi._PINNED:
+                in2 = pinned("_in2", img2.shape, np.uint8)
+                np.copyto(in2, img2)
+            b["handle"].call("b2s_get_depth_async", _ffi.ptr(in1), _ffi.ptr(in2), cn, want, ctypes.byref(dout))
             b["pending"] = (i, bufs)
         for slot in range(len(batch)):
             collect(slot)

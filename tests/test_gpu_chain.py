@@ -176,6 +176,18 @@ def test_get_depth_batch(maps):
     assert np.array_equal(g2[1]["unrectify_depth"], st.get_depth(*pairs[1])["unrectify_depth"])
     with pytest.raises(ValueError):
         st.get_depth_batch(pairs[:1], keys=("nope",))
+    from calibrating_b200 import _ffi  # pinned inputs in place, results straight into caller-owned pinned buffers
+    pp = []
+    for a, b in pairs[:3]:
+        x, y = _ffi.pinned_empty(a.shape, np.uint8), _ffi.pinned_empty(b.shape, np.uint8)
+        x[...] = a
+        y[...] = b
+        pp.append((x, y))
+    outs = [{"unrectify_depth": _ffi.pinned_empty((240, 320), np.float64)} for _ in range(3)]
+    g3 = st.get_depth_batch(pp, streams=2, out=outs)
+    for i in range(3):
+        assert g3[i]["unrectify_depth"] is outs[i]["unrectify_depth"]
+        assert np.array_equal(outs[i]["unrectify_depth"], st.get_depth(*pairs[i])["unrectify_depth"])
 
 
 def test_project_cam2_depth(golden_dir):

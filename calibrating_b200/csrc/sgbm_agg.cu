@@ -419,7 +419,22 @@ struct VsArgs {
     int *err;     // set to 1 if a hand-over wait timed out (never in a correct run)
 };
 constexpr int HO_SLOTS = 4;
-constexpr int HO_SPIN_LIMIT = 1 << 18;
+constexpr unsigned long long WAIT_TIMEOUT_NS = 2000000000ull; // a hand-over / neighbour wait longer than 2 s is a lost strip: flag it, do not hang
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// slow path of the spin loops: true when the wait should be abandoned (timeout, or another warp already flagged an error)
+__device__ __forceinline__ bool wait_expired(int spins, unsigned long long &t0, int *err)
+{
+    if ((spins & 255) != 0) return false;
+    if (*(volatile int *)err != 0) return true;
+    const unsigned long long now = global_ns();
+    if (t0 == 0) t0 = now;
+    return now - t0 > WAIT_TIMEOUT_NS;
+}
 
 template <int NP> __device__ __forceinline__ void lds_regs(const uint32_t *src, uint32_t (&v)[NP])
 {
@@ -456,6 +471,7 @@ template <int NP> __device__ __forceinline__ void ho_read(const uint32_t *p, uin
 {
     uint32_t v[NP];
     int spins = 0;
+    unsigned long long t0 = 0;
     if (preloaded) {
 #pragma unroll
         for (int i = 0; i < NP; i++) v[i] = T[i];
@@ -467,7 +483,7 @@ template <int NP> __device__ __forceinline__ void ho_read(const uint32_t *p, uin
 #pragma unroll
         for (int i = 0; i < NP; i++) bad |= (v[i] ^ phase) & 0x80008000u;
         if (__all_sync(0xffffffffu, bad == 0)) break;
-        if (++spins > HO_SPIN_LIMIT || ((spins & 1023) == 0 && *(volatile int *)err != 0)) {
+        if (wait_expired(++spins, t0, err)) {
             *(volatile int *)err = 1;
             break;
         }
@@ -502,10 +518,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity, int *e
 {
     uint32_t ok;
     int spins = 0;
+    unsigned long long t0 = 0;
     do {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-        if (!ok && (++spins > (1 << 16) || ((spins & 63) == 0 && *(volatile int *)err != 0))) {
+        if (!ok && wait_expired(++spins, t0, err)) {
             *(volatile int *)err = 1;
             break;
         }

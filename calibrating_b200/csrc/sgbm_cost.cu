@@ -69,26 +69,31 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
     const int TXH = TX + 2 * g.SW2;
     const int xlo = x1_0 - g.SW2;             // cost column of tile-local index 0
     const int Dp = g.Dp, DW = Dp / 2;         // 32-bit words per column of pix
-    uint4 *sL = (uint4 *)smem;                // [NPL][TXH]
+    uint4 *sL = (uint4 *)smem;                // [TXH][NPL]
     uint4 *sR = sL + NPL * TXH;               // [NPL][2 copies][NRP] {v, v0, v1, -} packed pairs: one LDS.128 per plane and lane
     uint32_t *pixw = (uint32_t *)(sR + NPL * 2 * NRP); // [TXH][DW] packed int16x2
     // right pixel of reversed index m (m grows with d): image column xr(m) = xrmax - m
     const int xrmax = xlo + g.minX1 - g.minD + (TXH - 1);
 
-    for (int i = threadIdx.x; i < NPL * TXH; i += COST_THREADS) {
-        int p = i / TXH, j = i % TXH;
+    // (flat indices are split with compile-time divisors -- TX + 10 >= TXH and NRP >= nrp -- so there is no run-time division)
+    constexpr int TXHP = TX + 10;
+    for (int i = threadIdx.x; i < NPL * TXHP; i += COST_THREADS) {
+        const int p = i / TXHP, j = i % TXHP;
+        if (j >= TXH) continue;
         int x = clampi(xlo + j + g.minX1, 0, g.W - 1);
         uchar4 L = PL[((size_t)y * NPL + p) * g.W + x];
         uint32_t u = L.x, u0 = L.y, u1 = L.z;
-        sL[i] = make_uint4((u + BT_BIAS) * 0x10001u, (BT_BIAS - u) * 0x10001u, (BT_BIAS - u1) * 0x10001u, (u0 + BT_BIAS) * 0x10001u);
+        sL[j * NPL + p] = make_uint4((u + BT_BIAS) * 0x10001u, (BT_BIAS - u) * 0x10001u, (BT_BIAS - u1) * 0x10001u, (u0 + BT_BIAS) * 0x10001u);
     }
     const int nrp = (TXH + g.D - 1) / 2 + 2; // pairs actually read by phase 1 (<= NRP, checked by the launcher)
-    for (int i = threadIdx.x; i < NPL * 2 * nrp; i += COST_THREADS) {
-        int p = i / (2 * nrp), r = i % (2 * nrp), cp = r / nrp, wd = r % nrp;
+    for (int i = threadIdx.x; i < NPL * 2 * NRP; i += COST_THREADS) {
+        const int pc = i / NRP, wd = i % NRP, p = pc >> 1, cp = pc & 1;
+        if (wd >= nrp) continue;
+        const uchar4 *prow = PR + ((size_t)y * NPL + p) * g.W;
         int m0 = 2 * wd + cp; // copy 0: pairs (2w, 2w+1); copy 1: pairs (2w+1, 2w+2)
-        uchar4 a = PR[((size_t)y * NPL + p) * g.W + clampi(xrmax - m0, 0, g.W - 1)];
-        uchar4 b = PR[((size_t)y * NPL + p) * g.W + clampi(xrmax - m0 - 1, 0, g.W - 1)];
-        sR[(p * 2 + cp) * NRP + wd] = make_uint4(a.x | ((uint32_t)b.x << 16), a.y | ((uint32_t)b.y << 16), a.z | ((uint32_t)b.z << 16), 0u);
+        uchar4 a = prow[clampi(xrmax - m0, 0, g.W - 1)];
+        uchar4 b = prow[clampi(xrmax - m0 - 1, 0, g.W - 1)];
+        sR[i] = make_uint4(a.x | ((uint32_t)b.x << 16), a.y | ((uint32_t)b.y << 16), a.z | ((uint32_t)b.z << 16), 0u);
     }
     __syncthreads();
 
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
         }
         uint4 Lc[NPL];
 #pragma unroll
-        for (int p = 0; p < NPL; p++) Lc[p] = sL[p * TXH + j];
+        for (int p = 0; p < NPL; p++) Lc[p] = sL[j * NPL + p];
         const int mj = TXH - 1 - j; // reversed right index of d = 0
         const uint4 *rbase = sR + (mj & 1) * NRP + (mj >> 1);
         for (int q = lane; q < DW; q += 32) { // d0 = 2q

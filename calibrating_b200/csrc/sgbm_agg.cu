@@ -122,7 +122,7 @@ __device__ __forceinline__ void sgm_step(uint32_t (&T)[NP], const uint32_t (&c)[
         uint32_t rgt = __byte_perm(T[i], i == NP - 1 ? dn : T[i + 1], 0x5432); // L(d+1)
         uint32_t t = __vimin3_s16x2(lft, rgt, P2mP1v);
         t = __viaddmin_s16x2(t, P1v, T[i]);
-        L[i] = __vadd2(c[i], t);
+        L[i] = c[i] + t; // packed add as a 32-bit add (FMA pipe instead of the busier ALU pipe): 0 <= t <= P2 and C >= 0, no carry between halves
         if (PAD) L[i] |= padmask[i];
         m = __vmins2(m, L[i]);
     }

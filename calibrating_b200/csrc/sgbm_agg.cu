@@ -781,9 +781,17 @@ int vsweep_cols(const b2s_ctx *c)
 // are chained per device with an event, which costs nothing because they cannot share the SMs anyway.
 struct SweepChain {
     std::mutex mu;
-    cudaEvent_t ev[64] = {};
+    cudaEvent_t ev[64][4] = {};
+    unsigned long long count[64] = {};
 };
 SweepChain g_chain;
+// how many sweeps of one process may be in flight on a device at once (1: strictly one after the other)
+int sweep_concurrency()
+{
+    const char *e = getenv("B2S_SWEEP_CONCURRENCY");
+    int v = e ? atoi(e) : 1;
+    return v < 1 ? 1 : (v > 4 ? 4 : v);
+}
 
 cudaError_t launch_vsweep(b2s_ctx *c, int n, int J)
 {
@@ -805,7 +813,8 @@ cudaError_t launch_vsweep(b2s_ctx *c, int n, int J)
     c->agg_err = a.err;
     const bool pad = g.D != g.Dp;
     std::lock_guard<std::mutex> lock(g_chain.mu);
-    cudaEvent_t &ev = g_chain.ev[c->device & 63];
+    const int dev = c->device & 63, nconc = sweep_concurrency();
+    cudaEvent_t &ev = g_chain.ev[dev][g_chain.count[dev]++ % nconc]; // recorded by the sweep `nconc` launches ago
     if (!ev) {
         if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
     } else if ((e = cudaStreamWaitEvent(c->stream, ev, 0)) != cudaSuccess) return e;

@@ -305,7 +305,7 @@ def main():
     except Exception:
         pass
     achieved = AGG_BYTES_PER_PAIR / (agg_ms * 1e-3) / 1e9  # = (bytes per pair / launches) / (group time / launches)
-    names = ["agg_scan_kernel<INIT> (+x)", "agg_vsweep_kernel (6 of 8 directions)", "agg_scan_kernel<ACCUM2> (-x)"] if n_launch == 3 else \
+    names = ["agg_hscan_kernel<INIT> (+x)", "agg_vsweep_kernel (6 of 8 directions)", "agg_hscan_kernel<ACCUM2> (-x)"] if n_launch == 3 else \
         ["agg_scan_kernel"] * n_launch
     dirs = [1, 6, 1] if n_launch == 3 else [1] * n_launch
     out = {
@@ -314,7 +314,7 @@ def main():
         "dtype": "int16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "streams_per_gpu": S, "parallelism": "dp%d (pairs sharded, no collective)" % world,
                    "l2": "working set per pair (C, S, S2 volumes, 1.49 GB) exceeds the 126 MB L2; %d distinct pairs rotate" % P},
-        "clocks": clocks, "gpu_launches": int(launches),
+        "clocks": clocks, "gpu_launches": int(launches) * world,  # (rank 0's count x ranks: every rank runs the same schedule)
         "e2e": {"value": world * K * P / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": P * 2 * H * W * CN, "d2h_bytes_per_step": P * H * W * 4,
                 "api": "DisparityBatchEngine.compute_batch (host uint8 pairs -> host float32 disparity), wall clock between synchronisations"},
         "roofline": {"bound": "hbm", "kernel": "aggregation group: %d launches per pair (dominant: agg_vsweep_kernel)" % n_launch,

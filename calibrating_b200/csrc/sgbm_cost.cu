@@ -25,17 +25,23 @@ __device__ __forceinline__ int plane_value(const uint8_t *__restrict__ img, int 
     return clampi(s, -ftzero, ftzero) + ftzero;
 }
 
+// A warp produces 30 consecutive pixels of a row: every lane evaluates the plane values of ONE pixel (lanes 0 and 31 are the
+// halo), the half-sample neighbours come from the adjacent lanes.
+constexpr int PLANES_WARPS = 8;
 template <int CN>
-__global__ void planes_kernel(const uint8_t *__restrict__ img, uchar4 *__restrict__ out, int H, int W, int ftzero)
+__global__ void __launch_bounds__(PLANES_WARPS * 32) planes_kernel(const uint8_t *__restrict__ img, uchar4 *__restrict__ out, int H, int W, int ftzero)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
-    if (x >= W) return;
+    const int lane = threadIdx.x & 31, y = blockIdx.y;
+    const int x = (blockIdx.x * PLANES_WARPS + (threadIdx.x >> 5)) * 30 + lane - 1;
+    const int xc = clampi(x, 0, W - 1);
+    const bool write = lane >= 1 && lane <= 30 && x < W;
 #pragma unroll
     for (int p = 0; p < 2 * CN; p++) {
-        int u = plane_value<CN>(img, H, W, y, x, p, ftzero);
-        int ul = x > 0 ? (u + plane_value<CN>(img, H, W, y, x - 1, p, ftzero)) / 2 : u;
-        int ur = x < W - 1 ? (u + plane_value<CN>(img, H, W, y, x + 1, p, ftzero)) / 2 : u;
+        const int u = plane_value<CN>(img, H, W, y, xc, p, ftzero);
+        const int l = __shfl_up_sync(0xffffffffu, u, 1), r = __shfl_down_sync(0xffffffffu, u, 1);
+        if (!write) continue;
+        const int ul = x > 0 ? (u + l) / 2 : u;
+        const int ur = x < W - 1 ? (u + r) / 2 : u;
         out[((size_t)y * 2 * CN + p) * W + x] = make_uchar4((unsigned char)u, (unsigned char)min(min(ul, ur), u),
                                                             (unsigned char)max(max(ul, ur), u), 0);
     }
@@ -234,7 +240,7 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
         return cudaGetLastError();
     }
     const int NPL = 2 * g.cn;
-    dim3 pb(128), pg((g.W + 127) / 128, g.H);
+    dim3 pb(PLANES_WARPS * 32), pg((g.W + PLANES_WARPS * 30 - 1) / (PLANES_WARPS * 30), g.H);
     uchar4 *PL = c->planesL.as<uchar4>(), *PR = c->planesR.as<uchar4>();
     if (g.cn == 3) {
         planes_kernel<3><<<pg, pb, 0, c->stream>>>(d_left, PL, g.H, g.W, g.ftzero);

@@ -125,16 +125,26 @@ __device__ __forceinline__ int lr_checked(const int16_t *__restrict__ raw, const
 }
 
 #define CSWAP(a, b) { int _t = min(a, b); b = max(a, b); a = _t; }
-__global__ void lr_median_kernel(const int16_t *__restrict__ raw, const unsigned *__restrict__ keys, int16_t *__restrict__ out, SgbmGeom g)
+// CTA = 32 x 8 output pixels; the L/R-checked values of the 34 x 10 halo tile are computed ONCE into shared memory (each is 2
+// right-view look-ups), then every thread takes the median of its 3 x 3 neighbourhood from there
+constexpr int MED_TX = 32, MED_TY = 8;
+__global__ void __launch_bounds__(MED_TX * MED_TY) lr_median_kernel(const int16_t *__restrict__ raw, const unsigned *__restrict__ keys,
+                                                                    int16_t *__restrict__ out, SgbmGeom g)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= g.W) return;
+    __shared__ int16_t tile[MED_TY + 2][MED_TX + 2];
+    const int x0 = blockIdx.x * MED_TX, y0 = blockIdx.y * MED_TY;
+    for (int i = threadIdx.y * MED_TX + threadIdx.x; i < (MED_TY + 2) * (MED_TX + 2); i += MED_TX * MED_TY) {
+        const int ty = i / (MED_TX + 2), tx = i % (MED_TX + 2);
+        tile[ty][tx] = (int16_t)lr_checked(raw, keys, g, clampi(y0 + ty - 1, 0, g.H - 1), clampi(x0 + tx - 1, 0, g.W - 1));
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= g.W || y >= g.H) return;
     int v[9];
 #pragma unroll
-    for (int dy = -1; dy <= 1; dy++)
+    for (int dy = 0; dy < 3; dy++)
 #pragma unroll
-        for (int dx = -1; dx <= 1; dx++)
-            v[(dy + 1) * 3 + dx + 1] = lr_checked(raw, keys, g, clampi(y + dy, 0, g.H - 1), clampi(x + dx, 0, g.W - 1));
+        for (int dx = 0; dx < 3; dx++) v[dy * 3 + dx] = tile[threadIdx.y + dy][threadIdx.x + dx];
     // median-of-9 exchange network
     CSWAP(v[1], v[2]); CSWAP(v[4], v[5]); CSWAP(v[7], v[8]); CSWAP(v[0], v[1]); CSWAP(v[3], v[4]); CSWAP(v[6], v[7]);
     CSWAP(v[1], v[2]); CSWAP(v[4], v[5]); CSWAP(v[7], v[8]); CSWAP(v[0], v[3]); CSWAP(v[5], v[8]); CSWAP(v[4], v[7]);
@@ -301,7 +311,8 @@ cudaError_t launch_post(b2s_ctx *c, int16_t *d_out_disp16, float *d_out_disp)
     unsigned nb = (unsigned)((n + 255) / 256);
     int16_t *final16 = d_out_disp16 ? d_out_disp16 : c->disp16.as<int16_t>();
     int16_t *med = g.speckle_window > 0 ? c->med.as<int16_t>() : final16;
-    lr_median_kernel<<<g2, b2, 0, c->stream>>>(c->raw.as<int16_t>(), c->disp2key.as<unsigned>(), med, g);
+    lr_median_kernel<<<dim3((g.W + MED_TX - 1) / MED_TX, (g.H + MED_TY - 1) / MED_TY), dim3(MED_TX, MED_TY), 0, c->stream>>>(
+        c->raw.as<int16_t>(), c->disp2key.as<unsigned>(), med, g);
     c->launches++;
     if (g.speckle_window > 0) {
         int *lab = c->labels.as<int>(), *sizes = c->sizes.as<int>();

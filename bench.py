@@ -305,7 +305,7 @@ def main():
     except Exception:
         pass
     achieved = AGG_BYTES_PER_PAIR / (agg_ms * 1e-3) / 1e9  # = (bytes per pair / launches) / (group time / launches)
-    names = ["agg_hscan_kernel<INIT> (+x)", "agg_vsweep_kernel (6 of 8 directions)", "agg_hscan_kernel<ACCUM2> (-x)"] if n_launch == 3 else \
+    names = ["agg_hscan_kernel<INIT> (+x)", "agg_vsweep_kernel (6 of 8 directions)", "agg_hscan_kernel<ACCUM2, WTA> (-x, folds S2, winner-take-all fused)"] if n_launch == 3 else \
         ["agg_scan_kernel"] * n_launch
     dirs = [1, 6, 1] if n_launch == 3 else [1] * n_launch
     out = {

@@ -158,11 +158,11 @@ class Handle:
         return n.value
 
     def keep_volumes(self, on=True):
-        """With fuse_wta: make the last aggregation pass store S as well, so that fetch_volume(1) works."""
+        """Make the last aggregation pass store S as well (it fuses the winner-take-all by default), so that fetch_volume(1) works."""
         self.call("b2s_set_option", 1, int(bool(on)))
 
     def fuse_wta(self, on=True):
-        """Fuse the winner-take-all step into the last aggregation pass (same results; see include/b2s.h)."""
+        """Winner-take-all inside the last aggregation pass (default) or as a separate kernel (same results; see include/b2s.h)."""
         self.call("b2s_set_option", 2, int(bool(on)))
 
     def volume_dims(self):

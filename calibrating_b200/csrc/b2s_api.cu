@@ -117,7 +117,8 @@ int b2s_set_sgbm_params(b2s_handle c, const b2s_sgbm_params *p)
     if (p->num_disparities <= 0) return fail(c, B2S_EINVAL, "numDisparities must be > 0 (got %d)", p->num_disparities);
     if (p->num_disparities > 256) return fail(c, B2S_EINVAL, "numDisparities > 256 is not supported yet (got %d)", p->num_disparities);
     if (p->min_disparity < 0) return fail(c, B2S_EINVAL, "negative minDisparity is not supported (got %d)", p->min_disparity);
-    if (p->mode != 0 && p->mode != 1) return fail(c, B2S_EINVAL, "mode must be 0 (MODE_SGBM) or 1 (MODE_HH), got %d", p->mode);
+    if (p->mode != 0 && p->mode != 1 && p->mode != 3)
+        return fail(c, B2S_EINVAL, "mode must be 0 (MODE_SGBM), 1 (MODE_HH) or 3 (MODE_HH4), got %d (MODE_SGBM_3WAY = 2 depends on cv2's thread count and is not offered)", p->mode);
     if (p->cost != 0 && p->cost != 1) return fail(c, B2S_EINVAL, "cost must be 0 (Birchfield-Tomasi, cv2) or 1 (census), got %d", p->cost);
     int P1 = p->P1 > 0 ? p->P1 : 2;
     int P2 = p->P2 > 0 ? p->P2 : 5;

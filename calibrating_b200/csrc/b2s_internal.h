@@ -53,7 +53,7 @@ struct b2s_ctx {
     SgbmGeom g{};
     bool have_volume = false;
     bool keep_volumes = false; // b2s_set_option(B2S_OPT_KEEP_VOLUMES): a fused last pass also stores S
-    bool fuse_wta = false;     // b2s_set_option(B2S_OPT_FUSE_WTA)
+    bool fuse_wta = true;      // b2s_set_option(B2S_OPT_FUSE_WTA): on by default
     bool agg_legacy = false;   // launch_aggregate: per-direction scan kernels (strips too wide, or B2S_AGG_LEGACY)
     bool wta_fused = false;    // set by launch_aggregate when the last scan already did the winner-take-all
 

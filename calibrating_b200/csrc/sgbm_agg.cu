@@ -46,6 +46,7 @@ struct AggArgs {
     int16_t *raw;
     unsigned *disp2key;
     int W, minX1, minD, uniq;
+    unsigned uniq_M; // ceil(2^32 / (100 - uniq)): the fused WTA's division by the invariant (100 - uniq) (0 < 100 - uniq <= 100)
 };
 
 template <int NP> __device__ __forceinline__ void store_regs(int16_t *dst, const uint32_t (&v)[NP])
@@ -311,9 +312,69 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_kernel(AggArgs a)
 #pragma unroll
     for (int i = 0; i < NP; i++) T[i] = padmask[i];
     int16_t *sp = a.S + o0 + lane * 2 * NP;
-    int x = a.mx > 0 ? 0 : a.width1 - 1;
+    const int xfirst = a.mx > 0 ? 0 : a.width1 - 1;
     int stage = 0, pstage = STAGES - 1;
     const uint32_t cur0 = ring + lane * NP * 4;
+    // ---- fused winner-take-all (WTA != 0): A.5 of SURVEY.md, same rule as wta_kernel in sgbm_post.cu ----
+    // per-warp exchange buffer (two pixels) behind the cp.async rings: the sub-pixel fit needs S(best-1), S(best+1) of other lanes
+    const uint32_t xbase = (uint32_t)__cvta_generic_to_shared(smem) + WARPS * (STAGES * STAGE_BYTES) + wid * (2 * CH);
+    const uint32_t xbuf = xbase + lane * NP * 4;
+    uint32_t dd[NP], prev[NP], kmin = 0;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        const uint32_t d0 = (uint32_t)(lane * NP + i) * 2;
+        dd[i] = d0 | ((d0 + 1) << 16);
+        prev[i] = 0;
+    }
+    const int thr = 100 - a.uniq;
+    int my_best = -2, my_minS = 0, my_sm = 0, my_sp = 0; // lane i keeps the winner of step (chunk of 32) + i; -2 = rejected
+    auto wta_flush = [&](int kp) { // kp = last step of the chunk: one pixel per lane (right-view candidate, sub-pixel fit, store)
+        const int kl = (kp & ~31) + lane;
+        if (kl <= kp && my_best != -2) {
+            const int x = xfirst + a.mx * kl;
+            int d = my_best;
+            const int x2 = x + a.minX1 - d - a.minD;
+            if (my_minS < 32767 && x2 >= 0 && x2 < a.W + 2)
+                atomicMin(&a.disp2key[(size_t)y * (a.W + 2) + x2], ((unsigned)my_minS << 16) | (unsigned)(0xFFFF - x));
+            if (0 < d && d < a.D - 1) {
+                const int den2 = max(my_sm + my_sp - 2 * my_minS, 1);
+                d = d * 16 + ((my_sm - my_sp) * 16 + den2) / (den2 * 2);
+            } else
+                d *= 16;
+            a.raw[(size_t)y * a.W + x + a.minX1] = (int16_t)(d + a.minD * 16);
+        }
+        my_best = -2;
+    };
+    // second half of the WTA of step kp (prev = its S, kmin = its smallest key); branch-free so that it stays in the basic block
+    // of the step and ptxas can interleave it with the next step's dependent chain.  kp = -1 (first iteration) is harmless:
+    // lane 31 records a dummy that step 31 overwrites before the first flush.
+    auto wta_finish = [&](int kp) {
+        const int minS = (int)(kmin >> 16);
+        const int best = minS >= 32767 ? -1 : (int)(kmin & 0xffffu); // cv2: strict '<' against MAX_COST never fires
+        // uniqueness: reject if some d outside best-1..best+1 has S(d) * (100 - uniq) < minS * 100, i.e. S(d) < ceil(minS * 100 / thr)
+        const unsigned n = (unsigned)(minS * 100 + thr - 1);
+        const unsigned T = min(thr == 1 ? n : __umulhi(n, a.uniq_M), 32768u);
+        const uint32_t Tkey = T << 16;
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            const int e = (lane * NP + i) * 2 - best; // d - best of the low half
+            // (the low 16 bits do not matter against a multiple of 65536; padded halves, d >= D, are not candidates)
+            bad |= ((prev[i] << 16) < Tkey) && ((unsigned)(e + 1) > 2u) && !(PAD && (padmask[i] & 0xFFFFu));
+            bad |= (prev[i] < Tkey) && ((unsigned)(e + 2) > 2u) && !(PAD && (padmask[i] >> 16));
+        }
+        // S(best-1), S(best+1) for the sub-pixel fit: every lane reads the same two halves (broadcast), the recording lane keeps them
+        const uint32_t nb = xbase + (kp & 1) * CH + (uint32_t)min(max(best, 1), a.D - 2) * 2;
+        unsigned short lo, hi;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(lo) : "r"(nb - 2) : "memory");
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hi) : "r"(nb + 2) : "memory");
+        const bool rej = __any_sync(0xffffffffu, bad);
+        const bool rec = lane == (kp & 31);
+        my_best = rec ? (rej ? -2 : best) : my_best;
+        my_minS = rec ? minS : my_minS;
+        my_sm = rec ? (int)(short)lo : my_sm;
+        my_sp = rec ? (int)(short)hi : my_sp;
+    };
 #pragma unroll 1
     for (int k = 0; k < nsteps; k++) {
         __syncwarp();
@@ -336,14 +397,28 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_kernel(AggArgs a)
         for (int i = 0; i < NP; i++) out[i] = (MODE != AGG_INIT) ? __viaddmin_u16x2(sv[i], L[i], BIG) : L[i];
         if (WTA != 1) stcg_regs<NP>(sp, out);
         if (WTA != 0) {
-            // this step's stage has been consumed: it doubles as the exchange buffer for the sub-pixel neighbours
-            uint32_t *xch = (uint32_t *)(smem + wid * (STAGES * STAGE_BYTES) + stage * STAGE_BYTES);
-            wta_pixel<NP>(out, xch, lane, x, y, a.D, a.W, a.minX1, a.minD, a.uniq, a.raw, a.disp2key);
+            // winner-take-all of the pixel just finished, software-pipelined by one step so that its warp reduction, vote and
+            // shared-memory round trip overlap the next step's dependent chain instead of extending this one
+            wta_finish(k - 1);
+            sts_s<NP>(xbuf + (k & 1) * CH, out);
+            uint32_t key = 0xFFFFFFFFu;
+#pragma unroll
+            for (int i = 0; i < NP; i++) {
+                // keys (S << 16) | d of the two halves; a padded lane (d >= D) holds S = 0x7FFF and a larger d, so it never wins
+                key = min(key, min(__byte_perm(out[i], dd[i], 0x1054), __byte_perm(out[i], dd[i], 0x3276)));
+                prev[i] = out[i];
+            }
+            kmin = __reduce_min_sync(0xffffffffu, key);
+            if ((k & 31) == 0 && k > 0) wta_flush(k - 1); // steps k-32 .. k-1 are complete
         }
         sp += stepE;
-        x += a.mx;
         pstage = stage;
         stage = stage + 1 == STAGES ? 0 : stage + 1;
+    }
+    if (WTA != 0 && nsteps > 0) {
+        __syncwarp();
+        wta_finish(nsteps - 1);
+        wta_flush(nsteps - 1);
     }
 }
 
@@ -358,14 +433,15 @@ template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *
         configured = true;
     }
     int nlines = a.my == 0 ? a.H : a.width1;
+    const size_t smem_h = smem + (WTA != 0 ? (size_t)WARPS * 2 * 128 * NP : 0); // + the fused WTA's exchange buffers
     if (a.my == 0 && !c->agg_legacy) {
         static bool configured_h = false;
         if (!configured_h) {
-            cudaError_t e = cudaFuncSetAttribute(agg_hscan_kernel<NP, PAD, MODE, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(agg_hscan_kernel<NP, PAD, MODE, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h);
             if (e != cudaSuccess) return e;
             configured_h = true;
         }
-        agg_hscan_kernel<NP, PAD, MODE, WTA><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
+        agg_hscan_kernel<NP, PAD, MODE, WTA><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem_h, c->stream>>>(a);
     } else
         agg_scan_kernel<NP, PAD, MODE, WTA><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
     c->launches++;
@@ -860,9 +936,12 @@ cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
     a.raw = c->raw.as<int16_t>();
     a.disp2key = c->disp2key.as<unsigned>();
     a.W = g.W; a.minX1 = g.minX1; a.minD = g.minD; a.uniq = g.uniq;
+    const int thr = 100 - g.uniq;
+    a.uniq_M = thr > 1 ? (unsigned)(((1ull << 32) + thr - 1) / thr) : 0u;
+    const bool can_fuse = c->fuse_wta && thr >= 1 && thr <= 100; // (uniquenessRatio >= 100 goes through wta_kernel)
     cudaError_t e;
     c->wta_fused = false;
-    const int n = vsweep_cols(c);
+    const int n = g.mode == 3 ? 0 : vsweep_cols(c);
     c->agg_legacy = n == 0; // the legacy path keeps the generic scan kernel for every direction (it is the cross-check)
     if (n > 0) {
         a.mx = 1; a.my = 0;
@@ -875,11 +954,27 @@ cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
         // stores S only if the volumes are kept.  Off by default: the scan is a latency-bound sequential loop (7 warps
         // per SM), and the ~60 extra dependent instructions per step cost more than the separate WTA kernel and the
         // S round trip save (measured 0.86 ms vs 0.37 + 0.41 ms at 1080p/128).
-        const int wta = c->fuse_wta ? (c->keep_volumes ? 2 : 1) : 0;
+        const int wta = can_fuse ? (c->keep_volumes ? 2 : 1) : 0;
         if ((e = launch_dir_np(c, a, g.mode == 1 ? AGG_ACCUM2 : AGG_ACCUM, wta)) != cudaSuccess) return e;
         c->wta_fused = wta != 0;
         mark();
         if (n_launches) *n_launches = 3;
+        return cudaSuccess;
+    }
+    if (g.mode == 3) {
+        // MODE_HH4 (cv2 pass 1: (+1,0) (0,+1); pass 2: (-1,0) (0,-1)): the vertical paths do not couple columns, so each is one
+        // launch of the generic scan with a warp per column; the horizontal ones use the fast row scan
+        static const int dirs4[4][2] = {{1, 0}, {0, 1}, {0, -1}, {-1, 0}};
+        c->agg_legacy = false;
+        for (int i = 0; i < 4; i++) {
+            a.mx = dirs4[i][0];
+            a.my = dirs4[i][1];
+            const int wta = (i == 3 && can_fuse) ? (c->keep_volumes ? 2 : 1) : 0;
+            if ((e = launch_dir_np(c, a, i == 0 ? AGG_INIT : AGG_ACCUM, wta)) != cudaSuccess) return e;
+            if (wta) c->wta_fused = true;
+            mark();
+        }
+        if (n_launches) *n_launches = 4;
         return cudaSuccess;
     }
     int nd = g.mode == 1 ? 8 : 5; // legacy: one scan kernel per direction

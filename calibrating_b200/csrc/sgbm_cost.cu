@@ -269,5 +269,12 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
     dim3 vg((unsigned)((row_vec + 255) / 256), (g.H + VBAND - 1) / VBAND);
     vsum_kernel<<<vg, 256, 0, c->stream>>>((const uint4 *)hs, c->C.as<uint4>(), g.H, row_vec, g.SH2);
     c->launches += 4;
+    if (g.mode == 3 && g.SH2 > 0 && g.H > 1) {
+        // MODE_HH4 of cv2 leaves the cost of the rows whose window reaches below the image (y > 0, y + SH2 >= H) constant:
+        // its column-parallel loop skips their update (found by differential testing; oracle/sgbm_ref.c, vertical half of A.3)
+        const int y0 = g.H - g.SH2 > 1 ? g.H - g.SH2 : 1;
+        cudaError_t em = cudaMemsetAsync(c->C.as<int16_t>() + (size_t)y0 * g.width1 * g.Dp, 0, (size_t)(g.H - y0) * g.width1 * g.Dp * sizeof(int16_t), c->stream);
+        if (em != cudaSuccess) return em;
+    }
     return cudaGetLastError();
 }

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _ffi
 
-MODE_SGBM, MODE_HH = 0, 1
+MODE_SGBM, MODE_HH, MODE_HH4 = 0, 1, 3  # cv2's MODE_SGBM_3WAY (2) depends on cv2's thread count and is not offered
 
 # calibrating/stereo_matching.py:29-58
 REFERENCE_DEFAULTS = dict(min_disparity=2, num_disparities=218, block_size=11, uniqueness_ratio=5, speckle_window_size=200,
@@ -82,7 +82,7 @@ class StereoSGBM:
 
 def StereoSGBM_create(minDisparity=0, numDisparities=16, blockSize=3, P1=0, P2=0, disp12MaxDiff=0, preFilterCap=0,
                       uniquenessRatio=0, speckleWindowSize=0, speckleRange=0, mode=MODE_SGBM, device=0, handle=None, cost=0):
-    """Keyword-compatible with cv2.StereoSGBM_create (MODE_SGBM=0 and MODE_HH=1 only); cost=COST_CENSUS is an extension."""
+    """Keyword-compatible with cv2.StereoSGBM_create (MODE_SGBM=0, MODE_HH=1 and MODE_HH4=3); cost=COST_CENSUS is an extension."""
     return StereoSGBM(device=device, handle=handle, min_disparity=minDisparity, num_disparities=numDisparities, block_size=blockSize,
                       P1=P1, P2=P2, disp12_max_diff=disp12MaxDiff, pre_filter_cap=preFilterCap, uniqueness_ratio=uniquenessRatio,
                       speckle_window_size=speckleWindowSize, speckle_range=speckleRange, mode=mode, cost=cost)

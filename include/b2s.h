@@ -40,7 +40,8 @@ extern "C" {
 typedef struct b2s_ctx *b2s_handle;
 
 /* Same fields and meaning as cv2.StereoSGBM_create (calibrating/stereo_matching.py:48-58);
- * mode: 0 = MODE_SGBM (5 paths, the reference default), 1 = MODE_HH (8 paths). */
+ * mode: 0 = MODE_SGBM (5 paths, the reference default), 1 = MODE_HH (8 paths), 3 = MODE_HH4 (4 paths: the two horizontal
+ * and the two vertical ones).  cv2's MODE_SGBM_3WAY (2) is rejected: its result depends on cv2's thread count. */
 typedef struct {
     int min_disparity, num_disparities, block_size;
     int P1, P2, disp12_max_diff, pre_filter_cap, uniqueness_ratio;
@@ -186,9 +187,10 @@ int b2s_undistort_img(b2s_handle h, const uint8_t *img1, int cn, uint8_t *out);
 #define B2S_FETCH_S 1    /* aggregated volume (H,width1,Dp) i16 */
 #define B2S_FETCH_RAW 2  /* (H,W) i16 disparity before median/speckle */
 #define B2S_FETCH_RIG 16 /* + k: k-th rig array in b2s_rig order: map1x map1y map2x map2y valid_mask1 unrect_mapx unrect_mapy undist_xy undist_fxy */
-/* Options (all default 0).
- * B2S_OPT_FUSE_WTA: fuse the winner-take-all step into the last aggregation pass; the aggregated volume S is then never
- *   written unless B2S_OPT_KEEP_VOLUMES is also set (B2S_FETCH_S fails otherwise).  Results are identical either way. */
+/* Options.
+ * B2S_OPT_FUSE_WTA (default 1): the winner-take-all step runs inside the last aggregation pass; the aggregated volume S is
+ *   then never written unless B2S_OPT_KEEP_VOLUMES (default 0) is also set (B2S_FETCH_S fails otherwise).  With 0 the pass
+ *   stores S and a separate kernel picks the winners.  Results are identical either way. */
 #define B2S_OPT_KEEP_VOLUMES 1
 #define B2S_OPT_FUSE_WTA 2
 int b2s_set_option(b2s_handle h, int option, int value);

@@ -8,7 +8,7 @@ import numpy as np
 
 from . import build as _build
 
-MODE_SGBM, MODE_HH = 0, 1
+MODE_SGBM, MODE_HH, MODE_HH4 = 0, 1, 3
 
 
 class SgbmParams(ctypes.Structure):

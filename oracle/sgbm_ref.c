@@ -21,7 +21,7 @@ typedef int16_t cost_t;
 typedef struct {
     int min_disparity, num_disparities, block_size;
     int P1, P2, disp12_max_diff, pre_filter_cap, uniqueness_ratio;
-    int speckle_window_size, speckle_range, mode; /* 0 = MODE_SGBM (5 paths), 1 = MODE_HH (8 paths) */
+    int speckle_window_size, speckle_range, mode; /* 0 = MODE_SGBM (5 paths), 1 = MODE_HH (8 paths), 3 = MODE_HH4 (4 paths) */
     int cost; /* 0 = Birchfield-Tomasi + box sum (cv2); 1 = 9x7 census / Hamming (BASELINE config 4; NOT in cv2: parity unpinned) */
 } sgbm_params;
 
@@ -160,12 +160,14 @@ int oracle_sgbm_compute(const uint8_t *left, const uint8_t *right, int H, int W,
     int P1 = prm->P1 > 0 ? prm->P1 : 2;
     int P2 = imax(prm->P2 > 0 ? prm->P2 : 5, P1 + 1);
     if (minD < 0) return -2;
+    if (prm->mode != 0 && prm->mode != 1 && prm->mode != 3) return -2; /* MODE_SGBM_3WAY depends on cv2's thread count: not restated */
     int minX1 = imax(maxD, 0), maxX1 = W + imin(minD, 0);
     int D = maxD - minD, width1 = maxX1 - minX1;
     const int DISP_SHIFT = 4, DISP_SCALE = 16;
     int INVALID = (minD - 1) * DISP_SCALE;
     if (W - maxD <= SW2 || D <= 0) return -1;
 
+    const int hh4 = prm->mode == 3; /* MODE_HH4: two passes, only the horizontal and the vertical path of each */
     size_t row = (size_t)width1 * D, vol = row * H;
     cost_t *Cv = (cost_t *)malloc(vol * sizeof(cost_t));
     cost_t *Sv = (cost_t *)calloc(vol, sizeof(cost_t));
@@ -215,9 +217,12 @@ int oracle_sgbm_compute(const uint8_t *left, const uint8_t *right, int H, int W,
                 h[(size_t)x1 * D + d] = (cost_t)s;
             }
     }
-    /* vertical half of A.3 */
+    /* vertical half of A.3.  MODE_HH4 quirk (cv2 4.13, found by differential testing, tests/test_oracle.py): the rows whose
+     * window reaches below the image (y > 0 and y + SH2 >= H) keep a constant cost -- cv2's column-parallel cost loop skips
+     * the "k >= height" update -- which is the same as C = 0 for them (L and S of such a row only see the path terms). */
     for (int y = 0; y < H; y++) {
         cost_t *c = Cv + (size_t)y * row;
+        if (hh4 && y > 0 && y + SH2 >= H) { memset(c, 0, row * sizeof(cost_t)); continue; }
         for (size_t i = 0; i < row; i++) {
             int s = 0;
             for (int k = -SH2; k <= SH2; k++) s += hs[(size_t)clampi(y + k, 0, H - 1) * row + i];
@@ -230,7 +235,7 @@ int oracle_sgbm_compute(const uint8_t *left, const uint8_t *right, int H, int W,
     /* A.4 aggregation */
     int16_t *raw = (int16_t *)malloc((size_t)H * W * sizeof(int16_t));
     for (size_t i = 0; i < (size_t)H * W; i++) raw[i] = (int16_t)INVALID;
-    int npass = prm->mode == 1 ? 2 : 1;
+    int npass = (prm->mode == 1 || prm->mode == 3) ? 2 : 1;
     /* Lr rows: [2 rows][4 dirs][width1+2][D], minLr likewise; x index shifted by +1 so that x=-1 and x=width1 are zero */
     size_t lrow = (size_t)(width1 + 2) * D;
     cost_t *Lr = (cost_t *)calloc(2 * 4 * lrow, sizeof(cost_t));
@@ -264,6 +269,11 @@ int oracle_sgbm_compute(const uint8_t *left, const uint8_t *right, int H, int W,
                 cost_t *o0 = Lc + 0 * lrow + (size_t)xi * D, *o1 = Lc + 1 * lrow + (size_t)xi * D;
                 cost_t *o2 = Lc + 2 * lrow + (size_t)xi * D, *o3 = Lc + 3 * lrow + (size_t)xi * D;
                 mc[0 * (width1 + 2) + xi] = (cost_t)path_step(Cp, Lc + 0 * lrow + (size_t)(xi - dx) * D, mc[0 * (width1 + 2) + xi - dx], o0, D, P1, P2);
+                if (hh4) {
+                    mc[2 * (width1 + 2) + xi] = (cost_t)path_step(Cp, Lp + 2 * lrow + (size_t)xi * D, mp[2 * (width1 + 2) + xi], o2, D, P1, P2);
+                    for (int d = 0; d < D; d++) Sp[d] = sat16((int)Sp[d] + o0[d] + o2[d]);
+                    continue;
+                }
                 mc[1 * (width1 + 2) + xi] = (cost_t)path_step(Cp, Lp + 1 * lrow + (size_t)(xi - dx) * D, mp[1 * (width1 + 2) + xi - dx], o1, D, P1, P2);
                 mc[2 * (width1 + 2) + xi] = (cost_t)path_step(Cp, Lp + 2 * lrow + (size_t)xi * D, mp[2 * (width1 + 2) + xi], o2, D, P1, P2);
                 mc[3 * (width1 + 2) + xi] = (cost_t)path_step(Cp, Lp + 3 * lrow + (size_t)(xi + dx) * D, mp[3 * (width1 + 2) + xi + dx], o3, D, P1, P2);

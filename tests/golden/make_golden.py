@@ -104,15 +104,15 @@ def main():
         res = st.get_depth(img1, img2, return_distort_depth=True)
     np.savez_compressed(os.path.join(HERE, "rig320_distort.npz"), unrectify_depth=res["unrectify_depth"],
                         distort_depth=res["distort_depth"])
-    # --- case C: raw cv2.StereoSGBM outputs on a small rectified pair, both modes (pins oracle/sgbm_ref.c)
+    # --- case C: raw cv2.StereoSGBM outputs on a small rectified pair, MODE_SGBM / MODE_HH / MODE_HH4 (pins oracle/sgbm_ref.c)
     l, r, _ = synth.rectified_pair(96, 200, 48, seed=3)
-    for mode, name in ((0, "sgbm"), (1, "hh")):
+    for mode, name in ((0, "sgbm"), (1, "hh"), (3, "hh4")):
         m = cv2.StereoSGBM_create(minDisparity=0, numDisparities=48, blockSize=5, P1=8 * 3 * 25, P2=32 * 3 * 25,
                                   disp12MaxDiff=1, uniquenessRatio=5, speckleWindowSize=50, speckleRange=2, mode=mode)
         out[name] = m.compute(l, r)
     m = cv2.StereoSGBM_create(minDisparity=2, numDisparities=40, blockSize=11, P1=968, P2=3872, disp12MaxDiff=0,
                               uniquenessRatio=5, speckleWindowSize=200, speckleRange=2)
-    np.savez_compressed(os.path.join(HERE, "sgbm_small.npz"), left=l, right=r, disp_sgbm=out["sgbm"], disp_hh=out["hh"],
+    np.savez_compressed(os.path.join(HERE, "sgbm_small.npz"), left=l, right=r, disp_sgbm=out["sgbm"], disp_hh=out["hh"], disp_hh4=out["hh4"],
                         disp_refparams=m.compute(l, r), cv2_version=cv2.__version__)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")), "cv2", cv2.__version__)
 

@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 def handle():
     from calibrating_b200 import _ffi
     h = _ffi.Handle(0)
+    h.keep_volumes(True)  # the stage-level checks fetch S (by default the last pass fuses the WTA and does not store it)
     yield h
     h.close()
 
@@ -24,7 +25,7 @@ def _case(rng, D=None, cn=None, mode=None, minD=None, bs=None):
     D = D or int(rng.choice([16, 24, 32, 48, 64, 70, 100, 128, 130, 200, 218, 256]))
     minD = int(rng.choice([0, 2, 3, 5])) if minD is None else minD
     cn = cn or int(rng.choice([1, 3]))
-    mode = int(rng.choice([0, 1])) if mode is None else mode
+    mode = int(rng.choice([0, 1, 3])) if mode is None else mode
     bs = bs or int(rng.choice([1, 3, 5, 7, 9, 11]))
     h = int(rng.integers(12, 70))
     w = int(rng.integers(D + minD + 12, D + minD + 150))
@@ -47,18 +48,18 @@ def test_stage_parity_random(handle, seed):
     got = m.compute(l, r)
     assert np.array_equal(handle.fetch_volume(0), ref["C"]), "cost volume"
     assert np.array_equal(handle.fetch_volume(1), ref["S"]), "aggregated volume"
-    if seed % 2 == 0:  # the same through the fused winner-take-all (S not stored, then stored on request)
-        handle.fuse_wta(True)
+    if seed % 2 == 0:  # the default configuration (S not stored) and the separate winner-take-all kernel
+        handle.keep_volumes(False)
         try:
-            assert np.array_equal(m.compute(l, r), ref["disp"]), "winner-take-all fused into the last scan"
+            assert np.array_equal(m.compute(l, r), ref["disp"]), "winner-take-all fused into the last scan, S not stored"
             with pytest.raises(Exception, match="not stored"):
                 handle.fetch_volume(1)
-            handle.keep_volumes(True)
-            assert np.array_equal(m.compute(l, r), ref["disp"])
-            assert np.array_equal(handle.fetch_volume(1), ref["S"]), "aggregated volume kept by the fused pass"
-        finally:
-            handle.keep_volumes(False)
             handle.fuse_wta(False)
+            assert np.array_equal(m.compute(l, r), ref["disp"]), "separate winner-take-all kernel"
+            assert np.array_equal(handle.fetch_volume(1), ref["S"]), "aggregated volume stored by the unfused pass"
+        finally:
+            handle.keep_volumes(True)
+            handle.fuse_wta(True)
     # (the device keeps the pre-L/R-check WTA map; the L/R check is fused into the median kernel's loads)
     assert np.array_equal(got, ref["disp"]), "WTA / uniqueness / subpixel / L-R check / median / speckle"
     f = m.compute_float(l, r)
@@ -92,12 +93,13 @@ def test_golden_vectors(handle, golden_dir):
                   uniqueness_ratio=5, speckle_window_size=50, speckle_range=2)
     assert np.array_equal(cb.StereoSGBM(handle=handle, mode=0, **common).compute(l, r), g["disp_sgbm"])
     assert np.array_equal(cb.StereoSGBM(handle=handle, mode=1, **common).compute(l, r), g["disp_hh"])
+    assert np.array_equal(cb.StereoSGBM(handle=handle, mode=cb.MODE_HH4, **common).compute(l, r), g["disp_hh4"])
     m = cb.StereoSGBM_create(minDisparity=2, numDisparities=40, blockSize=11, P1=968, P2=3872, disp12MaxDiff=0, uniquenessRatio=5,
                              speckleWindowSize=200, speckleRange=2, handle=handle)
     assert np.array_equal(m.compute(l, r), g["disp_refparams"])
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 3])
 def test_vs_cv2_live_640(handle, mode):
     cv2 = pytest.importorskip("cv2")
     l, r, _ = synth.rectified_pair(480, 640, 64, seed=7)
@@ -157,6 +159,22 @@ def test_errors(handle):
         cb.StereoSGBM(handle=handle, num_disparities=0)
     with pytest.raises(ValueError):
         cb.StereoSGBM(handle=handle, num_disparities=16, mode=2)
+
+
+@pytest.mark.parametrize("uniq", [1, 50, 90, 99, 100, 150])
+@pytest.mark.parametrize("D", [32, 70, 128])
+def test_extreme_uniqueness(handle, uniq, D):
+    """The fused WTA turns S(d) * (100 - uniq) < minS * 100 into S(d) < ceil(minS * 100 / (100 - uniq)) with a multiply-high
+    division; ratios >= 100 fall back to the separate kernel.  Noise and textured pairs, gray and RGB."""
+    rng = np.random.default_rng(uniq * 7 + D)
+    for k in range(2):
+        if k == 0:
+            l, r, _ = synth.rectified_pair(40, D + 90, D, uniq, 1)
+        else:
+            l = rng.integers(0, 256, (33, D + 50, 3), dtype=np.uint8)
+            r = rng.integers(0, 256, (33, D + 50, 3), dtype=np.uint8)
+        p = dict(num_disparities=D, block_size=3, P1=72, P2=288, disp12_max_diff=1, uniqueness_ratio=uniq, mode=k)
+        assert np.array_equal(cb.StereoSGBM(handle=handle, **p).compute(l, r), osgbm.sgbm_compute(l, r, **p)), (uniq, D, k)
 
 
 def test_textureless_and_saturated(handle):
@@ -256,7 +274,7 @@ def test_census_4k_256_accuracy(handle):
 
 
 @pytest.mark.parametrize("shape", [(1, 40), (2, 41), (3, 60), (5, 37), (9, 300)])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 3])
 def test_degenerate_shapes(handle, shape, mode):
     """Images of one to a few rows and cost volumes a few columns wide (fewer rows than the cp.async ring is deep, strips of a
     single column pair, block windows larger than the image) against the oracle."""

@@ -19,16 +19,19 @@ def test_sgbm_oracle_vs_golden(golden_dir):
                   uniqueness_ratio=5, speckle_window_size=50, speckle_range=2)
     assert np.array_equal(osgbm.sgbm_compute(l, r, mode=0, **common), g["disp_sgbm"])
     assert np.array_equal(osgbm.sgbm_compute(l, r, mode=1, **common), g["disp_hh"])
+    assert np.array_equal(osgbm.sgbm_compute(l, r, mode=3, **common), g["disp_hh4"])
     ref = osgbm.sgbm_compute(l, r, min_disparity=2, num_disparities=40, block_size=11, P1=968, P2=3872, disp12_max_diff=0,
                              uniqueness_ratio=5, speckle_window_size=200, speckle_range=2)
     assert np.array_equal(ref, g["disp_refparams"])
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(20))
 def test_sgbm_oracle_vs_cv2_random(seed):
     rng = np.random.default_rng(100 + seed)
     h = int(rng.integers(20, 60)); D = int(rng.choice([16, 24, 32, 48, 70])); minD = int(rng.choice([0, 2, 3, 5]))
     w = int(rng.integers(D + minD + 12, D + minD + 90)); cn = int(rng.choice([1, 3])); mode = int(rng.choice([0, 1]))
+    if seed >= 12:
+        mode = 3  # MODE_HH4
     bs = int(rng.choice([1, 3, 5, 7, 9, 11])); uniq = int(rng.choice([0, 1, 5, 10, 15])); d12 = int(rng.choice([-1, 0, 1, 2, 100]))
     spk = int(rng.choice([0, 20, 200]))
     P1, P2 = 8 * cn * bs * bs, 32 * cn * bs * bs
@@ -41,6 +44,14 @@ def test_sgbm_oracle_vs_cv2_random(seed):
                                 uniquenessRatio=uniq, speckleWindowSize=spk, speckleRange=2, mode=mode).compute(l, r)
     got = osgbm.sgbm_compute(l, r, min_disparity=minD, num_disparities=D, block_size=bs, P1=P1, P2=P2, disp12_max_diff=d12,
                              uniqueness_ratio=uniq, speckle_window_size=spk, speckle_range=2, mode=mode)
+    assert np.array_equal(ref, got)
+
+
+@pytest.mark.parametrize("uniq", [50, 99, 100, 150])
+def test_sgbm_oracle_extreme_uniqueness(uniq):
+    l, r, _ = synth.rectified_pair(40, 120, 32, 5, 1)
+    ref = cv2.StereoSGBM_create(0, 32, 3, 72, 288, 1, 0, uniq, 0, 0, 1).compute(l, r)
+    got = osgbm.sgbm_compute(l, r, num_disparities=32, block_size=3, P1=72, P2=288, disp12_max_diff=1, uniqueness_ratio=uniq, mode=1)
     assert np.array_equal(ref, got)
 
 

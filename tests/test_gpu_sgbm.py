@@ -177,6 +177,23 @@ def test_extreme_uniqueness(handle, uniq, D):
         assert np.array_equal(cb.StereoSGBM(handle=handle, **p).compute(l, r), osgbm.sgbm_compute(l, r, **p)), (uniq, D, k)
 
 
+@pytest.mark.parametrize("P1,P2", [(100, 8000), (4000, 12000), (11000, 12000), (1, 2)])
+def test_large_penalties(handle, P1, P2):
+    """Penalties far above the reference's, inside the domain where cv2 itself is well defined: max C + 2 * P2 <= 32767, so that
+    no int16 sum inside cv2's SIMD adds saturates (outside it cv2's result depends on its SIMD width; tests/test_oracle.py)."""
+    for k, (cn, bs) in enumerate([(1, 3), (3, 5)]):
+        l, r, _ = synth.rectified_pair(36, 150, 48, 40 + k, cn)
+        if k:
+            r = np.random.default_rng(3).integers(0, 256, r.shape, dtype=np.uint8)
+        for mode in (0, 1, 3):
+            p = dict(num_disparities=48, block_size=bs, P1=P1, P2=P2, disp12_max_diff=1, uniqueness_ratio=5, mode=mode)
+            ref = osgbm.sgbm_compute(l, r, want_volumes=True, **p)
+            assert int(ref["C"].max()) + 2 * P2 <= 32767
+            got = cb.StereoSGBM(handle=handle, **p).compute(l, r)
+            assert np.array_equal(handle.fetch_volume(1), ref["S"]), (cn, bs, mode, "S")
+            assert np.array_equal(got, ref["disp"]), (cn, bs, mode)
+
+
 def test_textureless_and_saturated(handle):
     """Constant images (all costs tie) and maximal-contrast noise (S saturates at 32767 with the reference's P2)."""
     for l, r in [(np.full((40, 300, 3), 128, np.uint8),) * 2,

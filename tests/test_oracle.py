@@ -55,6 +55,21 @@ def test_sgbm_oracle_extreme_uniqueness(uniq):
     assert np.array_equal(ref, got)
 
 
+@pytest.mark.parametrize("P1,P2", [(100, 8000), (4000, 12000), (11000, 12000)])
+def test_sgbm_oracle_large_penalties(P1, P2):
+    """Inside max C + 2 * P2 <= 32767 the int16 sums of cv2 never saturate and the restatement (int arithmetic) is exact.
+    Beyond that bound (e.g. P2 = 30000) cv2's saturating SIMD adds and its scalar tail disagree with each other, so its
+    result depends on the SIMD width of the build: not part of the parity claim."""
+    l, r, _ = synth.rectified_pair(36, 150, 48, 41, 3)
+    r = np.random.default_rng(3).integers(0, 256, r.shape, dtype=np.uint8)
+    for mode in (0, 1, 3):
+        ref = cv2.StereoSGBM_create(0, 48, 5, P1, P2, 1, 0, 5, 0, 0, mode).compute(l, r)
+        got = osgbm.sgbm_compute(l, r, num_disparities=48, block_size=5, P1=P1, P2=P2, disp12_max_diff=1, uniqueness_ratio=5, mode=mode,
+                                 want_volumes=True)
+        assert int(got["C"].max()) + 2 * P2 <= 32767
+        assert np.array_equal(ref, got["disp"]), mode
+
+
 def test_sgbm_oracle_precondition():
     l = np.zeros((20, 30), np.uint8)
     with pytest.raises(ValueError):

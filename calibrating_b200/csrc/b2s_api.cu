@@ -78,7 +78,7 @@ int b2s_destroy(b2s_handle c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->left, &c->right, &c->planesL, &c->planesR, &c->C, &c->S, &c->S2, &c->raw, &c->disp16, &c->disp2key, &c->labels,
-                      &c->sizes, &c->med, &c->dispf, &c->agg_ho, &c->map1x, &c->map1y, &c->map2x, &c->map2y, &c->vmask, &c->umapx, &c->umapy,
+                      &c->sizes, &c->med, &c->dispf, &c->agg_ho, &c->agg_errbuf, &c->map1x, &c->map1y, &c->map2x, &c->map2y, &c->vmask, &c->umapx, &c->umapy,
                       &c->und_xy, &c->und_fxy, &c->img1, &c->img2, &c->rect1, &c->rect2, &c->und1, &c->dispfinal, &c->rdepth,
                       &c->udepth, &c->lanczos_tab, &c->stage_f32, &c->dkey, &c->ddepth, &c->pkey, &c->pin, &c->pout};
     for (DevBuf *b : bufs) b->release();

@@ -68,6 +68,7 @@ struct b2s_ctx {
     DevBuf med;               // (H,W) int16 (median output before speckle)
     DevBuf dispf;             // (H,W) f32
     DevBuf agg_ho;            // hand-over rings of the fused vertical sweep + its error flag (sgbm_agg.cu)
+    DevBuf agg_errbuf;        // the aggregation kernels' device error flag
     int *agg_err = nullptr;   // device address of that flag (valid after an aggregation was enqueued)
 
     // rig

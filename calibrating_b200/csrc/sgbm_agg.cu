@@ -46,6 +46,7 @@ struct AggArgs {
     int16_t *raw;
     unsigned *disp2key;
     int W, minX1, minD, uniq;
+    int *err;        // device error flag (sgbm_agg.cu: wait_expired), set if a bulk copy never completes
     unsigned uniq_M; // ceil(2^32 / (100 - uniq)): the fused WTA's division by the invariant (100 - uniq) (0 < 100 - uniq <= 100)
 };
 
@@ -134,6 +135,60 @@ __device__ __forceinline__ void sgm_step(uint32_t (&T)[NP], const uint32_t (&c)[
         T[i] = L[i] - m; // both halves of L are >= their half of m: the 32-bit difference has no borrow = packed difference
         if (PAD) T[i] |= padmask[i];
     }
+}
+
+// ---- spin-wait guard and mbarrier helpers (fused vertical sweep and the bulk-copy pipeline of the horizontal scans) ----
+constexpr int HO_SLOTS = 4;
+constexpr unsigned long long WAIT_TIMEOUT_NS = 2000000000ull; // a hand-over / neighbour wait longer than 2 s is a lost strip: flag it, do not hang
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// slow path of the spin loops: true when the wait should be abandoned (timeout, or another warp already flagged an error)
+__device__ __forceinline__ bool wait_expired(int spins, unsigned long long &t0, int *err)
+{
+    if ((spins & 255) != 0) return false;
+    if (*(volatile int *)err != 0) return true;
+    const unsigned long long now = global_ns();
+    if (t0 == 0) t0 = now;
+    return now - t0 > WAIT_TIMEOUT_NS;
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t addr)
+{
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(addr) : "memory");
+}
+// wait until the phase of parity `parity` of the mbarrier has completed (acquire)
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity, int *err)
+{
+    uint32_t ok;
+    int spins = 0;
+    unsigned long long t0 = 0;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (!ok && wait_expired(++spins, t0, err)) {
+            *(volatile int *)err = 1;
+            break;
+        }
+    } while (!ok);
+}
+
+// 1-D bulk copy global -> shared (UBLKCP), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t sdst, const void *gsrc, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t addr, uint32_t bytes)
+{
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(addr), "r"(bytes) : "memory");
 }
 
 // WTA: 0 = store S; 1 = winner-take-all fused (A.5), S not stored; 2 = both (debug: S stays fetchable)
@@ -259,40 +314,50 @@ __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
 }
 
 // Horizontal lines only (my == 0), the two scans of the production schedule: same arithmetic as agg_scan_kernel, but the
-// per-step overhead is cut to the bone (a scan line is ONE warp's in-order instruction stream of 1792 dependent steps, so
-// its length is the kernel's duration): incremental 64-bit pointers, 32-bit shared addresses, the step of sgm_step.
+// per-step overhead is cut to the bone.  A scan line is ONE warp's in-order instruction stream of 1792 dependent steps and an
+// SM holds only 8 such warps, so the kernel's duration is (instructions per step) x (~4 cycles): the C / S / S2 chunks of
+// HS_CPX consecutive pixels are contiguous in memory and arrive by ONE bulk copy per source (cp.async.bulk -> UBLKCP, issued
+// by lane 0, completion counted on an mbarrier per ring slot), which leaves a step with its LDS, the arithmetic and a store.
+template <int NP> struct HsChunk { static constexpr int px = NP == 1 ? 16 : (NP == 2 ? 8 : 4); }; // pixels per bulk copy (<= 2 KB per source)
+constexpr int HS_SLOTS = 4;                                                                       // ring slots (chunks) per warp
 template <int NP, bool PAD, int MODE, int WTA>
 __global__ void __launch_bounds__(WARPS * 32) agg_hscan_kernel(AggArgs a)
 {
     constexpr int CH = 128 * NP;                       // bytes of one pixel's d-chunk
     constexpr int NSRC = MODE == AGG_ACCUM2 ? 3 : (MODE == AGG_ACCUM ? 2 : 1); // C only; C and S; C, S and S2
-    constexpr int STAGE_BYTES = CH * NSRC;
-    constexpr int STAGES = Stages<NP>::value;
-    constexpr int NSEG = STAGE_BYTES / 16, NLD = (NSEG + 31) / 32;
+    constexpr int CPX = HsChunk<NP>::px;
+    constexpr int SRC_BYTES = CPX * CH;                // one source's part of a slot
+    constexpr int SLOT_BYTES = NSRC * SRC_BYTES;
+    constexpr int RING_BYTES = HS_SLOTS * SLOT_BYTES;  // per warp
     extern __shared__ __align__(16) unsigned char smem[];
+    // shared memory: rings [WARPS][HS_SLOTS][NSRC][CPX][CH], WTA exchange buffers [WARPS][2][CH], mbarriers [WARPS][HS_SLOTS]
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t mb0 = sm0 + WARPS * RING_BYTES + (WTA != 0 ? WARPS * 2 * CH : 0);
+    if (threadIdx.x < WARPS * HS_SLOTS) mbar_init(mb0 + threadIdx.x * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int y = blockIdx.x * WARPS + wid;
     if (y >= a.H) return;
     const int Dp = 64 * NP, nsteps = a.width1;
-    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem) + wid * (STAGES * STAGE_BYTES);
+    const int nchunks = (nsteps + CPX - 1) / CPX;
+    const uint32_t ring = sm0 + wid * RING_BYTES, mbw = mb0 + wid * (HS_SLOTS * 8);
     const long long stepE = (long long)a.mx * Dp; // int16 elements to the next pixel of the line
-    const long long o0 = ((long long)y * a.width1 + (a.mx > 0 ? 0 : a.width1 - 1)) * Dp;
-    const int16_t *src[NLD];
-    uint32_t dsto[NLD];
-#pragma unroll
-    for (int q = 0; q < NLD; q++) {
-        const int seg = lane + 32 * q;
-        const int which = seg / (CH / 16), r = seg % (CH / 16);
-        src[q] = (which == 0 ? a.C : (which == 1 ? (const int16_t *)a.S : a.S2)) + o0 + r * 8;
-        dsto[q] = ring + seg * 16;
-    }
-    auto issue = [&](int stage) {
-#pragma unroll
-        for (int q = 0; q < NLD; q++) {
-            if (lane + 32 * q < NSEG) cp_async16_s(dsto[q] + stage * STAGE_BYTES, src[q]);
-            src[q] += stepE;
+    const long long row0 = (long long)y * a.width1 * Dp;
+    const long long o0 = row0 + (long long)(a.mx > 0 ? 0 : a.width1 - 1) * Dp;
+    // chunk j = steps [j*CPX, j*CPX + npx): pixels x0 .. x0 + npx - 1 in memory order (x0 = first step's x for +x, last step's for -x)
+    auto issue = [&](int j) {
+        if (lane == 0) {
+            const int k0 = j * CPX, npx = min(CPX, nsteps - k0);
+            const int x0 = a.mx > 0 ? k0 : a.width1 - k0 - npx;
+            const uint32_t slot = ring + (j % HS_SLOTS) * SLOT_BYTES, mb = mbw + (j % HS_SLOTS) * 8, bytes = (uint32_t)npx * CH;
+            const long long o = row0 + (long long)x0 * Dp;
+            mbar_arrive_expect_tx(mb, bytes * NSRC);
+            bulk_g2s(slot, a.C + o, bytes, mb);
+            if (NSRC > 1) bulk_g2s(slot + SRC_BYTES, a.S + o, bytes, mb);
+            if (NSRC > 2) bulk_g2s(slot + 2 * SRC_BYTES, a.S2 + o, bytes, mb);
         }
     };
     uint32_t padmask[NP];
@@ -304,20 +369,15 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_kernel(AggArgs a)
     const uint32_t P1v = (uint32_t)a.P1 * 0x10001u, P2mP1v = (uint32_t)(a.P2 - a.P1) * 0x10001u;
     const uint32_t BIG = 0x7FFF7FFFu;
 #pragma unroll 1
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < nsteps) issue(s);
-        cp_async_commit();
-    }
+    for (int j = 0; j < HS_SLOTS - 1 && j < nchunks; j++) issue(j);
     uint32_t T[NP];
 #pragma unroll
     for (int i = 0; i < NP; i++) T[i] = padmask[i];
     int16_t *sp = a.S + o0 + lane * 2 * NP;
     const int xfirst = a.mx > 0 ? 0 : a.width1 - 1;
-    int stage = 0, pstage = STAGES - 1;
-    const uint32_t cur0 = ring + lane * NP * 4;
     // ---- fused winner-take-all (WTA != 0): A.5 of SURVEY.md, same rule as wta_kernel in sgbm_post.cu ----
-    // per-warp exchange buffer (two pixels) behind the cp.async rings: the sub-pixel fit needs S(best-1), S(best+1) of other lanes
-    const uint32_t xbase = (uint32_t)__cvta_generic_to_shared(smem) + WARPS * (STAGES * STAGE_BYTES) + wid * (2 * CH);
+    // per-warp exchange buffer (two pixels) behind the rings: the sub-pixel fit needs S(best-1), S(best+1) of other lanes
+    const uint32_t xbase = sm0 + WARPS * RING_BYTES + wid * (2 * CH);
     const uint32_t xbuf = xbase + lane * NP * 4;
     uint32_t dd[NP], prev[NP], kmin = 0;
 #pragma unroll
@@ -375,45 +435,50 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_kernel(AggArgs a)
         my_sm = rec ? (int)(short)lo : my_sm;
         my_sp = rec ? (int)(short)hi : my_sp;
     };
+    int k = 0; // step index along the line
 #pragma unroll 1
-    for (int k = 0; k < nsteps; k++) {
-        __syncwarp();
-        if (k + STAGES - 1 < nsteps) issue(pstage);
-        cp_async_commit();
-        cp_async_wait<STAGES - 1>();
-        __syncwarp();
-        const uint32_t cur = cur0 + stage * STAGE_BYTES;
-        uint32_t c[NP], sv[NP], L[NP], out[NP];
-        lds_s<NP>(cur, c);
-        if (MODE != AGG_INIT) lds_s<NP>(cur + CH, sv);
-        if (MODE == AGG_ACCUM2) {
-            uint32_t s2[NP];
-            lds_s<NP>(cur + 2 * CH, s2);
+    for (int j = 0; j < nchunks; j++) {
+        __syncwarp(); // every lane is done with the slot of chunk j-1: it is refilled now (generic reads before an async-proxy write)
+        if (j + HS_SLOTS - 1 < nchunks) issue(j + HS_SLOTS - 1);
+        mbar_wait(mbw + (j % HS_SLOTS) * 8, (uint32_t)(j / HS_SLOTS) & 1u, a.err);
+        const int npx = min(CPX, nsteps - j * CPX);
+        // shared address of this lane's part of the current pixel, walking the chunk in scan order
+        uint32_t cur = ring + (j % HS_SLOTS) * SLOT_BYTES + lane * NP * 4 + (a.mx > 0 ? 0 : (npx - 1) * CH);
+        const int curstep = a.mx > 0 ? CH : -CH;
+#pragma unroll 1
+        for (int s = 0; s < npx; s++, k++) {
+            uint32_t c[NP], sv[NP], L[NP], out[NP];
+            lds_s<NP>(cur, c);
+            if (MODE != AGG_INIT) lds_s<NP>(cur + SRC_BYTES, sv);
+            if (MODE == AGG_ACCUM2) {
+                uint32_t s2[NP];
+                lds_s<NP>(cur + 2 * SRC_BYTES, s2);
 #pragma unroll
-            for (int i = 0; i < NP; i++) sv[i] = __viaddmin_u16x2(sv[i], s2[i], BIG);
-        }
-        sgm_step<NP, PAD>(T, c, L, padmask, P1v, P2mP1v, lane);
-#pragma unroll
-        for (int i = 0; i < NP; i++) out[i] = (MODE != AGG_INIT) ? __viaddmin_u16x2(sv[i], L[i], BIG) : L[i];
-        if (WTA != 1) stcg_regs<NP>(sp, out);
-        if (WTA != 0) {
-            // winner-take-all of the pixel just finished, software-pipelined by one step so that its warp reduction, vote and
-            // shared-memory round trip overlap the next step's dependent chain instead of extending this one
-            wta_finish(k - 1);
-            sts_s<NP>(xbuf + (k & 1) * CH, out);
-            uint32_t key = 0xFFFFFFFFu;
-#pragma unroll
-            for (int i = 0; i < NP; i++) {
-                // keys (S << 16) | d of the two halves; a padded lane (d >= D) holds S = 0x7FFF and a larger d, so it never wins
-                key = min(key, min(__byte_perm(out[i], dd[i], 0x1054), __byte_perm(out[i], dd[i], 0x3276)));
-                prev[i] = out[i];
+                for (int i = 0; i < NP; i++) sv[i] = __viaddmin_u16x2(sv[i], s2[i], BIG);
             }
-            kmin = __reduce_min_sync(0xffffffffu, key);
-            if ((k & 31) == 0 && k > 0) wta_flush(k - 1); // steps k-32 .. k-1 are complete
+            sgm_step<NP, PAD>(T, c, L, padmask, P1v, P2mP1v, lane);
+#pragma unroll
+            for (int i = 0; i < NP; i++) out[i] = (MODE != AGG_INIT) ? __viaddmin_u16x2(sv[i], L[i], BIG) : L[i];
+            if (WTA != 1) stcg_regs<NP>(sp, out);
+            if (WTA != 0) {
+                // winner-take-all of the pixel just finished, software-pipelined by one step so that its warp reduction, vote and
+                // shared-memory round trip overlap the next step's dependent chain instead of extending this one
+                __syncwarp(); // the exchange buffer written in the previous step is read by other lanes below
+                wta_finish(k - 1);
+                sts_s<NP>(xbuf + (k & 1) * CH, out);
+                uint32_t key = 0xFFFFFFFFu;
+#pragma unroll
+                for (int i = 0; i < NP; i++) {
+                    // keys (S << 16) | d of the two halves; a padded lane (d >= D) holds S = 0x7FFF and a larger d, so it never wins
+                    key = min(key, min(__byte_perm(out[i], dd[i], 0x1054), __byte_perm(out[i], dd[i], 0x3276)));
+                    prev[i] = out[i];
+                }
+                kmin = __reduce_min_sync(0xffffffffu, key);
+                if ((k & 31) == 0 && k > 0) wta_flush(k - 1); // steps k-32 .. k-1 are complete
+            }
+            sp += stepE;
+            cur += curstep;
         }
-        sp += stepE;
-        pstage = stage;
-        stage = stage + 1 == STAGES ? 0 : stage + 1;
     }
     if (WTA != 0 && nsteps > 0) {
         __syncwarp();
@@ -433,7 +498,8 @@ template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *
         configured = true;
     }
     int nlines = a.my == 0 ? a.H : a.width1;
-    const size_t smem_h = smem + (WTA != 0 ? (size_t)WARPS * 2 * 128 * NP : 0); // + the fused WTA's exchange buffers
+    // horizontal scans: bulk-copy rings + the fused WTA's exchange buffers + one mbarrier per ring slot
+    const size_t smem_h = (size_t)WARPS * HS_SLOTS * (STAGE_BYTES * HsChunk<NP>::px) + (WTA != 0 ? (size_t)WARPS * 2 * 128 * NP : 0) + WARPS * HS_SLOTS * 8;
     if (a.my == 0 && !c->agg_legacy) {
         static bool configured_h = false;
         if (!configured_h) {
@@ -468,7 +534,6 @@ cudaError_t launch_dir_np(b2s_ctx *c, const AggArgs &a, int mode, int wta = 0)
     }
 }
 
-
 // ================================================================================================================
 // Fused vertical sweep: the three directions that cross image rows, for the top-down sweep (moves (+1,+1) (0,+1) (-1,+1))
 // and -- MODE_HH -- the bottom-up sweep (moves (+1,-1) (0,-1) (-1,-1)) in ONE launch that reads C once per sweep
@@ -494,24 +559,6 @@ struct VsArgs {
     uint32_t *ho; // hand-over rings [J][G-1][2][HO_SLOTS][32*NP] u32
     int *err;     // set to 1 if a hand-over wait timed out (never in a correct run)
 };
-constexpr int HO_SLOTS = 4;
-constexpr unsigned long long WAIT_TIMEOUT_NS = 2000000000ull; // a hand-over / neighbour wait longer than 2 s is a lost strip: flag it, do not hang
-__device__ __forceinline__ unsigned long long global_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-// slow path of the spin loops: true when the wait should be abandoned (timeout, or another warp already flagged an error)
-__device__ __forceinline__ bool wait_expired(int spins, unsigned long long &t0, int *err)
-{
-    if ((spins & 255) != 0) return false;
-    if (*(volatile int *)err != 0) return true;
-    const unsigned long long now = global_ns();
-    if (t0 == 0) t0 = now;
-    return now - t0 > WAIT_TIMEOUT_NS;
-}
-
 template <int NP> __device__ __forceinline__ void lds_regs(const uint32_t *src, uint32_t (&v)[NP])
 {
     if constexpr (NP == 2) { uint2 t = *(const uint2 *)src; v[0] = t.x; v[1] = t.y; }
@@ -579,30 +626,6 @@ template <int NP> __device__ __forceinline__ void ho_write(uint32_t *p, uint32_t
 #pragma unroll
         for (int i = 0; i < NP; i++) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p + i), "r"(v[i]) : "memory");
     }
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t addr)
-{
-    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(addr) : "memory");
-}
-// wait until the phase of parity `parity` of the mbarrier has completed (acquire)
-__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity, int *err)
-{
-    uint32_t ok;
-    int spins = 0;
-    unsigned long long t0 = 0;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-        if (!ok && wait_expired(++spins, t0, err)) {
-            *(volatile int *)err = 1;
-            break;
-        }
-    } while (!ok);
 }
 
 // JW = sweeps handled by one CTA (2: warps [0,n) run the top-down sweep, warps [n,2n) the bottom-up sweep; 1: a.up selects),
@@ -879,14 +902,12 @@ cudaError_t launch_vsweep(b2s_ctx *c, int n, int J)
     a.S2 = c->S2.as<int16_t>();
     a.H = g.H; a.width1 = g.width1; a.D = g.D; a.P1 = g.P1; a.P2 = g.P2; a.n = n; a.up = 0;
     size_t ho_bytes = (size_t)2 * (G > 1 ? G - 1 : 1) * 2 * HO_SLOTS * 32 * g.NP * sizeof(uint32_t);
-    cudaError_t e = c->agg_ho.ensure(ho_bytes + 256);
+    cudaError_t e = c->agg_ho.ensure(ho_bytes);
     if (e != cudaSuccess) return e;
-    // every int16 of the rings starts with phase 1 (steps 0..3 write phase 0); the word after the rings is the error flag
+    // every int16 of the rings starts with phase 1 (steps 0..3 write phase 0)
     if ((e = cudaMemsetAsync(c->agg_ho.p, 0xFF, ho_bytes, c->stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync((char *)c->agg_ho.p + ho_bytes, 0, 256, c->stream)) != cudaSuccess) return e;
     a.ho = c->agg_ho.as<uint32_t>();
-    a.err = (int *)((char *)c->agg_ho.p + ho_bytes);
-    c->agg_err = a.err;
+    a.err = c->agg_err; // (launch_aggregate)
     const bool pad = g.D != g.Dp;
     std::lock_guard<std::mutex> lock(g_chain.mu);
     const int dev = c->device & 63, nconc = sweep_concurrency();
@@ -936,10 +957,14 @@ cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
     a.raw = c->raw.as<int16_t>();
     a.disp2key = c->disp2key.as<unsigned>();
     a.W = g.W; a.minX1 = g.minX1; a.minD = g.minD; a.uniq = g.uniq;
+    // device error flag of this aggregation (a wait that timed out: lost strip hand-over or bulk copy), read by agg_poll_error
+    cudaError_t e;
+    if ((e = c->agg_errbuf.ensure(256)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(c->agg_errbuf.p, 0, 256, c->stream)) != cudaSuccess) return e;
+    a.err = c->agg_err = c->agg_errbuf.as<int>();
     const int thr = 100 - g.uniq;
     a.uniq_M = thr > 1 ? (unsigned)(((1ull << 32) + thr - 1) / thr) : 0u;
     const bool can_fuse = c->fuse_wta && thr >= 1 && thr <= 100; // (uniquenessRatio >= 100 goes through wta_kernel)
-    cudaError_t e;
     c->wta_fused = false;
     const int n = g.mode == 3 ? 0 : vsweep_cols(c);
     c->agg_legacy = n == 0; // the legacy path keeps the generic scan kernel for every direction (it is the cross-check)

@@ -171,7 +171,7 @@ static int make_geom(b2s_ctx *c, int H, int W, int cn)
     CK(c, c->planesR.ensure(npx * 2 * cn * 4));
     CK(c, c->C.ensure(vol));
     CK(c, c->S.ensure(vol));
-    if (g.mode == 1) CK(c, c->S2.ensure(vol));
+    CK(c, c->S2.ensure(vol)); // MODE_HH: the bottom-up sweep's partial sum; before that, the cost stage's row sums (agg_fuses_vsum)
     CK(c, c->raw.ensure(npx * 2));
     CK(c, c->disp16.ensure(npx * 2));
     CK(c, c->med.ensure(npx * 2));

@@ -55,6 +55,7 @@ struct b2s_ctx {
     bool keep_volumes = false; // b2s_set_option(B2S_OPT_KEEP_VOLUMES): a fused last pass also stores S
     bool fuse_wta = true;      // b2s_set_option(B2S_OPT_FUSE_WTA): on by default
     bool agg_legacy = false;   // launch_aggregate: per-direction scan kernels (strips too wide, or B2S_AGG_LEGACY)
+    bool hs_pending = false;   // launch_cost_volume stopped at the row sums (in S2): the first horizontal scan forms C (agg_fuses_vsum)
     bool wta_fused = false;    // set by launch_aggregate when the last scan already did the winner-take-all
 
     // matcher buffers
@@ -96,6 +97,7 @@ struct b2s_ctx {
 cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t *d_right);
 // sgbm_agg.cu
 cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks = nullptr);
+bool agg_fuses_vsum(const b2s_ctx *c);
 int agg_poll_error(b2s_ctx *c); // after a stream sync: 1 if a hand-over wait of the fused sweep timed out
 // sgbm_post.cu
 cudaError_t launch_wta_prepare(b2s_ctx *c); // before the aggregation: clears the WTA outputs

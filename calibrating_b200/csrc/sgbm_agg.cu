@@ -46,6 +46,8 @@ struct AggArgs {
     int16_t *raw;
     unsigned *disp2key;
     int W, minX1, minD, uniq;
+    const int16_t *hs; // agg_hscan_vsum_kernel: row sums of the per-pixel cost (H, width1, Dp), C = vertical box sum of them
+    int SH2;
     int *err;        // device error flag (sgbm_agg.cu: wait_expired), set if a bulk copy never completes
     unsigned uniq_M; // ceil(2^32 / (100 - uniq)): the fused WTA's division by the invariant (100 - uniq) (0 < 100 - uniq <= 100)
 };
@@ -487,6 +489,90 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_kernel(AggArgs a)
     }
 }
 
+// The first horizontal scan with the vertical half of the cost's box filter folded in (block sizes up to 5): the cost stage
+// leaves the horizontal window sums hs of every row (sgbm_cost.cu), and this kernel forms C(y) = sum_k hs(clamp(y+k)) for
+// its row on the fly (NV = 2*SH2+1 bulk copies per chunk, VIADD.16x2 like vsum_kernel), stores it for the later passes and
+// scans it.  That removes vsum_kernel's launch and the C read of this scan: 2 B/voxel less DRAM traffic per pair; the NV-fold
+// re-read of hs rows by neighbouring warps is served by L2.
+template <int NP> struct HvChunk { static constexpr int px = NP == 1 ? 12 : (NP == 2 ? 6 : (NP == 3 ? 4 : 3)); }; // 1.5 KB per hs row
+constexpr int HV_SLOTS = 3;
+template <int NP, bool PAD, int NV>
+__global__ void __launch_bounds__(WARPS * 32) agg_hscan_vsum_kernel(AggArgs a)
+{
+    constexpr int CH = 128 * NP;
+    constexpr int CPX = HvChunk<NP>::px;
+    constexpr int SRC_BYTES = CPX * CH;
+    constexpr int SLOT_BYTES = NV * SRC_BYTES;
+    constexpr int RING_BYTES = HV_SLOTS * SLOT_BYTES;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t mb0 = sm0 + WARPS * RING_BYTES;
+    if (threadIdx.x < WARPS * HV_SLOTS) mbar_init(mb0 + threadIdx.x * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int y = blockIdx.x * WARPS + wid;
+    if (y >= a.H) return;
+    const int Dp = 64 * NP, nsteps = a.width1;
+    const int nchunks = (nsteps + CPX - 1) / CPX;
+    const uint32_t ring = sm0 + wid * RING_BYTES, mbw = mb0 + wid * (HV_SLOTS * 8);
+    const long long rowE = (long long)a.width1 * Dp;
+    const int16_t *hrow[NV]; // the NV rows of the window, replicated at the image border (A.3)
+#pragma unroll
+    for (int v = 0; v < NV; v++) hrow[v] = a.hs + (long long)min(max(y + v - NV / 2, 0), a.H - 1) * rowE;
+    auto issue = [&](int j) {
+        if (lane == 0) {
+            const int k0 = j * CPX, npx = min(CPX, nsteps - k0);
+            const uint32_t slot = ring + (j % HV_SLOTS) * SLOT_BYTES, mb = mbw + (j % HV_SLOTS) * 8, bytes = (uint32_t)npx * CH;
+            mbar_arrive_expect_tx(mb, bytes * NV);
+#pragma unroll
+            for (int v = 0; v < NV; v++) bulk_g2s(slot + v * SRC_BYTES, hrow[v] + (long long)k0 * Dp, bytes, mb);
+        }
+    };
+    uint32_t padmask[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        int d0 = (lane * NP + i) * 2;
+        padmask[i] = PAD ? ((d0 >= a.D ? 0x00007FFFu : 0u) | (d0 + 1 >= a.D ? 0x7FFF0000u : 0u)) : 0u;
+    }
+    const uint32_t P1v = (uint32_t)a.P1 * 0x10001u, P2mP1v = (uint32_t)(a.P2 - a.P1) * 0x10001u;
+#pragma unroll 1
+    for (int j = 0; j < HV_SLOTS - 1 && j < nchunks; j++) issue(j);
+    uint32_t T[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) T[i] = padmask[i];
+    const long long o0 = (long long)y * rowE + lane * 2 * NP;
+    int16_t *sp = a.S + o0, *cp = const_cast<int16_t *>(a.C) + o0;
+#pragma unroll 1
+    for (int j = 0; j < nchunks; j++) {
+        __syncwarp(); // every lane is done with the slot of chunk j-1: it is refilled now
+        if (j + HV_SLOTS - 1 < nchunks) issue(j + HV_SLOTS - 1);
+        mbar_wait(mbw + (j % HV_SLOTS) * 8, (uint32_t)(j / HV_SLOTS) & 1u, a.err);
+        const int npx = min(CPX, nsteps - j * CPX);
+        uint32_t cur = ring + (j % HV_SLOTS) * SLOT_BYTES + lane * NP * 4;
+#pragma unroll 1
+        for (int s = 0; s < npx; s++) {
+            uint32_t c[NP], L[NP];
+            lds_s<NP>(cur, c);
+#pragma unroll
+            for (int v = 1; v < NV; v++) {
+                uint32_t h[NP];
+                lds_s<NP>(cur + v * SRC_BYTES, h);
+#pragma unroll
+                for (int i = 0; i < NP; i++) c[i] = __vadd2(c[i], h[i]);
+            }
+            stcg_regs<NP>(cp, c);
+            sgm_step<NP, PAD>(T, c, L, padmask, P1v, P2mP1v, lane);
+            stcg_regs<NP>(sp, L);
+            sp += Dp;
+            cp += Dp;
+            cur += CH;
+        }
+    }
+}
+
 template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *c, const AggArgs &a)
 {
     constexpr int STAGE_BYTES = 128 * NP * (MODE == AGG_ACCUM2 ? 3 : (MODE == AGG_ACCUM ? 2 : 1));
@@ -530,6 +616,41 @@ cudaError_t launch_dir_np(b2s_ctx *c, const AggArgs &a, int mode, int wta = 0)
     case 2: return pad ? launch_dir<2, true>(c, a, mode, wta) : launch_dir<2, false>(c, a, mode, wta);
     case 3: return pad ? launch_dir<3, true>(c, a, mode, wta) : launch_dir<3, false>(c, a, mode, wta);
     case 4: return pad ? launch_dir<4, true>(c, a, mode, wta) : launch_dir<4, false>(c, a, mode, wta);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int NP, bool PAD, int NV> cudaError_t launch_hscan_vsum_t(b2s_ctx *c, const AggArgs &a)
+{
+    const size_t smem = (size_t)WARPS * HV_SLOTS * NV * HvChunk<NP>::px * 128 * NP + WARPS * HV_SLOTS * 8;
+    static bool configured = false; // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(agg_hscan_vsum_kernel<NP, PAD, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    agg_hscan_vsum_kernel<NP, PAD, NV><<<(a.H + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
+    c->launches++;
+    return cudaGetLastError();
+}
+template <int NP, bool PAD> cudaError_t launch_hscan_vsum_p(b2s_ctx *c, const AggArgs &a)
+{
+    switch (a.SH2) {
+    case 0: return launch_hscan_vsum_t<NP, PAD, 1>(c, a);
+    case 1: return launch_hscan_vsum_t<NP, PAD, 3>(c, a);
+    case 2: return launch_hscan_vsum_t<NP, PAD, 5>(c, a);
+    default: return cudaErrorInvalidValue;
+    }
+}
+// the +x scan reading the cost stage's row sums (agg_fuses_vsum)
+cudaError_t launch_hscan_vsum(b2s_ctx *c, const AggArgs &a)
+{
+    const bool pad = c->g.D != c->g.Dp;
+    switch (c->g.NP) {
+    case 1: return pad ? launch_hscan_vsum_p<1, true>(c, a) : launch_hscan_vsum_p<1, false>(c, a);
+    case 2: return pad ? launch_hscan_vsum_p<2, true>(c, a) : launch_hscan_vsum_p<2, false>(c, a);
+    case 3: return pad ? launch_hscan_vsum_p<3, true>(c, a) : launch_hscan_vsum_p<3, false>(c, a);
+    case 4: return pad ? launch_hscan_vsum_p<4, true>(c, a) : launch_hscan_vsum_p<4, false>(c, a);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -928,6 +1049,14 @@ cudaError_t launch_vsweep(b2s_ctx *c, int n, int J)
 
 } // namespace
 
+// True when the cost stage may stop at the row sums (in S2) and leave the vertical box sum to the first horizontal scan:
+// BT cost, window height <= 5, the production schedule (not MODE_HH4, whose bottom rows get a constant cost, nor the legacy path).
+bool agg_fuses_vsum(const b2s_ctx *c)
+{
+    if (getenv("B2S_NO_VSUM_FUSION")) return false;
+    return c->prm.cost == 0 && c->g.SH2 <= 2 && c->g.mode != 3 && vsweep_cols(c) > 0;
+}
+
 int agg_poll_error(b2s_ctx *c)
 {
     if (!c->agg_err) return 0;
@@ -970,7 +1099,14 @@ cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
     c->agg_legacy = n == 0; // the legacy path keeps the generic scan kernel for every direction (it is the cross-check)
     if (n > 0) {
         a.mx = 1; a.my = 0;
-        if ((e = launch_dir_np(c, a, AGG_INIT)) != cudaSuccess) return e;
+        if (c->hs_pending) { // the cost stage left row sums in S2: this scan also forms C (consumed once: S2 is the up-sweep's output)
+            a.hs = c->S2.as<int16_t>();
+            a.SH2 = g.SH2;
+            e = launch_hscan_vsum(c, a);
+            c->hs_pending = false;
+        } else
+            e = launch_dir_np(c, a, AGG_INIT);
+        if (e != cudaSuccess) return e;
         mark();
         if ((e = launch_vsweep(c, n, g.mode == 1 ? 2 : 1)) != cudaSuccess) return e;
         mark();

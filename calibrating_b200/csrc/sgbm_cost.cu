@@ -229,6 +229,7 @@ __global__ void vsum_kernel(const uint4 *__restrict__ hs, uint4 *__restrict__ C,
 cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t *d_right)
 {
     const SgbmGeom &g = c->g;
+    c->hs_pending = false;
     if (c->prm.cost == 1) { // census: descriptors live in the (8 bytes per gray pixel) plane buffers
         dim3 b(128), gd((g.W + 127) / 128, g.H);
         unsigned long long *DL = c->planesL.as<unsigned long long>(), *DR = c->planesR.as<unsigned long long>();
@@ -254,7 +255,11 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
     const int nrp = need <= 104 ? 104 : NRP_MAX;
     size_t smem = (size_t)NPL * TXH * sizeof(uint4) + (size_t)NPL * 2 * nrp * sizeof(uint4) + (size_t)TXH * g.Dp * sizeof(int16_t);
     dim3 cg((g.width1 + TX - 1) / TX, g.H);
-    int16_t *hs = c->S.as<int16_t>(); // S is free until aggregation starts
+    // row sums: into S (free until aggregation starts), or into S2 when the first horizontal scan takes over the vertical half of
+    // the box filter (sgbm_agg.cu: agg_hscan_vsum_kernel; S is that scan's output, S2 is not written before the vertical sweep)
+    const bool fuse_vsum = agg_fuses_vsum(c);
+    int16_t *hs = fuse_vsum ? c->S2.as<int16_t>() : c->S.as<int16_t>();
+    c->hs_pending = fuse_vsum;
     auto launch = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -265,10 +270,12 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
     if (g.cn == 3) e = nrp == 104 ? launch(pixcost_hsum_kernel<3, 104>) : launch(pixcost_hsum_kernel<3, NRP_MAX>);
     else e = nrp == 104 ? launch(pixcost_hsum_kernel<1, 104>) : launch(pixcost_hsum_kernel<1, NRP_MAX>);
     if (e != cudaSuccess) return e;
+    c->launches += 3;
+    if (fuse_vsum) return cudaGetLastError();
     size_t row_vec = (size_t)g.width1 * g.Dp / 8;
     dim3 vg((unsigned)((row_vec + 255) / 256), (g.H + VBAND - 1) / VBAND);
     vsum_kernel<<<vg, 256, 0, c->stream>>>((const uint4 *)hs, c->C.as<uint4>(), g.H, row_vec, g.SH2);
-    c->launches += 4;
+    c->launches++;
     if (g.mode == 3 && g.SH2 > 0 && g.H > 1) {
         // MODE_HH4 of cv2 leaves the cost of the rows whose window reaches below the image (y > 0, y + SH2 >= H) constant:
         // its column-parallel loop skips their update (found by differential testing; oracle/sgbm_ref.c, vertical half of A.3)

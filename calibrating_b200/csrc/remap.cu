@@ -66,6 +66,20 @@ namespace {
 __device__ __forceinline__ int sat_short(int v) { return min(max(v, -32768), 32767); }
 __device__ __forceinline__ unsigned char fix_cast(int sum) { return (unsigned char)min(max((sum + (1 << 14)) >> 15, 0), 255); }
 
+// two taps per instruction: d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1 (IDP.2A.LO.S16.U8) / bytes 2, 3 (HI)
+__device__ __forceinline__ int dp2a_lo(int a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi(int a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // thread = one destination pixel (all channels).  xshift: destination column x samples the map at x - xshift
 // (Stereo.rectify's translation of rectify_img2, stereo_camera.py:230-240); vacated columns are 0.
 template <int CN, int INTERP>
@@ -98,20 +112,58 @@ __global__ void remap_u8_kernel(const uint8_t *__restrict__ src, int sH, int sW,
         }
         const uint4 *w4 = (const uint4 *)(tab + (size_t)(fy * 32 + fx) * 64);
         const bool inside = x0 >= 0 && x0 + 8 <= sW && y0 >= 0 && y0 + 8 <= sH;
+        if (inside) {
+            // whole 8x8 window inside the image (all but a border of 4 pixels): a row of the window is 8*CN contiguous bytes at an
+            // arbitrary byte address (sW * CN is not a multiple of 4 in general, so the alignment changes from row to row).
+            // Read it as aligned 32-bit words, realign with funnel shifts, and take two taps per IDP.2A: the packed int16 weight
+            // pairs as they lie in the table times two u8 samples gathered by one PRMT.
+            constexpr int NW = 2 * CN; // 32-bit words of one window row
+            const size_t a0 = ((size_t)y0 * sW + x0) * CN, rstep = (size_t)sW * CN;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const uint4 wq = w4[r];
+                const int wpair[4] = {(int)wq.x, (int)wq.y, (int)wq.z, (int)wq.w}; // taps (0,1) (2,3) (4,5) (6,7)
+                const size_t a = a0 + r * rstep;
+                const uint32_t *wp = (const uint32_t *)(src + (a & ~(size_t)3));
+                const unsigned s = (unsigned)(a & 3) * 8;
+                uint32_t W[NW + 1], B[NW];
+#pragma unroll
+                for (int i = 0; i < NW; i++) W[i] = __ldg(wp + i);
+                W[NW] = s ? __ldg(wp + NW) : 0u; // (an aligned row ends with its last word: nothing is read past the window)
+#pragma unroll
+                for (int i = 0; i < NW; i++) B[i] = __funnelshift_r(W[i], W[i + 1], s);
+                if (CN == 1) {
+                    acc[0] = dp2a_lo(wpair[0], B[0], acc[0]);
+                    acc[0] = dp2a_hi(wpair[1], B[0], acc[0]);
+                    acc[0] = dp2a_lo(wpair[2], B[1], acc[0]);
+                    acc[0] = dp2a_hi(wpair[3], B[1], acc[0]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+#pragma unroll
+                        for (int c = 0; c < CN; c++) {
+                            const int ja = 2 * q * CN + c, jb = ja + CN; // bytes of taps 2q and 2q+1 of channel c in the window row
+                            const uint32_t pr = __byte_perm(B[ja >> 2], B[jb >> 2], (ja & 3) | (((jb & 3) + 4) << 4));
+                            acc[c] = dp2a_lo(wpair[q], pr, acc[c]);
+                        }
+                }
+            }
+        } else {
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             uint4 wq = w4[r];
             int w[8] = {(short)(wq.x & 0xffff), ((int)wq.x) >> 16, (short)(wq.y & 0xffff), ((int)wq.y) >> 16,
                         (short)(wq.z & 0xffff), ((int)wq.z) >> 16, (short)(wq.w & 0xffff), ((int)wq.w) >> 16};
             int yy = y0 + r;
-            if (!inside && (yy < 0 || yy >= sH)) continue;
+            if (yy < 0 || yy >= sH) continue;
             const uint8_t *row = src + ((size_t)yy * sW + x0) * CN;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                if (!inside && (x0 + k < 0 || x0 + k >= sW)) continue;
+                if (x0 + k < 0 || x0 + k >= sW) continue;
 #pragma unroll
                 for (int c = 0; c < CN; c++) acc[c] += (int)row[k * CN + c] * w[k];
             }
+        }
         }
     } else {
         if (ix >= sW || ix + 2 <= 0 || iy >= sH || iy + 2 <= 0) {

@@ -6,13 +6,18 @@ import calibrating_b200 as cb
 from calibrating_b200 import synth
 from oracle import sgbm as osgbm
 
-for (h, w, D, cn, mode, bs) in [(24, 150, 64, 3, 1, 5), (17, 300, 218, 3, 0, 11), (30, 120, 16, 1, 1, 3), (20, 400, 256, 1, 0, 7), (21, 330, 130, 3, 1, 9)]:
+for (h, w, D, cn, mode, bs) in [(24, 150, 64, 3, 1, 5), (17, 300, 218, 3, 0, 11), (30, 120, 16, 1, 1, 3), (20, 400, 256, 1, 0, 7), (21, 330, 130, 3, 1, 9), (19, 170, 48, 3, 3, 5), (9, 140, 100, 1, 1, 1)]:
     l, r, _ = synth.rectified_pair(h, w, D, 1, cn)
     p = dict(min_disparity=2, num_disparities=D, block_size=bs, P1=8 * cn * bs * bs, P2=32 * cn * bs * bs, disp12_max_diff=1,
              uniqueness_ratio=5, speckle_window_size=30, speckle_range=2, mode=mode)
     m = cb.StereoSGBM(**p)
+    m.handle.keep_volumes(True)  # (the default configuration does not store S; it is exercised below)
     got = m.compute(l, r)
     ref = osgbm.sgbm_compute(l, r, want_volumes=True, **p)
+    m.handle.keep_volumes(False)
+    assert np.array_equal(m.compute(l, r), ref["disp"])
+    m.handle.fuse_wta(False)
+    assert np.array_equal(m.compute(l, r), ref["disp"])
     print((h, w, D, cn, mode, bs), "C", np.array_equal(m.handle.fetch_volume(0), ref["C"]), "S", np.array_equal(m.handle.fetch_volume(1), ref["S"]),
           "raw", np.array_equal(m.handle.fetch_raw(h, w), ref["raw"]), "disp", np.array_equal(got, ref["disp"]))
 rig = synth.rig_dict((320, 240))
@@ -26,8 +31,8 @@ p = dict(min_disparity=0, num_disparities=64, block_size=5, P1=10, P2=120, disp1
          speckle_range=2, mode=1, cost=cb.COST_CENSUS)
 m = cb.StereoSGBM(**p)
 print("census", np.array_equal(m.compute(l, r), osgbm.sgbm_compute(l, r, **p)))
-m.handle.fuse_wta(True)
-print("census fused wta", np.array_equal(m.compute(l, r), osgbm.sgbm_compute(l, r, **p)))
+m.handle.fuse_wta(False)
+print("census separate wta", np.array_equal(m.compute(l, r), osgbm.sgbm_compute(l, r, **p)))
 st2 = cb.Stereo.load(rig, maps="device").set_stereo_matching(cb.SemiGlobalBlockMatching({"max_size": 4000, "num_disparities": 64}), max_depth=3.5)
 res2 = st2.get_depth(img1, img2, return_distort_depth=True)
 print("device maps chain equal", all(np.array_equal(res[k], res2[k]) for k in res), res2["distort_depth"].shape)

@@ -4,17 +4,21 @@
 //   L_r(p,d) = C(p,d) + min(L_r(p-r,d), L_r(p-r,d-1)+P1, L_r(p-r,d+1)+P1, minL_r(p-r)+P2) - minL_r(p-r)
 // The saturating sum over directions is order-independent for non-negative L, so the eight (MODE_HH) or five (MODE_SGBM)
 // directions are grouped by what they need rather than by OpenCV's two sweeps:
-//   agg_hscan_kernel<INIT>      the horizontal path (+1,0): 1080 independent image rows, S = L
+//   agg_hscan_vsum_kernel       the horizontal path (+1,0): 1080 independent image rows, S = L; forms C on the way from the cost
+//                               stage's row sums (the vertical half of the box filter; block sizes <= 5), or
+//   agg_hscan_kernel<INIT>      the same path on a finished C
 //   agg_vsweep_kernel           every path that crosses rows, in ONE launch: the three top-down paths add to S, the three
 //                               bottom-up paths (MODE_HH) go to S2; lock-step strips of columns, see the kernel's comment
-//   agg_hscan_kernel<ACCUM[2]>  the horizontal path (-1,0) last: S = sat(S [+ S2] + L) (optionally with the winner-take-all fused)
+//   agg_hscan_kernel<ACCUM[2]>  the horizontal path (-1,0) last: S = sat(S [+ S2] + L), with the winner-take-all fused (default:
+//                               S is then never written) or followed by wta_kernel (sgbm_post.cu)
 //   agg_scan_kernel             generic one-direction-per-launch scan (any direction; diagonal lines wrap around the image
-//                               edge with a state reset): the legacy schedule for strips wider than 32 columns and the
-//                               cross-check of the tests (B2S_AGG_LEGACY=1)
+//                               edge with a state reset): the two vertical paths of MODE_HH4, the legacy schedule for strips
+//                               wider than 32 columns, and the cross-check of the tests (B2S_AGG_LEGACY=1)
 // Common to all: one warp = one line (or column), a lane owns 2*NP consecutive disparities as NP packed int16x2 registers;
 // state kept normalised (L - minL), so a step (sgm_step) is VIMNMX3.S16x2 / VIADDMNMX.S16x2 / VIADD.16x2 (DPX) per register,
 // two SHFLs for the d-1 / d+1 neighbours across lanes and one CREDUX.MIN for minL; the C (and S) chunk of a pixel is 128*NP
-// contiguous bytes, streamed through a private cp.async (LDGSTS) ring per warp.
+// contiguous bytes.  The horizontal scans fetch several pixels per bulk copy (UBLKCP + mbarrier), the kernels that move across
+// rows stream single pixels through a private cp.async (LDGSTS) ring per warp.
 #include <stdlib.h>
 
 #include <mutex>
@@ -117,8 +121,14 @@ __device__ __forceinline__ void sgm_step(uint32_t (&T)[NP], const uint32_t (&c)[
     const uint32_t BIG = 0x7FFF7FFFu;
     uint32_t up = __shfl_up_sync(0xffffffffu, T[NP - 1], 1);
     uint32_t dn = __shfl_down_sync(0xffffffffu, T[0], 1);
-    if (lane == 0) up = BIG;
-    if (lane == 31) dn = BIG;
+    // the d = -1 / d = D sentinels of the edge lanes as a multiply-add (FMA pipe) instead of a select: the kernels that
+    // use this step are bound by the ALU pipe, which the packed min / max cannot leave
+    // (the factors go through an empty asm so that the compiler does not turn the multiply-add back into a select)
+    uint32_t ku = lane != 0 ? 1u : 0u, kd = lane != 31 ? 1u : 0u;
+    asm("" : "+r"(ku));
+    asm("" : "+r"(kd));
+    up = up * ku + (lane == 0 ? BIG : 0u);
+    dn = dn * kd + (lane == 31 ? BIG : 0u);
     uint32_t m = BIG;
 #pragma unroll
     for (int i = 0; i < NP; i++) {

@@ -587,7 +587,8 @@ template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *
 {
     constexpr int STAGE_BYTES = 128 * NP * (MODE == AGG_ACCUM2 ? 3 : (MODE == AGG_ACCUM ? 2 : 1));
     size_t smem = (size_t)WARPS * Stages<NP>::value * STAGE_BYTES;
-    static bool configured = false; // per instantiation
+    static bool configured_dev[64] = {}; // per instantiation and device (the attribute belongs to the device's context)
+    bool &configured = configured_dev[c->device & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(agg_scan_kernel<NP, PAD, MODE, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -597,7 +598,8 @@ template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *
     // horizontal scans: bulk-copy rings + the fused WTA's exchange buffers + one mbarrier per ring slot
     const size_t smem_h = (size_t)WARPS * HS_SLOTS * (STAGE_BYTES * HsChunk<NP>::px) + (WTA != 0 ? (size_t)WARPS * 2 * 128 * NP : 0) + WARPS * HS_SLOTS * 8;
     if (a.my == 0 && !c->agg_legacy) {
-        static bool configured_h = false;
+        static bool configured_h_dev[64] = {};
+        bool &configured_h = configured_h_dev[c->device & 63];
         if (!configured_h) {
             cudaError_t e = cudaFuncSetAttribute(agg_hscan_kernel<NP, PAD, MODE, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h);
             if (e != cudaSuccess) return e;
@@ -633,7 +635,8 @@ cudaError_t launch_dir_np(b2s_ctx *c, const AggArgs &a, int mode, int wta = 0)
 template <int NP, bool PAD, int NV> cudaError_t launch_hscan_vsum_t(b2s_ctx *c, const AggArgs &a)
 {
     const size_t smem = (size_t)WARPS * HV_SLOTS * NV * HvChunk<NP>::px * 128 * NP + WARPS * HV_SLOTS * 8;
-    static bool configured = false; // per instantiation
+    static bool configured_dev[64] = {}; // per instantiation and device (the attribute belongs to the device's context)
+    bool &configured = configured_dev[c->device & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(agg_hscan_vsum_kernel<NP, PAD, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -959,7 +962,8 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
 
 template <int NP, bool PAD, int JW, int R> cudaError_t launch_vsweep_t(b2s_ctx *c, const VsArgs &a, int G, size_t smem)
 {
-    static bool configured = false; // per instantiation
+    static bool configured_dev[64] = {}; // per instantiation and device (the attribute belongs to the device's context)
+    bool &configured = configured_dev[c->device & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(agg_vsweep_kernel<NP, PAD, JW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;

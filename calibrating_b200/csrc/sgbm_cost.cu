@@ -143,7 +143,29 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
 
     // phase 2: thread -> (segment of 16 columns, packed d pair); sliding window with wrap arithmetic
     const uint32_t *pw = pixw;
-    const int SEG = 16;
+    constexpr int SEG = 16;
+    if (xlo >= 0 && x1_0 + TX - 1 + g.SW2 <= g.width1 - 1) {
+        // every window of the tile lies inside the cost volume (all tiles but the first and the last of a row): no clamping,
+        // the added / dropped columns are two pointers that advance with the output
+        const int WIN = 2 * g.SW2 + 1;
+        for (int i = threadIdx.x; i < (TX / SEG) * DW; i += COST_THREADS) {
+            const int seg = i / DW, w = i % DW;
+            const uint32_t *psub = pw + (seg * SEG) * DW + w; // column xs - SW2 of the tile
+            uint32_t s = 0;
+            for (int k = 0; k < WIN; k++) s = __vadd2(s, psub[k * DW]);
+            const uint32_t *padd = psub + WIN * DW;
+            uint32_t *out = (uint32_t *)(hs + ((size_t)y * g.width1 + x1_0 + seg * SEG) * Dp) + w;
+#pragma unroll
+            for (int t = 0; t < SEG; t++) {
+                *out = s;
+                out += DW;
+                if (t + 1 < SEG) s = __vsub2(__vadd2(s, *padd), *psub);
+                padd += DW;
+                psub += DW;
+            }
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < (TX / SEG) * DW; i += COST_THREADS) {
         int seg = i / DW, w = i % DW;
         int xs = x1_0 + seg * SEG;

@@ -117,57 +117,3 @@ cudaError_t launch_gen_maps(b2s_ctx *c, const b2s_map_params &p, float *mapx, fl
                             uint16_t *fxy16);
 cudaError_t launch_depth_bare(b2s_ctx *c, const float *d_disp, double *d_depth);
 cudaError_t launch_unrectify(b2s_ctx *c, const double *d_depth, double *d_out);
-
-#ifdef __CUDACC__
-// SURVEY.md Appendix A.5 for one pixel whose final S values sit in the lanes of a warp (lane = 2*NP consecutive
-// disparities, packed int16x2): argmin, uniqueness vote, sub-pixel interpolation, right-view candidate.  cv2 visits x1 in
-// descending order and keeps, per right-image column x2, the candidate with the smallest minS (strict '>': among equal
-// costs the largest x1 wins); that order-dependent rule is an atomicMin on the key (minS << 16) | (0xFFFF - x1).
-// xch: NP*32 words of shared memory private to the warp (exchange of S[d-1], S[d+1] for the interpolation).
-template <int NP>
-__device__ __forceinline__ void wta_pixel(const uint32_t (&v)[NP], uint32_t *xch, int lane, int x, int y, int D, int W, int minX1, int minD,
-                                          int uniq, int16_t *__restrict__ raw, unsigned *__restrict__ disp2key)
-{
-    int sv[2 * NP];
-    unsigned key = 0xFFFFFFFFu;
-#pragma unroll
-    for (int i = 0; i < NP; i++) {
-        sv[2 * i] = (int)(short)(v[i] & 0xffffu);
-        sv[2 * i + 1] = ((int)v[i]) >> 16;
-    }
-#pragma unroll
-    for (int j = 0; j < 2 * NP; j++) {
-        int d = lane * 2 * NP + j;
-        if (d < D) key = min(key, ((unsigned)(sv[j] & 0xffff) << 16) | (unsigned)d);
-    }
-    key = __reduce_min_sync(0xffffffffu, key);
-    const int minS = (int)(key >> 16);
-    int best = (int)(key & 0xffffu);
-    if (minS >= 32767) best = -1; // cv2: strict '<' against MAX_COST never fires
-    bool bad = false;
-#pragma unroll
-    for (int j = 0; j < 2 * NP; j++) {
-        int d = lane * 2 * NP + j;
-        if (d < D && sv[j] * (100 - uniq) < minS * 100 && abs(best - d) > 1) bad = true;
-    }
-    if (__any_sync(0xffffffffu, bad)) return;
-#pragma unroll
-    for (int i = 0; i < NP; i++) xch[lane * NP + i] = v[i];
-    __syncwarp();
-    if (lane == 0) {
-        int d = best;
-        int x2 = x + minX1 - d - minD;
-        if (minS < 32767 && x2 >= 0 && x2 < W + 2)
-            atomicMin(&disp2key[(size_t)y * (W + 2) + x2], ((unsigned)minS << 16) | (unsigned)(0xFFFF - x));
-        if (0 < d && d < D - 1) {
-            const int16_t *Sp = (const int16_t *)xch;
-            int sm = Sp[d - 1], sp = Sp[d + 1], s0 = Sp[d];
-            int den2 = max(sm + sp - 2 * s0, 1);
-            d = d * 16 + ((sm - sp) * 16 + den2) / (den2 * 2);
-        } else
-            d *= 16;
-        raw[(size_t)y * W + x + minX1] = (int16_t)(d + minD * 16);
-    }
-    __syncwarp();
-}
-#endif

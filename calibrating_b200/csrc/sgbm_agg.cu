@@ -46,7 +46,7 @@ struct AggArgs {
     int H, width1, D;
     int mx, my;
     int P1, P2;
-    // fused winner-take-all of the last scan (WTA != 0): see wta_pixel in b2s_internal.h
+    // fused winner-take-all of the last scan (agg_hscan_kernel, WTA != 0)
     int16_t *raw;
     unsigned *disp2key;
     int W, minX1, minD, uniq;
@@ -203,8 +203,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t addr, uint32_t by
     asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(addr), "r"(bytes) : "memory");
 }
 
-// WTA: 0 = store S; 1 = winner-take-all fused (A.5), S not stored; 2 = both (debug: S stays fetchable)
-template <int NP, bool PAD, int MODE, int WTA>
+template <int NP, bool PAD, int MODE>
 __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
 {
     constexpr int CH = 128 * NP;                       // bytes of one pixel's d-chunk
@@ -315,12 +314,7 @@ __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
             Ln[i] = __vadd2(L[i], negmin) | padmask[i];
             out[i] = (MODE != AGG_INIT) ? __viaddmin_u16x2(sv[i], L[i], BIG) : L[i]; // saturating accumulate (L >= 0)
         }
-        if (WTA != 1) store_regs<NP>(a.S + ((size_t)y * a.width1 + x) * Dp + lane * 2 * NP, out);
-        if (WTA != 0) {
-            // this step's stage has been consumed: it doubles as the exchange buffer for the sub-pixel neighbours
-            uint32_t *xch = (uint32_t *)(ring + (k % STAGES) * STAGE_BYTES);
-            wta_pixel<NP>(out, xch, lane, x, y, a.D, a.W, a.minX1, a.minD, a.uniq, a.raw, a.disp2key);
-        }
+        store_regs<NP>(a.S + ((size_t)y * a.width1 + x) * Dp + lane * 2 * NP, out);
         advance(x, y);
     }
 }
@@ -330,6 +324,7 @@ __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
 // SM holds only 8 such warps, so the kernel's duration is (instructions per step) x (~4 cycles): the C / S / S2 chunks of
 // HS_CPX consecutive pixels are contiguous in memory and arrive by ONE bulk copy per source (cp.async.bulk -> UBLKCP, issued
 // by lane 0, completion counted on an mbarrier per ring slot), which leaves a step with its LDS, the arithmetic and a store.
+// WTA: 0 = store S; 1 = winner-take-all fused (A.5), S not stored; 2 = both (B2S_OPT_KEEP_VOLUMES: S stays fetchable)
 template <int NP> struct HsChunk { static constexpr int px = NP == 1 ? 16 : (NP == 2 ? 8 : 4); }; // pixels per bulk copy (<= 2 KB per source)
 constexpr int HS_SLOTS = 4;                                                                       // ring slots (chunks) per warp
 template <int NP, bool PAD, int MODE, int WTA>
@@ -586,19 +581,11 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_vsum_kernel(AggArgs a)
 template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *c, const AggArgs &a)
 {
     constexpr int STAGE_BYTES = 128 * NP * (MODE == AGG_ACCUM2 ? 3 : (MODE == AGG_ACCUM ? 2 : 1));
-    size_t smem = (size_t)WARPS * Stages<NP>::value * STAGE_BYTES;
-    static bool configured_dev[64] = {}; // per instantiation and device (the attribute belongs to the device's context)
-    bool &configured = configured_dev[c->device & 63];
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(agg_scan_kernel<NP, PAD, MODE, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    int nlines = a.my == 0 ? a.H : a.width1;
-    // horizontal scans: bulk-copy rings + the fused WTA's exchange buffers + one mbarrier per ring slot
-    const size_t smem_h = (size_t)WARPS * HS_SLOTS * (STAGE_BYTES * HsChunk<NP>::px) + (WTA != 0 ? (size_t)WARPS * 2 * 128 * NP : 0) + WARPS * HS_SLOTS * 8;
+    const int nlines = a.my == 0 ? a.H : a.width1;
     if (a.my == 0 && !c->agg_legacy) {
-        static bool configured_h_dev[64] = {};
+        // horizontal scans: bulk-copy rings + the fused WTA's exchange buffers + one mbarrier per ring slot
+        const size_t smem_h = (size_t)WARPS * HS_SLOTS * (STAGE_BYTES * HsChunk<NP>::px) + (WTA != 0 ? (size_t)WARPS * 2 * 128 * NP : 0) + WARPS * HS_SLOTS * 8;
+        static bool configured_h_dev[64] = {}; // per instantiation and device (the attribute belongs to the device's context)
         bool &configured_h = configured_h_dev[c->device & 63];
         if (!configured_h) {
             cudaError_t e = cudaFuncSetAttribute(agg_hscan_kernel<NP, PAD, MODE, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h);
@@ -606,8 +593,19 @@ template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *
             configured_h = true;
         }
         agg_hscan_kernel<NP, PAD, MODE, WTA><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem_h, c->stream>>>(a);
-    } else
-        agg_scan_kernel<NP, PAD, MODE, WTA><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
+    } else if constexpr (WTA != 0) {
+        return cudaErrorInvalidValue; // the generic scan has no fused winner-take-all (launch_aggregate never asks for one)
+    } else {
+        const size_t smem = (size_t)WARPS * Stages<NP>::value * STAGE_BYTES;
+        static bool configured_dev[64] = {};
+        bool &configured = configured_dev[c->device & 63];
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(agg_scan_kernel<NP, PAD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        agg_scan_kernel<NP, PAD, MODE><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
+    }
     c->launches++;
     return cudaGetLastError();
 }
@@ -1125,10 +1123,8 @@ cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
         if ((e = launch_vsweep(c, n, g.mode == 1 ? 2 : 1)) != cudaSuccess) return e;
         mark();
         a.mx = -1;
-        // B2S_OPT_FUSE_WTA: the last scan also does the winner-take-all (its lanes hold the final S of the pixel) and
-        // stores S only if the volumes are kept.  Off by default: the scan is a latency-bound sequential loop (7 warps
-        // per SM), and the ~60 extra dependent instructions per step cost more than the separate WTA kernel and the
-        // S round trip save (measured 0.86 ms vs 0.37 + 0.41 ms at 1080p/128).
+        // the last scan also does the winner-take-all (its lanes hold the final S of the pixel) and stores S only if the
+        // volumes are kept; B2S_OPT_FUSE_WTA = 0 or uniquenessRatio >= 100 leave it to wta_kernel (sgbm_post.cu)
         const int wta = can_fuse ? (c->keep_volumes ? 2 : 1) : 0;
         if ((e = launch_dir_np(c, a, g.mode == 1 ? AGG_ACCUM2 : AGG_ACCUM, wta)) != cudaSuccess) return e;
         c->wta_fused = wta != 0;

@@ -70,6 +70,22 @@ def test_sgbm_oracle_large_penalties(P1, P2):
         assert np.array_equal(ref, got["disp"]), mode
 
 
+@pytest.mark.parametrize("h", [1, 2, 3, 4, 6])
+@pytest.mark.parametrize("bs", [3, 5, 11])
+def test_sgbm_oracle_hh4_few_rows(h, bs):
+    """MODE_HH4 on images shorter than the block: cv2 keeps a constant cost for every row y > 0 with y + bs/2 >= H
+    (oracle/sgbm_ref.c, vertical half of A.3), i.e. for all rows but the first one here."""
+    rng = np.random.default_rng(10 * h + bs)
+    r = cv2.GaussianBlur(rng.integers(0, 255, (h, 60), dtype=np.uint8), (5, 1), 0)
+    l = (np.roll(r, 6, axis=1).astype(int) + rng.integers(0, 9, (h, 60))).clip(0, 255).astype(np.uint8)
+    ref = cv2.StereoSGBM_create(0, 16, bs, 20, 80, -1, 0, 0, 0, 0, 3).compute(l, r)
+    got = osgbm.sgbm_compute(l, r, num_disparities=16, block_size=bs, P1=20, P2=80, disp12_max_diff=-1, uniqueness_ratio=0, mode=3,
+                             want_volumes=True)
+    assert np.array_equal(ref, got["disp"])
+    if h > 1:
+        assert not got["C"][max(1, h - bs // 2):].any()
+
+
 def test_sgbm_oracle_precondition():
     l = np.zeros((20, 30), np.uint8)
     with pytest.raises(ValueError):

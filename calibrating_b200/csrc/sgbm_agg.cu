@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
 // Horizontal lines only (my == 0), the two scans of the production schedule: same arithmetic as agg_scan_kernel, but the
 // per-step overhead is cut to the bone.  A scan line is ONE warp's in-order instruction stream of 1792 dependent steps and an
 // SM holds only 8 such warps, so the kernel's duration is (instructions per step) x (~4 cycles): the C / S / S2 chunks of
-// HS_CPX consecutive pixels are contiguous in memory and arrive by ONE bulk copy per source (cp.async.bulk -> UBLKCP, issued
+// HsChunk<NP>::px consecutive pixels are contiguous in memory and arrive by ONE bulk copy per source (cp.async.bulk -> UBLKCP, issued
 // by lane 0, completion counted on an mbarrier per ring slot), which leaves a step with its LDS, the arithmetic and a store.
 // WTA: 0 = store S; 1 = winner-take-all fused (A.5), S not stored; 2 = both (B2S_OPT_KEEP_VOLUMES: S stays fetchable)
 template <int NP> struct HsChunk { static constexpr int px = NP == 1 ? 16 : (NP == 2 ? 8 : 4); }; // pixels per bulk copy (<= 2 KB per source)

@@ -77,6 +77,10 @@ def test_foreign_plugin_and_stage_methods(golden):
     assert np.array_equal(st.undistort_img(g["img1"]), ref.undistort_img(g["img1"]))
     gray = g["img1"][..., 0].copy()
     assert np.array_equal(st.undistort_img(gray), ref.undistort_img(gray))
+    gray2 = g["img2"][..., 1].copy()  # single-channel LANCZOS4 rectification (its own tap-pair path in remap_u8_kernel)
+    r1, r2 = st.rectify(gray, gray2)
+    e1, e2 = ref.rectify(gray, gray2)
+    assert r1.shape == e1.shape and np.array_equal(r1, e1) and np.array_equal(r2, e2)
 
 
 @pytest.mark.parametrize("interp", ["lanczos4", "linear"])

@@ -85,6 +85,7 @@ SIGNATURES = {
     "b2s_launch_count": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_longlong)]),
     "b2s_bench_aggregate": (c_int, [c_void_p, c_int, ctypes.POINTER(c_float)]),
     "b2s_bench_aggregate_parts": (c_int, [c_void_p, c_int, ctypes.POINTER(c_float), c_int, ctypes.POINTER(c_int)]),
+    "b2s_enqueue_aggregate": (c_int, [c_void_p, c_int]),
     "b2s_event_record": (c_int, [c_void_p, c_int]),
     "b2s_event_elapsed": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.POINTER(c_float)]),
     "b2s_collect_timings": (c_int, [c_void_p, c_int]),
@@ -165,6 +166,10 @@ class Handle:
         """Winner-take-all inside the last aggregation pass (default) or as a separate kernel (same results; see include/b2s.h)."""
         self.call("b2s_set_option", 2, int(bool(on)))
 
+    def agg_schedule(self, wave=False):
+        """B2S_OPT_AGG_SCHEDULE: False = scans + lock-step sweep (default), True = wavefront sweeps (MODE_HH)."""
+        self.call("b2s_set_option", 3, int(bool(wave)))
+
     def volume_dims(self):
         v = [c_int() for _ in range(4)]
         self.call("b2s_volume_dims", *[ctypes.byref(x) for x in v])
@@ -204,6 +209,9 @@ class Handle:
         ms = c_float()
         self.call("b2s_bench_aggregate", int(iters), ctypes.byref(ms))
         return ms.value
+
+    def enqueue_aggregate(self, iters=1):
+        self.call("b2s_enqueue_aggregate", int(iters))
 
     def bench_aggregate_parts(self, iters=10):
         """mean ms of every kernel launch of the aggregation group, in launch order"""

@@ -145,7 +145,8 @@ static int make_geom(b2s_ctx *c, int H, int W, int cn)
     g.minD = p.min_disparity;
     g.maxD = g.minD + p.num_disparities;
     g.D = p.num_disparities;
-    g.NP = (g.D + 63) / 64;
+    g.layout = agg_wave_selected(c, p.mode) ? 1 : 0;
+    g.NP = g.layout == 1 ? 2 * ((g.D + 127) / 128) : (g.D + 63) / 64; // the wavefront kernel takes whole blocks of 128 disparities
     g.Dp = 64 * g.NP;
     int bs = p.block_size > 0 ? p.block_size : 5;
     g.SW2 = g.SH2 = bs / 2;
@@ -163,7 +164,7 @@ static int make_geom(b2s_ctx *c, int H, int W, int cn)
     g.mode = p.mode;
     if (W - g.maxD <= g.SW2) return fail(c, B2S_ESIZE, "input images are too small for your window size and max disparity");
     if (g.ftzero > 127) return fail(c, B2S_EINVAL, "preFilterCap %d too large", p.pre_filter_cap);
-    if ((64 + 2 * g.SW2 + g.D - 1) / 2 + 2 > 168) // shared-memory tile of the cost kernel (sgbm_cost.cu: TX, NRP)
+    if ((g.layout == 0 ? (64 + 2 * g.SW2 + g.D - 1) / 2 + 2 : (64 + 2 * g.SW2 + g.Dp + 1) / 2) > 168) // shared-memory tile of the cost kernel (sgbm_cost.cu: TX, NRP)
         return fail(c, B2S_EINVAL, "blockSize %d is too large for numDisparities %d (supported: blockSize + numDisparities <= 269)", bs, g.D);
     c->g = g;
     size_t npx = (size_t)H * W, vol = (size_t)H * g.width1 * g.Dp * sizeof(int16_t);
@@ -543,7 +544,7 @@ int b2s_debug_fetch(b2s_handle c, int which, void *dst, size_t bytes)
     switch (which) {
     case B2S_FETCH_C: src = c->C.p; need = vol; break;
     case B2S_FETCH_S:
-        if (c->wta_fused && !c->keep_volumes)
+        if ((c->wta_fused || (c->wta_adds_s2 && c->fuse_wta)) && !c->keep_volumes)
             return fail(c, B2S_ESTATE, "the aggregated volume was not stored (winner-take-all is fused into the last scan); "
                                        "call b2s_set_option(h, B2S_OPT_KEEP_VOLUMES, 1) before computing");
         src = c->S.p; need = vol; break;
@@ -562,6 +563,15 @@ int b2s_debug_fetch(b2s_handle c, int which, void *dst, size_t bytes)
     if (bytes != need) return fail(c, B2S_EINVAL, "b2s_debug_fetch: need %zu bytes, got %zu", need, bytes);
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
+    if ((which == B2S_FETCH_C || which == B2S_FETCH_S) && g.layout != 0) {
+        // the ABI promises disparities in natural order: undo the device layout (SgbmGeom::layout) pixel by pixel
+        int16_t *px = (int16_t *)dst;
+        std::vector<int16_t> tmp(g.Dp);
+        for (size_t i = 0, n = (size_t)g.H * g.width1; i < n; i++, px += g.Dp) {
+            for (int d = 0; d < g.Dp; d++) tmp[d] = px[b2s_dindex(g.layout, d)];
+            memcpy(px, tmp.data(), (size_t)g.Dp * 2);
+        }
+    }
     return B2S_OK;
 }
 
@@ -571,6 +581,10 @@ int b2s_set_option(b2s_handle c, int option, int value)
     switch (option) {
     case B2S_OPT_KEEP_VOLUMES: c->keep_volumes = value != 0; return B2S_OK;
     case B2S_OPT_FUSE_WTA: c->fuse_wta = value != 0; return B2S_OK;
+    case B2S_OPT_AGG_SCHEDULE:
+        if (value != 0 && value != 1) return fail(c, B2S_EINVAL, "B2S_OPT_AGG_SCHEDULE: 0 (scans + sweep) or 1 (wavefront), got %d", value);
+        c->agg_schedule = value;
+        return B2S_OK;
     default: return fail(c, B2S_EINVAL, "b2s_set_option: unknown option %d", option);
     }
 }
@@ -595,14 +609,33 @@ int b2s_bench_aggregate(b2s_handle c, int iters, float *ms_per_iter)
     if (!c->have_volume) return fail(c, B2S_ESTATE, "no cost volume resident (run a disparity computation first)");
     CK(c, cudaSetDevice(c->device));
     int nl = 0;
+    // the group = path aggregation + winner-take-all (launch_wta is a no-op when the last scan fused it)
     CK(c, launch_aggregate(c, &nl)); // warm-up
+    CK(c, launch_wta(c));
     CK(c, cudaEventRecord(c->ev[0], c->stream));
-    for (int i = 0; i < iters; i++) CK(c, launch_aggregate(c, &nl));
+    for (int i = 0; i < iters; i++) {
+        CK(c, launch_aggregate(c, &nl));
+        CK(c, launch_wta(c));
+    }
     CK(c, cudaEventRecord(c->ev[7], c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     float ms = 0;
     CK(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[7]));
     *ms_per_iter = ms / iters;
+    if (agg_poll_error(c)) return fail(c, B2S_ECUDA, "aggregation hand-over timed out");
+    return B2S_OK;
+}
+
+int b2s_enqueue_aggregate(b2s_handle c, int iters)
+{
+    if (!c || iters <= 0) return B2S_EINVAL;
+    if (!c->have_volume) return fail(c, B2S_ESTATE, "no cost volume resident (run a disparity computation first)");
+    CK(c, cudaSetDevice(c->device));
+    int nl = 0;
+    for (int i = 0; i < iters; i++) {
+        CK(c, launch_aggregate(c, &nl));
+        CK(c, launch_wta(c));
+    }
     return B2S_OK;
 }
 
@@ -613,9 +646,14 @@ int b2s_bench_aggregate_parts(b2s_handle c, int iters, float *ms_parts, int max_
     CK(c, cudaSetDevice(c->device));
     int nl = 0;
     CK(c, launch_aggregate(c, &nl)); // warm-up
+    CK(c, launch_wta(c));
     for (int k = 0; k < max_parts; k++) ms_parts[k] = 0.f;
     for (int i = 0; i < iters; i++) {
         CK(c, launch_aggregate(c, &nl, c->aev));
+        if (!c->wta_fused && nl < B2S_AGG_MAX_PARTS) { // the stand-alone winner-take-all is the group's last part
+            CK(c, launch_wta(c));
+            CK(c, cudaEventRecord(c->aev[++nl], c->stream));
+        }
         CK(c, cudaStreamSynchronize(c->stream));
         for (int k = 0; k < nl && k < max_parts && k < B2S_AGG_MAX_PARTS; k++) {
             float ms = 0;

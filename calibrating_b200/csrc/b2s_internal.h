@@ -36,7 +36,15 @@ struct SgbmGeom {
     int minX1, width1;
     int SW2, SH2, ftzero, uniq, d12, P1, P2, invalid;
     int speckle_window, speckle_range, mode;
+    // order of the disparities inside a pixel's d-chunk of C / S (32-bit words of two int16):
+    //   0: word q = disparities (2q, 2q+1)                                  (scan / sweep kernels of sgbm_agg.cu)
+    //   1: word q = disparities (16b+j, 16b+8+j), b = q/8, j = q%8  ("block layout", wavefront kernel of sgbm_wave.cu)
+    int layout;
 };
+// int16 index of disparity d inside a pixel's d-chunk
+__host__ __device__ inline int b2s_dindex(int layout, int d) { return layout == 0 ? d : ((d >> 4) << 4) + ((d & 7) << 1) + ((d >> 3) & 1); }
+// first disparity of word q (the second one is +1 in layout 0, +8 in layout 1)
+__host__ __device__ inline int b2s_word_d0(int layout, int q) { return layout == 0 ? 2 * q : ((q >> 3) << 4) + (q & 7); }
 
 enum { AGG_INIT = 0, AGG_ACCUM = 1, AGG_ACCUM2 = 2 };
 constexpr int B2S_AGG_MAX_PARTS = 8;
@@ -54,9 +62,11 @@ struct b2s_ctx {
     bool have_volume = false;
     bool keep_volumes = false; // b2s_set_option(B2S_OPT_KEEP_VOLUMES): a fused last pass also stores S
     bool fuse_wta = true;      // b2s_set_option(B2S_OPT_FUSE_WTA): on by default
+    int agg_schedule = 0;      // b2s_set_option(B2S_OPT_AGG_SCHEDULE): 0 = scans + lock-step sweep (sgbm_agg.cu), 1 = wavefront sweeps (sgbm_wave.cu)
     bool agg_legacy = false;   // launch_aggregate: per-direction scan kernels (strips too wide, or B2S_AGG_LEGACY)
     bool hs_pending = false;   // launch_cost_volume stopped at the row sums (in S2): the first horizontal scan forms C (agg_fuses_vsum)
     bool wta_fused = false;    // set by launch_aggregate when the last scan already did the winner-take-all
+    bool wta_adds_s2 = false;  // set by launch_aggregate (wavefront schedule, MODE_HH): the aggregated volume is sat(S + S2), formed by wta_kernel
 
     // matcher buffers
     DevBuf left, right;       // (H,W,cn) u8
@@ -98,6 +108,9 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
 // sgbm_agg.cu
 cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks = nullptr);
 bool agg_fuses_vsum(const b2s_ctx *c);
+bool agg_wave_selected(const b2s_ctx *c, int mode); // the wavefront schedule (sgbm_wave.cu) applies to this matcher mode (decides SgbmGeom::layout)
+// sgbm_wave.cu
+cudaError_t launch_wave(b2s_ctx *c, int ndirs);
 int agg_poll_error(b2s_ctx *c); // after a stream sync: 1 if a hand-over wait of the fused sweep timed out
 // sgbm_post.cu
 cudaError_t launch_wta_prepare(b2s_ctx *c); // before the aggregation: clears the WTA outputs

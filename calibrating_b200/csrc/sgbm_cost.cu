@@ -64,7 +64,9 @@ constexpr int COST_THREADS = 256;
 constexpr int BT_BIAS = 256;
 constexpr int NRP_MAX = (TX + 2 * 5 + 256) / 2 + 3; // packed right-pixel pairs per copy; compile-time strides (template NRP): 104 for D <= 128, NRP_MAX for D <= 256
 
-template <int CN, int NRP>
+// LAYOUT 1 (block layout of the wavefront kernel: a word = disparities (d, d+8)): the right-pixel table holds ONE entry per
+// reversed index m = (pixel m, pixel m+8) instead of the two alignment copies of neighbouring pairs; 2*NRP entries per plane.
+template <int CN, int NRP, int LAYOUT>
 __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4 *__restrict__ PL, const uchar4 *__restrict__ PR,
                                                                     int16_t *__restrict__ hs, SgbmGeom g)
 {
@@ -94,11 +96,19 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
     const int nrp = (TXH + g.D - 1) / 2 + 2; // pairs actually read by phase 1 (<= NRP, checked by the launcher)
     for (int i = threadIdx.x; i < NPL * 2 * NRP; i += COST_THREADS) {
         const int pc = i / NRP, wd = i % NRP, p = pc >> 1, cp = pc & 1;
-        if (wd >= nrp) continue;
         const uchar4 *prow = PR + ((size_t)y * NPL + p) * g.W;
-        int m0 = 2 * wd + cp; // copy 0: pairs (2w, 2w+1); copy 1: pairs (2w+1, 2w+2)
+        int m0, m1;
+        if (LAYOUT == 0) {
+            if (wd >= nrp) continue;
+            m0 = 2 * wd + cp; // copy 0: pairs (2w, 2w+1); copy 1: pairs (2w+1, 2w+2)
+            m1 = m0 + 1;
+        } else {
+            m0 = cp * NRP + wd; // one table of 2*NRP entries: pair (m, m+8)
+            if (m0 >= TXH + g.Dp) continue;
+            m1 = m0 + 8;
+        }
         uchar4 a = prow[clampi(xrmax - m0, 0, g.W - 1)];
-        uchar4 b = prow[clampi(xrmax - m0 - 1, 0, g.W - 1)];
+        uchar4 b = prow[clampi(xrmax - m1, 0, g.W - 1)];
         sR[i] = make_uint4(a.x | ((uint32_t)b.x << 16), a.y | ((uint32_t)b.y << 16), a.z | ((uint32_t)b.z << 16), 0u);
     }
     __syncthreads();
@@ -117,16 +127,17 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
 #pragma unroll
         for (int p = 0; p < NPL; p++) Lc[p] = sL[j * NPL + p];
         const int mj = TXH - 1 - j; // reversed right index of d = 0
-        const uint4 *rbase = sR + (mj & 1) * NRP + (mj >> 1);
-        for (int q = lane; q < DW; q += 32) { // d0 = 2q
-            if (2 * q >= g.D) { // padded d-lanes are zero in C
+        const uint4 *rbase = LAYOUT == 0 ? sR + (mj & 1) * NRP + (mj >> 1) : sR + mj;
+        for (int q = lane; q < DW; q += 32) { // word q = disparities (d0, d1)
+            const int d0 = b2s_word_d0(LAYOUT, q), d1 = d0 + (LAYOUT == 0 ? 1 : 8);
+            if (d0 >= g.D) { // padded d-lanes are zero in C
                 out[q] = 0;
                 continue;
             }
             uint32_t acc = 0;
 #pragma unroll
             for (int p = 0; p < NPL; p++) {
-                const uint4 R4 = rbase[p * 2 * NRP + q];
+                const uint4 R4 = rbase[p * 2 * NRP + (LAYOUT == 0 ? q : d0)];
                 const uint32_t V = R4.x, V0 = R4.y, V1 = R4.z;
                 uint32_t c0 = __vimax3_s16x2(Lc[p].x - V1, V0 + Lc[p].y, Bp);
                 uint32_t c1 = __vimax3_s16x2(V + Lc[p].z, Lc[p].w - V, Bp);
@@ -135,7 +146,7 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
                 acc += c;
             }
             acc -= unbias;
-            if (2 * q + 1 >= g.D) acc &= 0x0000FFFFu;
+            if (d1 >= g.D) acc &= 0x0000FFFFu;
             out[q] = acc;
         }
     }
@@ -217,10 +228,10 @@ __global__ void __launch_bounds__(256) census_cost_kernel(const unsigned long lo
     const unsigned long long *rrow = dr + (size_t)y * g.W;
     uint32_t *out = C + ((size_t)y * g.width1 + x1) * DW;
     for (int q = lane; q < DW; q += 32) {
-        const int d0 = 2 * q;
+        const int d0 = b2s_word_d0(g.layout, q), d1 = d0 + (g.layout == 0 ? 1 : 8);
         uint32_t v = 0;
         if (d0 < g.D) v = __popcll(l ^ rrow[x - (d0 + g.minD)]);
-        if (d0 + 1 < g.D) v |= (uint32_t)__popcll(l ^ rrow[x - (d0 + 1 + g.minD)]) << 16;
+        if (d1 < g.D) v |= (uint32_t)__popcll(l ^ rrow[x - (d1 + g.minD)]) << 16;
         out[q] = v; // padded d-lanes are zero in C
     }
 }
@@ -272,7 +283,7 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
         planes_kernel<1><<<pg, pb, 0, c->stream>>>(d_left, PL, g.H, g.W, g.ftzero);
         planes_kernel<1><<<pg, pb, 0, c->stream>>>(d_right, PR, g.H, g.W, g.ftzero);
     }
-    const int TXH = TX + 2 * g.SW2, need = (TXH + g.D - 1) / 2 + 2;
+    const int TXH = TX + 2 * g.SW2, need = g.layout == 0 ? (TXH + g.D - 1) / 2 + 2 : (TXH + g.Dp + 1) / 2;
     if (need > NRP_MAX) return cudaErrorInvalidValue; // (b2s_api.cu rejects such block sizes with a message)
     const int nrp = need <= 104 ? 104 : NRP_MAX;
     size_t smem = (size_t)NPL * TXH * sizeof(uint4) + (size_t)NPL * 2 * nrp * sizeof(uint4) + (size_t)TXH * g.Dp * sizeof(int16_t);
@@ -289,8 +300,13 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
         return cudaSuccess;
     };
     cudaError_t e;
-    if (g.cn == 3) e = nrp == 104 ? launch(pixcost_hsum_kernel<3, 104>) : launch(pixcost_hsum_kernel<3, NRP_MAX>);
-    else e = nrp == 104 ? launch(pixcost_hsum_kernel<1, 104>) : launch(pixcost_hsum_kernel<1, NRP_MAX>);
+    if (g.layout == 0) {
+        if (g.cn == 3) e = nrp == 104 ? launch(pixcost_hsum_kernel<3, 104, 0>) : launch(pixcost_hsum_kernel<3, NRP_MAX, 0>);
+        else e = nrp == 104 ? launch(pixcost_hsum_kernel<1, 104, 0>) : launch(pixcost_hsum_kernel<1, NRP_MAX, 0>);
+    } else {
+        if (g.cn == 3) e = nrp == 104 ? launch(pixcost_hsum_kernel<3, 104, 1>) : launch(pixcost_hsum_kernel<3, NRP_MAX, 1>);
+        else e = nrp == 104 ? launch(pixcost_hsum_kernel<1, 104, 1>) : launch(pixcost_hsum_kernel<1, NRP_MAX, 1>);
+    }
     if (e != cudaSuccess) return e;
     c->launches += 3;
     if (fuse_vsum) return cudaGetLastError();

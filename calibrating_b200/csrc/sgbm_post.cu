@@ -14,24 +14,39 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v,
 // (strict '>' => among equal costs the largest x1 wins).  That order-dependent rule is an atomicMin on the key
 // (minS << 16) | (0xFFFF - x1).
 constexpr int WTA_CHUNK = 32;
-template <int NP>
-__global__ void __launch_bounds__(256) wta_kernel(const int16_t *__restrict__ S, int16_t *__restrict__ raw,
-                                                  unsigned *__restrict__ disp2key, SgbmGeom g)
+// ADD2: the aggregated volume is sat16(S + S2) (the two sweeps of the wavefront schedule, sgbm_wave.cu), formed here on
+// the fly; keep != 0 also writes it back to S (B2S_OPT_KEEP_VOLUMES: S stays fetchable).
+template <int NP, bool ADD2, int LAYOUT>
+__global__ void __launch_bounds__(256) wta_kernel(int16_t *__restrict__ S, const int16_t *__restrict__ S2, int16_t *__restrict__ raw,
+                                                  unsigned *__restrict__ disp2key, SgbmGeom g, int keep)
 {
     // a warp walks WTA_CHUNK consecutive pixels of one row (no index divisions); blockIdx.y = row
     const int lane = threadIdx.x & 31, y = blockIdx.y;
     const int xb = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * WTA_CHUNK, xe = min(xb + WTA_CHUNK, g.width1);
     if (xb >= xe) return;
     const int Dp = 64 * NP;
-    const int16_t *Srow = S + (size_t)y * g.width1 * Dp;
-    auto load_px = [&](int x, uint32_t (&v)[NP]) {
-        const int16_t *Sp = Srow + (size_t)x * Dp;
+    int16_t *Srow = S + (size_t)y * g.width1 * Dp;
+    const int16_t *S2row = S2 + (size_t)y * g.width1 * Dp;
+    auto load_one = [&](const int16_t *Sp, uint32_t (&v)[NP]) {
         if constexpr (NP == 1) v[0] = __ldcs((const uint32_t *)(Sp + lane * 2));
         else if constexpr (NP == 2) { uint2 t = __ldcs((const uint2 *)(Sp + lane * 4)); v[0] = t.x; v[1] = t.y; }
         else if constexpr (NP == 4) { uint4 t = __ldcs((const uint4 *)(Sp + lane * 8)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
         else {
 #pragma unroll
             for (int i = 0; i < NP; i++) v[i] = __ldcs((const uint32_t *)(Sp + lane * 2 * NP) + i);
+        }
+    };
+    auto load_px = [&](int x, uint32_t (&v)[NP]) {
+        load_one(Srow + (size_t)x * Dp, v);
+        if constexpr (ADD2) {
+            uint32_t v2[NP];
+            load_one(S2row + (size_t)x * Dp, v2);
+#pragma unroll
+            for (int i = 0; i < NP; i++) v[i] = __viaddmin_u16x2(v[i], v2[i], 0x7FFF7FFFu);
+            if (keep) {
+#pragma unroll
+                for (int i = 0; i < NP; i++) *((uint32_t *)(Srow + (size_t)x * Dp + lane * 2 * NP) + i) = v[i];
+            }
         }
     };
     // three pixels in flight per warp: the body is one dependent chain per pixel, and with a single 256-byte load
@@ -57,7 +72,7 @@ __global__ void __launch_bounds__(256) wta_kernel(const int16_t *__restrict__ S,
             }
 #pragma unroll
             for (int j = 0; j < 2 * NP; j++) {
-                int d = lane * 2 * NP + j;
+                const int d = b2s_word_d0(LAYOUT, lane * NP + (j >> 1)) + (j & 1) * (LAYOUT == 0 ? 1 : 8);
                 if (d < g.D) key = min(key, ((unsigned)(sv[j] & 0xffff) << 16) | (unsigned)d);
             }
             key = __reduce_min_sync(0xffffffffu, key);
@@ -67,7 +82,7 @@ __global__ void __launch_bounds__(256) wta_kernel(const int16_t *__restrict__ S,
             bool bad = false;
 #pragma unroll
             for (int j = 0; j < 2 * NP; j++) {
-                int d = lane * 2 * NP + j;
+                const int d = b2s_word_d0(LAYOUT, lane * NP + (j >> 1)) + (j & 1) * (LAYOUT == 0 ? 1 : 8);
                 if (d < g.D && sv[j] * thr_mul < minS * 100 && abs(best - d) > 1) bad = true;
             }
             const bool rej = __any_sync(0xffffffffu, bad);
@@ -76,6 +91,10 @@ __global__ void __launch_bounds__(256) wta_kernel(const int16_t *__restrict__ S,
                 my_minS = minS;
             }
         }
+    }
+    if (ADD2 && keep) {
+        __threadfence_block();
+        __syncwarp();
     }
     // the per-pixel tail (right-view candidate, sub-pixel interpolation, store) runs once for the warp's 32 pixels, one per lane
     const int x = xb + lane;
@@ -87,7 +106,14 @@ __global__ void __launch_bounds__(256) wta_kernel(const int16_t *__restrict__ S,
         if (minS < 32767 && x2 >= 0 && x2 < g.W + 2)
             atomicMin(&disp2key[(size_t)y * (g.W + 2) + x2], ((unsigned)minS << 16) | (unsigned)(0xFFFF - x));
         if (0 < d && d < g.D - 1) {
-            int sm = Sp[d - 1], sp = Sp[d + 1], s0 = Sp[d];
+            const int im = b2s_dindex(LAYOUT, d - 1), ip = b2s_dindex(LAYOUT, d + 1), i0 = b2s_dindex(LAYOUT, d);
+            int sm = Sp[im], sp = Sp[ip], s0 = Sp[i0];
+            if constexpr (ADD2) {
+                if (!keep) { // (with keep the sums are already in S; the __syncwarp above orders the write-back before these reads)
+                    const int16_t *Sq = S2row + (size_t)x * Dp;
+                    sm = min(sm + Sq[im], 32767); sp = min(sp + Sq[ip], 32767); s0 = min(s0 + Sq[i0], 32767);
+                }
+            }
             int den2 = max(sm + sp - 2 * s0, 1);
             d = d * 16 + ((sm - sp) * 16 + den2) / (den2 * 2);
         } else
@@ -289,16 +315,24 @@ cudaError_t launch_wta(b2s_ctx *c)
     if (c->wta_fused) return cudaSuccess; // the last aggregation scan already selected the winners (sgbm_agg.cu)
     const SgbmGeom &g = c->g;
     dim3 blocks((g.width1 + 8 * WTA_CHUNK - 1) / (8 * WTA_CHUNK), g.H);
-    const int16_t *S = c->S.as<int16_t>();
+    int16_t *S = c->S.as<int16_t>();
+    const int16_t *S2 = c->S2.as<int16_t>();
     int16_t *raw = c->raw.as<int16_t>();
     unsigned *keys = c->disp2key.as<unsigned>();
+    const int keep = (c->keep_volumes || !c->fuse_wta) ? 1 : 0; // (B2S_OPT_FUSE_WTA = 0 promises a stored S, like the unfused scans)
+#define B2S_WTA(NPV)                                                                                                                      \
+    if (g.layout == 1 && c->wta_adds_s2) wta_kernel<NPV, true, 1><<<blocks, 256, 0, c->stream>>>(S, S2, raw, keys, g, keep);              \
+    else if (g.layout == 1) wta_kernel<NPV, false, 1><<<blocks, 256, 0, c->stream>>>(S, S2, raw, keys, g, 0);                             \
+    else if (c->wta_adds_s2) wta_kernel<NPV, true, 0><<<blocks, 256, 0, c->stream>>>(S, S2, raw, keys, g, keep);                          \
+    else wta_kernel<NPV, false, 0><<<blocks, 256, 0, c->stream>>>(S, S2, raw, keys, g, 0);
     switch (g.NP) {
-    case 1: wta_kernel<1><<<blocks, 256, 0, c->stream>>>(S, raw, keys, g); break;
-    case 2: wta_kernel<2><<<blocks, 256, 0, c->stream>>>(S, raw, keys, g); break;
-    case 3: wta_kernel<3><<<blocks, 256, 0, c->stream>>>(S, raw, keys, g); break;
-    case 4: wta_kernel<4><<<blocks, 256, 0, c->stream>>>(S, raw, keys, g); break;
+    case 1: B2S_WTA(1) break;
+    case 2: B2S_WTA(2) break;
+    case 3: B2S_WTA(3) break;
+    case 4: B2S_WTA(4) break;
     default: return cudaErrorInvalidValue;
     }
+#undef B2S_WTA
     c->launches++;
     return cudaGetLastError();
 }

@@ -190,21 +190,31 @@ int b2s_undistort_img(b2s_handle h, const uint8_t *img1, int cn, uint8_t *out);
 /* Options.
  * B2S_OPT_FUSE_WTA (default 1): the winner-take-all step runs inside the last aggregation pass; the aggregated volume S is
  *   then never written unless B2S_OPT_KEEP_VOLUMES (default 0) is also set (B2S_FETCH_S fails otherwise).  With 0 the pass
- *   stores S and a separate kernel picks the winners.  Results are identical either way. */
+ *   stores S and a separate kernel picks the winners.  Results are identical either way.
+ * B2S_OPT_AGG_SCHEDULE (default 0): how the eight paths of MODE_HH are scheduled.  0 = two horizontal scans around a
+ *   lock-step vertical sweep (20 bytes of DRAM traffic per cost voxel; the fastest for one pair); 1 = two wavefront sweeps of four
+ *   paths each in OpenCV's own order (the canonical 8 bytes per voxel; sgbm_wave.cu).  Results are identical; other modes
+ *   ignore it.  The environment variable B2S_AGG_SCHEDULE=sweep|wave overrides the option. */
 #define B2S_OPT_KEEP_VOLUMES 1
 #define B2S_OPT_FUSE_WTA 2
+#define B2S_OPT_AGG_SCHEDULE 3
 int b2s_set_option(b2s_handle h, int option, int value);
 int b2s_volume_dims(b2s_handle h, int *H, int *width1, int *D, int *Dp);
 int b2s_debug_fetch(b2s_handle h, int which, void *dst, size_t bytes);
 int b2s_timings(b2s_handle h, b2s_timing *t);      /* CUDA-event stage times of the last synchronous call */
 int b2s_launch_count(b2s_handle h, long long *n);  /* kernels launched by this handle since creation */
-/* Timed loop of the aggregation kernels alone on the resident cost volume of the last call (bench.py roofline):
- * runs `iters` repetitions on the handle's stream between two CUDA events, returns the mean ms per repetition. */
+/* Timed loop of the aggregation GROUP (path aggregation + winner-take-all: everything between the cost volume C and the raw
+ * winner map) alone on the resident cost volume of the last call (bench.py roofline): runs `iters` repetitions on the
+ * handle's stream between two CUDA events, returns the mean ms per repetition. */
 int b2s_bench_aggregate(b2s_handle h, int iters, float *ms_per_iter);
-/* Same, with one CUDA-event interval per kernel launch of the aggregation group (in launch order: horizontal +x scan,
- * fused vertical sweep, horizontal -x scan; or one scan per direction on the legacy path).  ms_parts[k] = mean ms of
+/* Same, with one CUDA-event interval per kernel launch of the group in launch order (wavefront schedule, MODE_HH: the
+ * two-sweep launch, then the winner-take-all that adds the two sums; MODE_SGBM: the top-down sweep, then the (-1,0) scan with
+ * the fused winner-take-all; B2S_AGG_SCHEDULE=sweep: +x scan, fused vertical sweep, -x scan).  ms_parts[k] = mean ms of
  * launch k over `iters` repetitions, *n_parts = number of launches (<= max_parts). */
 int b2s_bench_aggregate_parts(b2s_handle h, int iters, float *ms_parts, int max_parts, int *n_parts);
+/* Enqueue `iters` repetitions of the group on the handle's stream without waiting (several handles in flight: the batched
+ * figure of bench.py; bracket with b2s_event_record / b2s_event_elapsed). */
+int b2s_enqueue_aggregate(b2s_handle h, int iters);
 /* User CUDA events on the handle's stream (slot 0..3), for device-side timing of caller-defined regions. */
 int b2s_event_record(b2s_handle h, int slot);
 /* ms between event `slot_a` of handle a and event `slot_b` of handle b (same device); waits for event b. */

@@ -68,11 +68,40 @@ def test_stage_parity_random(handle, seed):
     assert f.dtype == np.float32 and np.array_equal(f, exp / 16.0)
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_wavefront_schedule(handle, seed, monkeypatch):
+    """The wavefront schedule (sgbm_wave.cu; B2S_AGG_SCHEDULE=wave / B2S_OPT_AGG_SCHEDULE = 1) on images of several bands (hand-over between CTAs through the
+    global ring), of fewer rows than a band, and taller than one wave of CTAs (bands wait for SMs)."""
+    if seed % 2:
+        monkeypatch.setenv("B2S_AGG_SCHEDULE", "wave")
+    else:
+        handle.call("b2s_set_option", 3, 1)
+    rng = np.random.default_rng(300 + seed)
+    c = _case(rng, mode=1)
+    if seed % 3 == 0:
+        c["h"] = int(rng.integers(1, 9))
+    if seed % 8 == 7:
+        c["h"] = 1500 if c["p"]["num_disparities"] > 128 else 2600  # more bands than CTAs fit on the device at once
+        c["w"] = c["p"]["num_disparities"] + c["p"]["min_disparity"] + 40
+    l, r, _ = synth.rectified_pair(c["h"], c["w"], c["p"]["num_disparities"], seed, c["cn"])
+    ref = osgbm.sgbm_compute(l, r, want_volumes=True, **c["p"])
+    try:
+        got = cb.StereoSGBM(handle=handle, **c["p"]).compute(l, r)
+        assert handle.volume_dims()[3] % 128 == 0, "the wavefront schedule (block layout) was not selected"
+        assert np.array_equal(handle.fetch_volume(0), ref["C"]), "cost volume (block layout, natural order through the ABI)"
+        assert np.array_equal(handle.fetch_volume(1), ref["S"]), "aggregated volume"
+        assert np.array_equal(got, ref["disp"])
+    finally:
+        handle.call("b2s_set_option", 3, 0)
+
+
 @pytest.mark.parametrize("cols", ["1", "2", "3", "5", "32", "legacy"])
 @pytest.mark.parametrize("seed", [1, 2, 3, 5, 6])
 def test_aggregation_strip_handover(handle, seed, cols, monkeypatch):
-    """The fused vertical sweep cut into strips of 1..32 columns (several CTAs exchanging diagonal states through the
-    global hand-over rings) and the legacy one-kernel-per-direction path all give the oracle's S volume."""
+    """The round-1 schedule (B2S_AGG_SCHEDULE=sweep): the fused vertical sweep cut into strips of 1..32 columns (several CTAs
+    exchanging diagonal states through the global hand-over rings) and the legacy one-kernel-per-direction path all give the
+    oracle's S volume."""
+    monkeypatch.setenv("B2S_AGG_SCHEDULE", "sweep")
     if cols == "legacy":
         monkeypatch.setenv("B2S_AGG_LEGACY", "1")
     else:

@@ -1,1 +1,1 @@
-#define B2S_BUILD_HASH "c79eec3fb79428fa"
+#define B2S_BUILD_HASH "a54bf16cfba84c83"

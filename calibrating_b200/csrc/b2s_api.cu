@@ -7,6 +7,12 @@
 #include <new>
 
 #include "b2s_internal.h"
+#if __has_include("build_hash.h")
+#include "build_hash.h" // written by calibrating_b200/build.py: sha256 over the CUDA sources
+#endif
+#ifndef B2S_BUILD_HASH
+#define B2S_BUILD_HASH "unknown"
+#endif
 
 static thread_local std::string g_create_err;
 
@@ -20,6 +26,13 @@ static int fail(b2s_ctx *c, int code, const char *fmt, ...)
     if (c) c->err = buf;
     else g_create_err = buf;
     return code;
+}
+// device error flags of the matcher (sgbm_agg.cu: agg_poll_error)
+static int agg_fail(b2s_ctx *c, int flags)
+{
+    if (flags & 1) return fail(c, B2S_ECUDA, "aggregation hand-over timed out (a wait inside the aggregation kernels expired)");
+    return fail(c, B2S_EINVAL, "a block sum of the cost volume wrapped past 32767 (C < 0): outside the int16 domain this matcher is exact "
+                               "on; use a smaller blockSize");
 }
 #define CK(c, call)                                                                                          \
     do {                                                                                                     \
@@ -35,6 +48,8 @@ int b2s_device_count(void)
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
 }
+
+const char *b2s_build_hash(void) { return B2S_BUILD_HASH; }
 
 const char *b2s_last_error(b2s_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
@@ -98,7 +113,7 @@ int b2s_sync(b2s_handle c)
     if (!c) return B2S_EINVAL;
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
-    if (agg_poll_error(c)) return fail(c, B2S_ECUDA, "aggregation hand-over timed out (strips of the fused sweep were not co-resident?)");
+    if (int ae = agg_poll_error(c)) return agg_fail(c, ae);
     return B2S_OK;
 }
 
@@ -236,7 +251,7 @@ static int compute_disparity_host(b2s_ctx *c, const uint8_t *left, const uint8_t
     if (sync) {
         CK(c, cudaStreamSynchronize(c->stream));
         collect_timing(c, false);
-        if (agg_poll_error(c)) return fail(c, B2S_ECUDA, "aggregation hand-over timed out");
+        if (int ae = agg_poll_error(c)) return agg_fail(c, ae);
     }
     return B2S_OK;
 }
@@ -430,7 +445,7 @@ static int get_depth_impl(b2s_ctx *c, const uint8_t *img1, const uint8_t *img2, 
     if (sync) {
         CK(c, cudaStreamSynchronize(c->stream));
         collect_timing(c, true);
-        if (agg_poll_error(c)) return fail(c, B2S_ECUDA, "aggregation hand-over timed out");
+        if (int ae = agg_poll_error(c)) return agg_fail(c, ae);
     }
     return B2S_OK;
 }
@@ -622,7 +637,7 @@ int b2s_bench_aggregate(b2s_handle c, int iters, float *ms_per_iter)
     float ms = 0;
     CK(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[7]));
     *ms_per_iter = ms / iters;
-    if (agg_poll_error(c)) return fail(c, B2S_ECUDA, "aggregation hand-over timed out");
+    if (int ae = agg_poll_error(c)) return agg_fail(c, ae);
     return B2S_OK;
 }
 
@@ -662,7 +677,7 @@ int b2s_bench_aggregate_parts(b2s_handle c, int iters, float *ms_parts, int max_
         }
     }
     *n_parts = nl < max_parts ? nl : max_parts;
-    if (agg_poll_error(c)) return fail(c, B2S_ECUDA, "aggregation hand-over timed out");
+    if (int ae = agg_poll_error(c)) return agg_fail(c, ae);
     return B2S_OK;
 }
 

@@ -111,7 +111,8 @@ bool agg_fuses_vsum(const b2s_ctx *c);
 bool agg_wave_selected(const b2s_ctx *c, int mode); // the wavefront schedule (sgbm_wave.cu) applies to this matcher mode (decides SgbmGeom::layout)
 // sgbm_wave.cu
 cudaError_t launch_wave(b2s_ctx *c, int ndirs);
-int agg_poll_error(b2s_ctx *c); // after a stream sync: 1 if a hand-over wait of the fused sweep timed out
+cudaError_t agg_error_flags(b2s_ctx *c); // creates the handle's device error flags (c->agg_err) on first use
+int agg_poll_error(b2s_ctx *c); // after a stream sync: bit 0 = a wait of the aggregation kernels timed out, bit 1 = cost volume outside the int16 exactness domain
 // sgbm_post.cu
 cudaError_t launch_wta_prepare(b2s_ctx *c); // before the aggregation: clears the WTA outputs
 cudaError_t launch_wta(b2s_ctx *c);         // after it: stand-alone WTA kernel unless the aggregation fused it

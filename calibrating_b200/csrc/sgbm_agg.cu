@@ -395,6 +395,7 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_vsum_kernel(AggArgs a)
     for (int i = 0; i < NP; i++) T[i] = padmask[i];
     const long long o0 = (long long)y * rowE + lane * 2 * NP;
     int16_t *sp = a.S + o0, *cp = const_cast<int16_t *>(a.C) + o0;
+    uint32_t ovf = 0;
 #pragma unroll 1
     for (int j = 0; j < nchunks; j++) {
         __syncwarp(); // every lane is done with the slot of chunk j-1: it is refilled now
@@ -414,6 +415,8 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_vsum_kernel(AggArgs a)
                 for (int i = 0; i < NP; i++) c[i] = __vadd2(c[i], h[i]);
             }
             stcg_regs<NP>(cp, c);
+#pragma unroll
+            for (int i = 0; i < NP; i++) ovf |= c[i]; // a wrapped block sum (C < 0) has bit 15 of its half set
             sgm_step<NP, PAD>(T, c, L, padmask, P1v, P2mP1v, lane);
             stcg_regs<NP>(sp, L);
             sp += Dp;
@@ -421,6 +424,7 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_vsum_kernel(AggArgs a)
             cur += CH;
         }
     }
+    if (ovf & 0x80008000u) a.err[1] = 1;
 }
 
 template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *c, const AggArgs &a)
@@ -430,25 +434,19 @@ template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *
     if (a.my == 0 && !c->agg_legacy) {
         // horizontal scans: bulk-copy rings + the fused WTA's exchange buffers + one mbarrier per ring slot
         const size_t smem_h = (size_t)WARPS * HS_SLOTS * (STAGE_BYTES * HsChunk<NP>::px) + (WTA != 0 ? (size_t)WARPS * 2 * 128 * NP : 0) + WARPS * HS_SLOTS * 8;
-        static bool configured_h_dev[64] = {}; // per instantiation and device (the attribute belongs to the device's context)
-        bool &configured_h = configured_h_dev[c->device & 63];
-        if (!configured_h) {
-            cudaError_t e = cudaFuncSetAttribute(agg_hscan_kernel<NP, PAD, MODE, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h);
-            if (e != cudaSuccess) return e;
-            configured_h = true;
-        }
+        static std::once_flag once_h[64]; // per instantiation and device (the attribute belongs to the device's context)
+        cudaError_t e = cudaSuccess;
+        std::call_once(once_h[c->device & 63], [&] { e = cudaFuncSetAttribute(agg_hscan_kernel<NP, PAD, MODE, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h); });
+        if (e != cudaSuccess) return e;
         agg_hscan_kernel<NP, PAD, MODE, WTA><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem_h, c->stream>>>(a);
     } else if constexpr (WTA != 0) {
         return cudaErrorInvalidValue; // the generic scan has no fused winner-take-all (launch_aggregate never asks for one)
     } else {
         const size_t smem = (size_t)WARPS * Stages<NP>::value * STAGE_BYTES;
-        static bool configured_dev[64] = {};
-        bool &configured = configured_dev[c->device & 63];
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(agg_scan_kernel<NP, PAD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured = true;
-        }
+        static std::once_flag once[64];
+        cudaError_t e = cudaSuccess;
+        std::call_once(once[c->device & 63], [&] { e = cudaFuncSetAttribute(agg_scan_kernel<NP, PAD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+        if (e != cudaSuccess) return e;
         agg_scan_kernel<NP, PAD, MODE><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
     }
     c->launches++;
@@ -478,13 +476,10 @@ cudaError_t launch_dir_np(b2s_ctx *c, const AggArgs &a, int mode, int wta = 0)
 template <int NP, bool PAD, int NV> cudaError_t launch_hscan_vsum_t(b2s_ctx *c, const AggArgs &a)
 {
     const size_t smem = (size_t)WARPS * HV_SLOTS * NV * HvChunk<NP>::px * 128 * NP + WARPS * HV_SLOTS * 8;
-    static bool configured_dev[64] = {}; // per instantiation and device (the attribute belongs to the device's context)
-    bool &configured = configured_dev[c->device & 63];
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(agg_hscan_vsum_kernel<NP, PAD, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static std::once_flag once[64]; // per instantiation and device (the attribute belongs to the device's context)
+    cudaError_t e = cudaSuccess;
+    std::call_once(once[c->device & 63], [&] { e = cudaFuncSetAttribute(agg_hscan_vsum_kernel<NP, PAD, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    if (e != cudaSuccess) return e;
     agg_hscan_vsum_kernel<NP, PAD, NV><<<(a.H + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
     c->launches++;
     return cudaGetLastError();
@@ -805,15 +800,12 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
 
 template <int NP, bool PAD, int JW, int R> cudaError_t launch_vsweep_t(b2s_ctx *c, const VsArgs &a, int G, size_t smem)
 {
-    static bool configured_dev[64] = {}; // per instantiation and device (the attribute belongs to the device's context)
-    bool &configured = configured_dev[c->device & 63];
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(agg_vsweep_kernel<NP, PAD, JW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static std::once_flag once[64]; // per instantiation and device (the attribute belongs to the device's context)
+    cudaError_t e = cudaSuccess;
+    std::call_once(once[c->device & 63], [&] { e = cudaFuncSetAttribute(agg_vsweep_kernel<NP, PAD, JW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
+    if (e != cudaSuccess) return e;
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, agg_vsweep_kernel<NP, PAD, JW, R>, a.n * JW * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, agg_vsweep_kernel<NP, PAD, JW, R>, a.n * JW * 32, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1 || G > occ * c->num_sms) return cudaErrorCooperativeLaunchTooLarge; // all strips must be co-resident
     agg_vsweep_kernel<NP, PAD, JW, R><<<G, a.n * JW * 32, smem, c->stream>>>(a);
@@ -928,12 +920,26 @@ bool agg_fuses_vsum(const b2s_ctx *c)
     return c->prm.cost == 0 && c->g.SH2 <= 2 && c->g.mode != 3 && vsweep_cols(c) > 0;
 }
 
+// Device error flags of a handle, read by agg_poll_error after a stream sync: word 0 = a wait of the aggregation kernels timed
+// out (lost hand-over or bulk copy), word 1 = a block sum of the cost volume wrapped past 32767 (C < 0; possible from block 11 with
+// three channels on: 121 * 279 = 33759), which the packed unsigned arithmetic of the aggregation does not follow.
+cudaError_t agg_error_flags(b2s_ctx *c)
+{
+    if (c->agg_err) return cudaSuccess;
+    cudaError_t e = c->agg_errbuf.ensure(256);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMemset(c->agg_errbuf.p, 0, 256)) != cudaSuccess) return e;
+    c->agg_err = c->agg_errbuf.as<int>();
+    return cudaSuccess;
+}
+
 int agg_poll_error(b2s_ctx *c)
 {
     if (!c->agg_err) return 0;
-    int v = 0;
-    if (cudaMemcpy(&v, c->agg_err, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
-    return v;
+    int v[2] = {0, 0};
+    if (cudaMemcpy(v, c->agg_err, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    if (v[0] || v[1]) cudaMemset(c->agg_err, 0, sizeof v); // reported once
+    return (v[0] ? 1 : 0) | (v[1] ? 2 : 0);
 }
 
 // Directions as (mx,my) of the MOVE along the path (predecessor = p - move).  cv2 pass 1: (+1,0) (+1,+1) (0,+1) (-1,+1);
@@ -958,10 +964,11 @@ cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
     a.disp2key = c->disp2key.as<unsigned>();
     a.W = g.W; a.minX1 = g.minX1; a.minD = g.minD; a.uniq = g.uniq;
     // device error flag of this aggregation (a wait that timed out: lost strip hand-over or bulk copy), read by agg_poll_error
+    // (sticky: cleared when the buffer is created and by agg_poll_error after it reported, never per launch -- several pairs may be
+    // queued on the stream between two polls)
     cudaError_t e;
-    if ((e = c->agg_errbuf.ensure(256)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(c->agg_errbuf.p, 0, 256, c->stream)) != cudaSuccess) return e;
-    a.err = c->agg_err = c->agg_errbuf.as<int>();
+    if ((e = agg_error_flags(c)) != cudaSuccess) return e;
+    a.err = c->agg_err;
     const int thr = 100 - g.uniq;
     a.uniq_M = thr > 1 ? (unsigned)(((1ull << 32) + thr - 1) / thr) : 0u;
     const bool can_fuse = c->fuse_wta && thr >= 1 && thr <= 100; // (uniquenessRatio >= 100 goes through wta_kernel)

@@ -6,6 +6,10 @@
 //
 // Layout in HBM: planes  (H, 2cn, W) uchar4 {value, lo, hi, 0}   lo/hi = Birchfield-Tomasi half-sample interval
 //                hs, C   (H, width1, Dp) int16, d fastest, Dp = 64*NP (padded d-lanes are zero in C)
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "b2s_internal.h"
 
 namespace {
@@ -238,7 +242,9 @@ __global__ void __launch_bounds__(256) census_cost_kernel(const unsigned long lo
 
 // C[y] = sum_{k=-SH2..SH2} hs[clamp(y+k, 0, H-1)]; thread = 8 consecutive int16 (uint4), band of rows per blockIdx.y
 constexpr int VBAND = 32;
-__global__ void vsum_kernel(const uint4 *__restrict__ hs, uint4 *__restrict__ C, int H, size_t row_vec, int SH2)
+// ovf (word 1 of the handle's error flags) is set when a block sum wrapped past 32767 (C < 0: bit 15 of a packed half): the packed
+// unsigned arithmetic of the aggregation kernels (saturating sums, phase bit of the hand-over rings) needs C >= 0.
+__global__ void vsum_kernel(const uint4 *__restrict__ hs, uint4 *__restrict__ C, int H, size_t row_vec, int SH2, int *ovf)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= row_vec) return;
@@ -248,13 +254,16 @@ __global__ void vsum_kernel(const uint4 *__restrict__ hs, uint4 *__restrict__ C,
         uint4 v = hs[(size_t)clampi(y0 + k, 0, H - 1) * row_vec + i];
         s.x = __vadd2(s.x, v.x); s.y = __vadd2(s.y, v.y); s.z = __vadd2(s.z, v.z); s.w = __vadd2(s.w, v.w);
     }
+    uint32_t bad = 0;
     for (int y = y0; y < y1; y++) {
         C[(size_t)y * row_vec + i] = s;
+        bad |= s.x | s.y | s.z | s.w;
         uint4 a = hs[(size_t)clampi(y + 1 + SH2, 0, H - 1) * row_vec + i];
         uint4 b = hs[(size_t)clampi(y - SH2, 0, H - 1) * row_vec + i];
         s.x = __vsub2(__vadd2(s.x, a.x), b.x); s.y = __vsub2(__vadd2(s.y, a.y), b.y);
         s.z = __vsub2(__vadd2(s.z, a.z), b.z); s.w = __vsub2(__vadd2(s.w, a.w), b.w);
     }
+    if (bad & 0x80008000u) *ovf = 1;
 }
 
 } // namespace
@@ -294,8 +303,19 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
     int16_t *hs = fuse_vsum ? c->S2.as<int16_t>() : c->S.as<int16_t>();
     c->hs_pending = fuse_vsum;
     auto launch = [&](auto kern) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        // the attribute is set once per kernel and device (all instantiations share this lambda's type, hence the set keyed by the
+        // kernel's address), to a size that covers every geometry the launcher accepts
+        static std::mutex mu;
+        static std::set<std::pair<const void *, int>> done;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if (!done.count({(const void *)kern, c->device})) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+                if (e != cudaSuccess) return e;
+                done.insert({(const void *)kern, c->device});
+            }
+        }
+        if (smem > 160 * 1024) return cudaErrorInvalidValue;
         kern<<<cg, COST_THREADS, smem, c->stream>>>(PL, PR, hs, g);
         return cudaSuccess;
     };
@@ -312,7 +332,9 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
     if (fuse_vsum) return cudaGetLastError();
     size_t row_vec = (size_t)g.width1 * g.Dp / 8;
     dim3 vg((unsigned)((row_vec + 255) / 256), (g.H + VBAND - 1) / VBAND);
-    vsum_kernel<<<vg, 256, 0, c->stream>>>((const uint4 *)hs, c->C.as<uint4>(), g.H, row_vec, g.SH2);
+    cudaError_t ee = agg_error_flags(c);
+    if (ee != cudaSuccess) return ee;
+    vsum_kernel<<<vg, 256, 0, c->stream>>>((const uint4 *)hs, c->C.as<uint4>(), g.H, row_vec, g.SH2, c->agg_err + 1);
     c->launches++;
     if (g.mode == 3 && g.SH2 > 0 && g.H > 1) {
         // MODE_HH4 of cv2 leaves the cost of the rows whose window reaches below the image (y > 0, y + SH2 >= H) constant:

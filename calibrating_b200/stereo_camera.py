@@ -11,6 +11,7 @@ from the reference's own yaml/dict schema via `Stereo.load`, or from (cam1, cam2
 """
 import copy as _copy
 import ctypes
+import weakref
 
 import cv2
 import numpy as np
@@ -296,7 +297,9 @@ class Stereo:
         rp.max_depth = float(self.get_max_depth())
         rp.min_disparity = int(self.min_disparity) if getattr(self, "translation_rectify_img", None) else 0
         rp.interp = {"lanczos4": 0, "linear": 1}[self.interp]
-        (handle or self.handle).call("b2s_set_rig_params", ctypes.byref(rp))
+        h = handle or self.handle
+        h.call("b2s_set_rig_params", ctypes.byref(rp))
+        h._rig_owner = weakref.ref(self)
         if handle is None:
             self._rig_dirty = False
 
@@ -309,11 +312,14 @@ class Stereo:
                                      (ctypes.c_double * 12)(*k))
 
     def _push_rig(self, handle=None):
-        """Upload the per-rig constants to the engine (once per rig and handle)."""
+        """Upload the per-rig constants to the engine (once per rig and handle).  A handle holds ONE rig: when several
+        Stereo objects share a matcher (and with it the engine handle), as example/test_different_stereo.py does, each of
+        them re-uploads its rig whenever another one was the last to do so."""
         if handle is None:
-            if not self._rig_dirty:
+            owner = getattr(self.handle, "_rig_owner", None)
+            if not self._rig_dirty and owner is not None and owner() is self:
                 return
-            self._batch = None  # (the handles of get_depth_batch carry the old rig)
+            self._drop_batch()  # (the handles of get_depth_batch carry the old rig)
         if self.maps == "device":
             return self._push_rig_params(handle)
         h = handle or self.handle
@@ -338,9 +344,23 @@ class Stereo:
         rig.min_disparity = int(self.min_disparity) if getattr(self, "translation_rectify_img", None) else 0
         rig.interp = {"lanczos4": 0, "linear": 1}[self.interp]
         h.call("b2s_set_rig", ctypes.byref(rig))
+        h._rig_owner = weakref.ref(self)
         self._push_cam1_model(handle)
         if handle is None:
             self._rig_dirty = False
+
+    def _drop_batch(self):
+        """Close the handles of get_depth_batch and give their pinned staging buffers back."""
+        for b in getattr(self, "_batch", None) or []:
+            try:
+                b["handle"].sync()
+            except Exception:
+                pass
+            for a in b["pin"].values():
+                _ffi.pinned_free(a)
+            b["pin"].clear()
+            b["handle"].close()
+        self._batch = None
 
     @staticmethod
     def _get_img(path_or_np):
@@ -468,7 +488,11 @@ class Stereo:
             if isinstance(plug, dict):
                 result.update(plug)
                 plug = plug["disparity"]
-            plug = np.ascontiguousarray(plug, np.float32)
+            plug = np.asarray(plug)
+            if plug.ndim != 2 or plug.shape != (h, w):
+                # (the reference would fail in `rectify_valid_mask1 * disparity`, stereo_camera.py:512)
+                raise ValueError("the stereo matching plugin returned a disparity of shape %s, expected %s" % (plug.shape, (h, w)))
+            plug = np.ascontiguousarray(plug, np.float32)  # (the engine computes on float32 disparities, like cv2's)
             self.handle.call("b2s_depth_from_disparity", _ffi.ptr(plug), _ffi.ptr(img1), cn, int(want), ctypes.byref(out))
         result.update(rectify_img1=rectify_img1, rectify_depth=rectify_depth, disparity=disparity, rectify_img2=rectify_img2)
         if want:
@@ -495,6 +519,7 @@ class Stereo:
         self._push_rig()
         batch = getattr(self, "_batch", None)
         if batch is None or len(batch) != streams:
+            self._drop_batch()
             from .stereo_matching import StereoSGBM
             batch = []
             for _ in range(int(streams)):

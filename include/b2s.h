@@ -199,6 +199,9 @@ int b2s_undistort_img(b2s_handle h, const uint8_t *img1, int cn, uint8_t *out);
 #define B2S_OPT_FUSE_WTA 2
 #define B2S_OPT_AGG_SCHEDULE 3
 int b2s_set_option(b2s_handle h, int option, int value);
+/* sha256 (first 16 hex digits) over the CUDA sources this library was built from (calibrating_b200/build.py); ties a
+ * profile under profiles/ to the binary it was measured on. */
+const char *b2s_build_hash(void);
 int b2s_volume_dims(b2s_handle h, int *H, int *width1, int *D, int *Dp);
 int b2s_debug_fetch(b2s_handle h, int which, void *dst, size_t bytes);
 int b2s_timings(b2s_handle h, b2s_timing *t);      /* CUDA-event stage times of the last synchronous call */

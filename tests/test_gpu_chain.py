@@ -126,18 +126,23 @@ def test_device_side_map_generation(size, golden):
     exp.update(zip(["unrect_mapx", "unrect_mapy"], dev._unrectify_maps()))
     for name, e in exp.items():
         got = dev.handle.fetch_rig(name, e.shape, np.float32)
-        same = (got == e).mean()
-        assert same >= 0.9999 and np.abs(got - e).max() <= 2e-4, (name, same)  # (100 % on these rigs; cv2's SIMD path may differ by an ulp)
+        # cv2's AVX path contracts some multiply-adds: at 1080p ONE pixel of map1x (row 974, column 1309 of the synthetic rig)
+        # lands on the other side of a float32 rounding boundary (1314.9327 vs 1314.9329, 1 ulp); everything else is identical
+        diff = np.argwhere(got != e)
+        ulp = np.abs(got.view(np.int32).astype(np.int64) - e.view(np.int32).astype(np.int64))
+        assert len(diff) <= 2 and ulp.max() <= 1, "%s: %d pixels differ from cv2.initUndistortRectifyMap, first %s, max %d ulp" % (
+            name, len(diff), diff[:3].tolist(), ulp.max())
+        if size == (320, 240):
+            assert len(diff) == 0, name
     und_xy, und_fxy = cv2.initUndistortRectifyMap(dev.cam1.K, dev.cam1.D, None, dev.cam1.K, (w1, h1), cv2.CV_16SC2)
-    assert (dev.handle.fetch_rig("undist_xy", (h1, w1, 2), np.int16) == und_xy).mean() >= 0.9999
-    assert (dev.handle.fetch_rig("undist_fxy", (h1, w1), np.uint16) == und_fxy).mean() >= 0.9999
+    assert np.array_equal(dev.handle.fetch_rig("undist_xy", (h1, w1, 2), np.int16), und_xy)
+    assert np.array_equal(dev.handle.fetch_rig("undist_fxy", (h1, w1), np.uint16), und_fxy)
     assert np.array_equal(dev.handle.fetch_rig("valid_mask1", (h, w), np.uint8).astype(bool), dev.rectify_valid_mask1)
-    for k in a:
-        if a[k].dtype == np.uint8:
-            assert (a[k] == b[k]).mean() >= 0.9999, k
+    for k in a:  # identical maps, identical kernels: identical results
+        if a[k].dtype == np.uint8 or "depth" not in k:
+            assert np.array_equal(a[k], b[k]), k
         else:
-            assert _close_depth(np.float64(b[k]), np.float64(a[k]), 1e-3).mean() >= 0.9999 if "depth" in k else \
-                (a[k] == b[k]).mean() >= 0.999, k
+            assert _close_depth(np.float64(b[k]), np.float64(a[k]), 1e-12).all(), k
 
 
 def test_distort_depth(golden_dir):
@@ -224,3 +229,42 @@ def test_project_cam2_depth(golden_dir):
             assert same > 0.99999, (interp, same)
             both = (got != 0) & (exp != 0)
             assert np.allclose(got[both], exp[both], rtol=1e-9, atol=0) or (np.abs(got[both] - exp[both]) <= 1e-9 * exp[both]).mean() > 0.9999
+
+
+def test_two_rigs_share_one_matcher():
+    """example/test_different_stereo.py and example/test_rotate_stereo.py of the reference hang ONE SemiGlobalBlockMatching on
+    two Stereo objects.  The engine handle (and the rig uploaded into it) is shared with the matcher, so every Stereo must
+    re-upload its rig when the other one used the handle in between."""
+    rig_a, rig_b = synth.rig_dict((320, 240)), synth.rig_dict((256, 192))
+    sm = cb.SemiGlobalBlockMatching({"max_size": 4000, "num_disparities": 64})
+    A = cb.Stereo.load(rig_a).set_stereo_matching(sm, max_depth=3.5)
+    B = cb.Stereo.load(rig_b).set_stereo_matching(sm, max_depth=2.5)
+    assert A.handle is B.handle
+    ia, ib = synth.render_rig(rig_a, seed=1), synth.render_rig(rig_b, seed=2)
+    a1 = A.get_depth(*ia)
+    b1 = B.get_depth(*ib)
+    a2 = A.get_depth(*ia)  # B's rig is in the handle now: A has to notice
+    b2 = B.get_depth(*ib)
+    for k in a1:
+        assert np.array_equal(a1[k], a2[k]), k
+        assert np.array_equal(b1[k], b2[k]), k
+    alone = cb.Stereo.load(rig_a).set_stereo_matching(cb.SemiGlobalBlockMatching({"max_size": 4000, "num_disparities": 64}), max_depth=3.5)
+    ref = alone.get_depth(*ia)
+    for k in a1:
+        assert np.array_equal(a1[k], ref[k]), k
+    r1, r2 = A.rectify(*ia)  # the stage methods follow the same rule
+    B.rectify(*ib)
+    assert np.array_equal(A.undistort_img(ia[0]), ref["undistort_img1"])
+    assert np.array_equal(r1, ref["rectify_img1"])
+
+
+def test_plugin_disparity_shape_is_checked():
+    rig = synth.rig_dict((320, 240))
+
+    class Half(cb.MetaStereoMatching):
+        def __call__(self, a, b):
+            return np.zeros((a.shape[0] // 2, a.shape[1] // 2), np.float32)
+
+    st = cb.Stereo.load(rig).set_stereo_matching(Half(), max_depth=3.5)
+    with pytest.raises(ValueError, match="shape"):
+        st.get_depth(*synth.render_rig(rig, seed=0))

@@ -338,3 +338,23 @@ def test_degenerate_shapes(handle, shape, mode):
         assert np.array_equal(handle.fetch_volume(0), ref["C"]), (D, bs, "C")
         assert np.array_equal(handle.fetch_volume(1), ref["S"]), (D, bs, "S")
         assert np.array_equal(got, ref["disp"]), (D, bs)
+
+
+@pytest.mark.parametrize("schedule", ["sweep", "legacy"])
+def test_cost_domain_is_checked(handle, schedule, monkeypatch):
+    """The packed unsigned arithmetic of the aggregation needs C >= 0.  A block sum wraps past 32767 only with large windows on
+    adversarial input (block 11 x 3 channels: at most 121 * 279 = 33759): the cost stage flags it on the device and the call
+    fails instead of returning a silently different result.  The reference's block 11 on an adversarial RGB pair (inverted
+    binary noise) stays inside the domain and is exact."""
+    monkeypatch.setenv("B2S_AGG_SCHEDULE", schedule)
+    rng = np.random.default_rng(5)
+    l = rng.integers(0, 2, (40, 260, 3), dtype=np.uint8) * 255
+    r = 255 - l
+    bad = dict(min_disparity=0, num_disparities=64, block_size=21, P1=968, P2=3872, mode=1)
+    assert osgbm.sgbm_compute(l, r, want_volumes=True, **bad)["C"].min() < 0, "the test input does not wrap C"
+    with pytest.raises(Exception, match="wrapped past 32767"):
+        cb.StereoSGBM(handle=handle, **bad).compute(l, r)
+    ok = dict(bad, block_size=11)
+    ref = osgbm.sgbm_compute(l, r, want_volumes=True, **ok)
+    assert ref["C"].min() >= 0
+    assert np.array_equal(cb.StereoSGBM(handle=handle, **ok).compute(l, r), ref["disp"])  # (the failed call cleared the sticky flag)

@@ -104,6 +104,18 @@ def main():
         res = st.get_depth(img1, img2, return_distort_depth=True)
     np.savez_compressed(os.path.join(HERE, "rig320_distort.npz"), unrectify_depth=res["unrectify_depth"],
                         distort_depth=res["distort_depth"])
+    # --- case E: Cam.project_cam2_depth (camera.py:298-309): a seeded depth image of cam2 (20 % holes) seen from cam1 through
+    # the rig's own T = [R | t], default interpolation 1.5 (pins oracle/reproject.py and b2s_project_depth)
+    rng = np.random.default_rng(7)
+    depth2 = rng.random((240, 320)) * 1.5 + 0.5
+    depth2[rng.random((240, 320)) < 0.2] = 0
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = np.float64(rig["R"]), np.float64(rig["t"]).ravel()
+    cam1, cam2 = calibrating.Cam.load(rig["cam1"]), calibrating.Cam.load(rig["cam2"])
+    with np.errstate(all="ignore"):
+        depth1 = cam1.project_cam2_depth(cam2, depth2, T=T)
+    np.savez_compressed(os.path.join(HERE, "rig320_project.npz"), depth2=depth2, T=T, depth1=depth1,
+                        rate=calibrating.utils._get_appropriate_interpolation_rate(cam1, cam2, 1.5))
     # --- case C: raw cv2.StereoSGBM outputs on a small rectified pair, MODE_SGBM / MODE_HH / MODE_HH4 (pins oracle/sgbm_ref.c)
     l, r, _ = synth.rectified_pair(96, 200, 48, seed=3)
     for mode, name in ((0, "sgbm"), (1, "hh"), (3, "hh4")):

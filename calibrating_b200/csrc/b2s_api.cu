@@ -93,7 +93,7 @@ int b2s_destroy(b2s_handle c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->left, &c->right, &c->planesL, &c->planesR, &c->C, &c->S, &c->S2, &c->raw, &c->disp16, &c->disp2key, &c->labels,
-                      &c->sizes, &c->med, &c->dispf, &c->agg_ho, &c->agg_errbuf, &c->map1x, &c->map1y, &c->map2x, &c->map2y, &c->vmask, &c->umapx, &c->umapy,
+                      &c->sizes, &c->med, &c->dispf, &c->sleft, &c->sright, &c->sdispf, &c->agg_ho, &c->agg_errbuf, &c->map1x, &c->map1y, &c->map2x, &c->map2y, &c->vmask, &c->umapx, &c->umapy,
                       &c->und_xy, &c->und_fxy, &c->img1, &c->img2, &c->rect1, &c->rect2, &c->und1, &c->dispfinal, &c->rdepth,
                       &c->udepth, &c->lanczos_tab, &c->stage_f32, &c->dkey, &c->ddepth, &c->pkey, &c->pin, &c->pout};
     for (DevBuf *b : bufs) b->release();
@@ -217,6 +217,43 @@ static int matcher_dev(b2s_ctx *c, const uint8_t *dl, const uint8_t *dr, int16_t
     return B2S_OK;
 }
 
+// SemiGlobalBlockMatching.__call__ (stereo_matching.py:60-70) on device data: with B2S_OPT_MAX_SIZE set and an image whose
+// longest side exceeds it, the pair is reduced by min(max_size / max(h, w), 1) (sides rounded half-to-even like Python's
+// round), matched at that size, and the float disparity comes back at full size times w / sw.  Sets the matcher geometry.
+// d_out16: device destination of the int16 disparity, or B2S_OWN16 = the handle's own buffer c->disp16 (resolved after make_geom,
+// which may reallocate it), or NULL = not wanted.
+#define B2S_OWN16 ((int16_t *)(uintptr_t)1)
+static int matcher_scaled_dev(b2s_ctx *c, const uint8_t *dl, const uint8_t *dr, int H, int W, int cn, int16_t *d_out16, float *d_outf, bool timed)
+{
+    int nh = H, nw = W;
+    const int longest = H > W ? H : W;
+    if (c->max_size > 0 && longest > c->max_size) {
+        const double ratio = (double)c->max_size / (double)longest;
+        nh = (int)nearbyint((double)H * ratio);
+        nw = (int)nearbyint((double)W * ratio);
+    }
+    if (nh == H && nw == W) {
+        int rc = make_geom(c, H, W, cn);
+        if (rc) return rc;
+        return matcher_dev(c, dl, dr, (d_out16 && d_out16 != B2S_OWN16) ? d_out16 : c->disp16.as<int16_t>(), d_outf, timed);
+    }
+    if (d_out16) return fail(c, B2S_EINVAL, "the int16 disparity is not defined when the matcher works on a down-scaled pair (max_size %d < %d): ask for the float disparity", c->max_size, longest);
+    if (!d_outf) return fail(c, B2S_EINVAL, "no output requested");
+    if (nh <= 0 || nw <= 0) return fail(c, B2S_ESIZE, "max_size %d leaves no image", c->max_size);
+    int rc = make_geom(c, nh, nw, cn);
+    if (rc) return rc;
+    const size_t ns = (size_t)nh * nw;
+    CK(c, c->sleft.ensure(ns * cn));
+    CK(c, c->sright.ensure(ns * cn));
+    CK(c, c->sdispf.ensure(ns * 4));
+    CK(c, launch_resize_u8(c, dl, H, W, cn, c->sleft.as<uint8_t>(), nh, nw));
+    CK(c, launch_resize_u8(c, dr, H, W, cn, c->sright.as<uint8_t>(), nh, nw));
+    if ((rc = matcher_dev(c, c->sleft.as<uint8_t>(), c->sright.as<uint8_t>(), c->disp16.as<int16_t>(), c->sdispf.as<float>(), timed))) return rc;
+    CK(c, launch_resize_f32(c, c->sdispf.as<float>(), nh, nw, d_outf, H, W, (float)W, (float)nw));
+    if (timed) cudaEventRecord(c->ev[5], c->stream); // (the up-scale belongs to the post stage)
+    return B2S_OK;
+}
+
 static void collect_timing(b2s_ctx *c, bool chain)
 {
     auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, c->ev[a], c->ev[b]); return t; };
@@ -234,16 +271,18 @@ static int compute_disparity_host(b2s_ctx *c, const uint8_t *left, const uint8_t
 {
     if (!c || !left || !right) return B2S_EINVAL;
     CK(c, cudaSetDevice(c->device));
-    int rc = make_geom(c, H, W, cn);
-    if (rc) return rc;
+    if (cn != 1 && cn != 3) return fail(c, B2S_EINVAL, "images must have 1 or 3 channels (got %d)", cn);
+    if (H <= 0 || W <= 0 || W > 65535) return fail(c, B2S_EINVAL, "bad image size %dx%d", W, H);
     size_t nb = (size_t)H * W * cn, npx = (size_t)H * W;
     CK(c, c->left.ensure(nb));
     CK(c, c->right.ensure(nb));
+    if (outf) CK(c, c->dispf.ensure(npx * 4));
     long long l0 = c->launches;
     cudaEventRecord(c->ev[0], c->stream);
     CK(c, cudaMemcpyAsync(c->left.p, left, nb, cudaMemcpyDefault, c->stream));
     CK(c, cudaMemcpyAsync(c->right.p, right, nb, cudaMemcpyDefault, c->stream));
-    rc = matcher_dev(c, c->left.as<uint8_t>(), c->right.as<uint8_t>(), c->disp16.as<int16_t>(), outf ? c->dispf.as<float>() : nullptr, true);
+    int rc = matcher_scaled_dev(c, c->left.as<uint8_t>(), c->right.as<uint8_t>(), H, W, cn, out16 ? B2S_OWN16 : nullptr,
+                                outf ? c->dispf.as<float>() : nullptr, true);
     if (rc) return rc;
     if (out16) CK(c, cudaMemcpyAsync(out16, c->disp16.p, npx * 2, cudaMemcpyDefault, c->stream));
     if (outf) CK(c, cudaMemcpyAsync(outf, c->dispf.p, npx * 4, cudaMemcpyDefault, c->stream));
@@ -270,10 +309,8 @@ int b2s_compute_disparity_dev(b2s_handle c, const uint8_t *dl, const uint8_t *dr
 {
     if (!c || !dl || !dr) return B2S_EINVAL;
     CK(c, cudaSetDevice(c->device));
-    int rc = make_geom(c, H, W, cn);
-    if (rc) return rc;
     long long l0 = c->launches;
-    rc = matcher_dev(c, dl, dr, d_out16 ? d_out16 : c->disp16.as<int16_t>(), d_outf, false);
+    int rc = matcher_scaled_dev(c, dl, dr, H, W, cn, d_out16, d_outf, false);
     c->timing.total_launches = (int)(c->launches - l0);
     return rc;
 }
@@ -430,12 +467,17 @@ static int get_depth_impl(b2s_ctx *c, const uint8_t *img1, const uint8_t *img2, 
     if (!c || !img1 || !img2 || !o) return B2S_EINVAL;
     if (!c->have_rig) return fail(c, B2S_ESTATE, "b2s_set_rig has not been called");
     CK(c, cudaSetDevice(c->device));
-    int rc = make_geom(c, c->rH, c->rW, cn);
-    if (rc) return rc;
+    int rc;
+    if (cn != 1 && cn != 3) return fail(c, B2S_EINVAL, "images must have 1 or 3 channels (got %d)", cn);
+    const bool scaled = c->max_size > 0 && (c->rH > c->rW ? c->rH : c->rW) > c->max_size;
+    if (scaled && o->disp16) return fail(c, B2S_EINVAL, "the int16 disparity is not defined when the matcher works on a down-scaled pair (max_size)");
+    CK(c, c->dispf.ensure((size_t)c->rW * c->rH * 4));
     long long l0 = c->launches;
     cudaEventRecord(c->ev[0], c->stream);
     if ((rc = rectify_dev(c, img1, img2, cn))) return rc;
-    if ((rc = matcher_dev(c, c->rect1.as<uint8_t>(), c->rect2.as<uint8_t>(), c->disp16.as<int16_t>(), c->dispf.as<float>(), true))) return rc;
+    if ((rc = matcher_scaled_dev(c, c->rect1.as<uint8_t>(), c->rect2.as<uint8_t>(), c->rH, c->rW, cn, scaled ? nullptr : B2S_OWN16,
+                                 c->dispf.as<float>(), true)))
+        return rc;
     if ((rc = depth_tail(c, c->dispf.as<float>(), 1, c->img1.as<uint8_t>(), cn, want_unrectify, o))) return rc;
     size_t n = (size_t)c->rW * c->rH;
     if (o->rectify_img1) CK(c, cudaMemcpyAsync(o->rectify_img1, c->rect1.p, n * cn, cudaMemcpyDefault, c->stream));
@@ -596,6 +638,10 @@ int b2s_set_option(b2s_handle c, int option, int value)
     switch (option) {
     case B2S_OPT_KEEP_VOLUMES: c->keep_volumes = value != 0; return B2S_OK;
     case B2S_OPT_FUSE_WTA: c->fuse_wta = value != 0; return B2S_OK;
+    case B2S_OPT_MAX_SIZE:
+        if (value < 0) return fail(c, B2S_EINVAL, "B2S_OPT_MAX_SIZE: >= 0 (0 = no limit), got %d", value);
+        c->max_size = value;
+        return B2S_OK;
     case B2S_OPT_AGG_SCHEDULE:
         if (value != 0 && value != 1) return fail(c, B2S_EINVAL, "B2S_OPT_AGG_SCHEDULE: 0 (scans + sweep) or 1 (wavefront), got %d", value);
         c->agg_schedule = value;

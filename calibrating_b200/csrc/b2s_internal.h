@@ -62,6 +62,7 @@ struct b2s_ctx {
     bool have_volume = false;
     bool keep_volumes = false; // b2s_set_option(B2S_OPT_KEEP_VOLUMES): a fused last pass also stores S
     bool fuse_wta = true;      // b2s_set_option(B2S_OPT_FUSE_WTA): on by default
+    int max_size = 0;          // b2s_set_option(B2S_OPT_MAX_SIZE): longest image side the matcher works on (0 = no limit), stereo_matching.py:26,61
     int agg_schedule = 0;      // b2s_set_option(B2S_OPT_AGG_SCHEDULE): 0 = scans + lock-step sweep (sgbm_agg.cu), 1 = wavefront sweeps (sgbm_wave.cu)
     bool agg_legacy = false;   // launch_aggregate: per-direction scan kernels (strips too wide, or B2S_AGG_LEGACY)
     bool hs_pending = false;   // launch_cost_volume stopped at the row sums (in S2): the first horizontal scan forms C (agg_fuses_vsum)
@@ -78,6 +79,7 @@ struct b2s_ctx {
     DevBuf labels, sizes;     // (H,W) int32 each (speckle filter)
     DevBuf med;               // (H,W) int16 (median output before speckle)
     DevBuf dispf;             // (H,W) f32
+    DevBuf sleft, sright, sdispf; // the down-scaled pair and its disparity (B2S_OPT_MAX_SIZE)
     DevBuf agg_ho;            // hand-over rings of the fused vertical sweep + its error flag (sgbm_agg.cu)
     DevBuf agg_errbuf;        // the aggregation kernels' device error flag
     int *agg_err = nullptr;   // device address of that flag (valid after an aggregation was enqueued)
@@ -129,5 +131,8 @@ cudaError_t launch_project_depth(b2s_ctx *c, const double *d_depth2, int W2, int
                                  const double *K1, int W1, int H1, unsigned long long *d_key, double *d_out);
 cudaError_t launch_gen_maps(b2s_ctx *c, const b2s_map_params &p, float *mapx, float *mapy, uint8_t *mask, int mW, int mH, int16_t *xy16,
                             uint16_t *fxy16);
+// resize.cu
+cudaError_t launch_resize_u8(b2s_ctx *c, const uint8_t *src, int sH, int sW, int cn, uint8_t *dst, int dH, int dW);
+cudaError_t launch_resize_f32(b2s_ctx *c, const float *src, int sH, int sW, float *dst, int dH, int dW, float mul, float div);
 cudaError_t launch_depth_bare(b2s_ctx *c, const float *d_disp, double *d_depth);
 cudaError_t launch_unrectify(b2s_ctx *c, const double *d_depth, double *d_out);

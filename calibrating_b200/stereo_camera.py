@@ -450,7 +450,7 @@ class Stereo:
         return self
 
     def get_depth(self, img1, img2, return_unrectify_depth=True, return_distort_depth=False):
-        """stereo_camera.py:492-533.  With the built-in `SemiGlobalBlockMatching` at full resolution the whole chain runs
+        """stereo_camera.py:492-533.  With the built-in `SemiGlobalBlockMatching` (any `max_size`) the whole chain runs
         in one C-ABI call (one upload, one stream of kernels, one download); with a foreign `MetaStereoMatching` plugin
         the rectify half and the depth half run on the device around the plugin's host call."""
         assert hasattr(self, "stereo_matching"), "Please stereo.set_stereo_matching(stereo_matching)"
@@ -463,7 +463,7 @@ class Stereo:
         w1, h1 = self.cam1.xy
         want = bool(return_unrectify_depth or return_distort_depth)
         sm = self.stereo_matching
-        fused = (isinstance(sm, SemiGlobalBlockMatching) and sm.stereo_sgbm.handle is self.handle and sm.max_size >= max(h, w))
+        fused = isinstance(sm, SemiGlobalBlockMatching) and sm.stereo_sgbm.handle is self.handle
         self._push_rig()
         ishape = (h, w) if img1.ndim == 2 else (h, w, cn)
         result = {}
@@ -481,7 +481,11 @@ class Stereo:
         if fused:
             rectify_img1, rectify_img2 = np.empty(ishape, np.uint8), np.empty(ishape, np.uint8)
             out.rectify_img1, out.rectify_img2 = rectify_img1.ctypes.data, rectify_img2.ctypes.data
-            self.handle.call("b2s_get_depth", _ffi.ptr(img1), _ffi.ptr(img2), cn, int(want), ctypes.byref(out))
+            self.handle.call("b2s_set_option", 4, sm._max_size_option())  # the matcher's max_size (stereo_matching.py:26,61)
+            try:
+                self.handle.call("b2s_get_depth", _ffi.ptr(img1), _ffi.ptr(img2), cn, int(want), ctypes.byref(out))
+            finally:
+                self.handle.call("b2s_set_option", 4, 0)
         else:
             rectify_img1, rectify_img2 = self.rectify(img1, img2)
             plug = sm(rectify_img1, rectify_img2)
@@ -505,7 +509,7 @@ class Stereo:
     # ---- throughput: several pairs in flight (not in the reference) -------------------------------
     def get_depth_batch(self, pairs, streams=4, keys=("unrectify_depth",), out=None):
         """`get_depth` for a list of (img1, img2) with `streams` engine handles (= CUDA streams) in flight: upload, the ~20
-        kernels and the download of different pairs overlap.  Needs the built-in `SemiGlobalBlockMatching` at full resolution
+        kernels and the download of different pairs overlap.  Needs the built-in `SemiGlobalBlockMatching`
         (the one-call path of `get_depth`).  keys: which result arrays to return, any of rectify_img1, rectify_img2, disparity,
         rectify_depth, unrectify_depth, undistort_img1, distort_depth.  Returns a list of dicts.
         Host copies are avoided when the caller supplies pinned memory (`_ffi.pinned_empty`): pinned input images are
@@ -514,10 +518,13 @@ class Stereo:
         sm = self.stereo_matching
         w, h = self.xy
         w1, h1 = self.cam1.xy
-        if not (isinstance(sm, SemiGlobalBlockMatching) and sm.max_size >= max(h, w)):
-            raise ValueError("get_depth_batch needs the built-in SemiGlobalBlockMatching at full resolution (max_size >= image size)")
+        if not isinstance(sm, SemiGlobalBlockMatching):
+            raise ValueError("get_depth_batch needs the built-in SemiGlobalBlockMatching")
         self._push_rig()
         batch = getattr(self, "_batch", None)
+        if batch is not None and getattr(self, "_batch_max_size", None) != sm._max_size_option():
+            batch = None
+        self._batch_max_size = sm._max_size_option()
         if batch is None or len(batch) != streams:
             self._drop_batch()
             from .stereo_matching import StereoSGBM
@@ -525,6 +532,7 @@ class Stereo:
             for _ in range(int(streams)):
                 hd = _ffi.Handle(self.device)
                 StereoSGBM(handle=hd, **sm.stereo_sgbm.params)
+                hd.call("b2s_set_option", 4, sm._max_size_option())
                 self._push_rig(hd)
                 batch.append(dict(handle=hd, pin={}, pending=None))
             self._batch = batch

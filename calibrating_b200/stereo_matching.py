@@ -88,21 +88,6 @@ def StereoSGBM_create(minDisparity=0, numDisparities=16, blockSize=3, P1=0, P2=0
                       speckle_window_size=speckleWindowSize, speckle_range=speckleRange, mode=mode, cost=cost)
 
 
-def _resize(img, arg):
-    """Stand-in for boxx.resize (calibrating/stereo_matching.py:62,66).  boxx is not vendored and its interpolation is
-    unpinned; this uses cv2 bilinear.  Full-resolution matching (`max_size >= max(h, w)`, the
-    documented way to get it) never reaches this function."""
-    import cv2
-    h, w = img.shape[:2]
-    if isinstance(arg, (int, float)):
-        nh, nw = int(round(h * arg)), int(round(w * arg))
-    else:
-        nh, nw = arg
-    if (nh, nw) == (h, w):
-        return img
-    return cv2.resize(img, (nw, nh), interpolation=cv2.INTER_LINEAR)
-
-
 class SemiGlobalBlockMatching(MetaStereoMatching):
     """Drop-in for calibrating.SemiGlobalBlockMatching (calibrating/stereo_matching.py:22-70)."""
 
@@ -115,13 +100,21 @@ class SemiGlobalBlockMatching(MetaStereoMatching):
         params.update({k: cfg[k] for k in REFERENCE_DEFAULTS if k in cfg})
         self.stereo_sgbm = StereoSGBM(device=device, handle=handle, **params)
 
+    def _max_size_option(self):
+        """`max_size` as the engine takes it (B2S_OPT_MAX_SIZE; 0 = no limit)."""
+        return int(min(max(self.max_size, 1), 2 ** 31 - 1))
+
     def __call__(self, img1, img2):
-        resize_ratio = min(self.max_size / max(img1.shape[:2]), 1)
-        if resize_ratio == 1:
+        """stereo_matching.py:60-70 in ONE C-ABI call: the down-scale to `max_size` (the reference's default is 1000), the
+        matcher, `/16`, `clip(0)`, the `< minD * 16` zeroing, the up-scale and the `* w / sw` all run on the device.  The two
+        `boxx.resize` calls of the reference are an un-vendored, unpinned dependency; the engine follows
+        cv2.resize(INTER_LINEAR) (uint8 bit-exact; see oracle/resize.py)."""
+        h = self.stereo_sgbm.handle
+        h.call("b2s_set_option", 4, self._max_size_option())
+        try:
             return self.stereo_sgbm.compute_float(img1, img2)
-        simg1, simg2 = _resize(img1, resize_ratio), _resize(img2, resize_ratio)
-        sdisparity = self.stereo_sgbm.compute_float(simg1, simg2)
-        return _resize(sdisparity, img1.shape[:2]) * img1.shape[1] / simg1.shape[1]
+        finally:
+            h.call("b2s_set_option", 4, 0)  # (the cv2-style StereoSGBM object sharing this handle never scales)
 
 
     def compute_batch(self, pairs, streams=2):

@@ -191,6 +191,10 @@ int b2s_undistort_img(b2s_handle h, const uint8_t *img1, int cn, uint8_t *out);
  * B2S_OPT_FUSE_WTA (default 1): the winner-take-all step runs inside the last aggregation pass; the aggregated volume S is
  *   then never written unless B2S_OPT_KEEP_VOLUMES (default 0) is also set (B2S_FETCH_S fails otherwise).  With 0 the pass
  *   stores S and a separate kernel picks the winners.  Results are identical either way.
+ * B2S_OPT_MAX_SIZE (default 0 = off): `max_size` of SemiGlobalBlockMatching (calibrating/stereo_matching.py:26,60-70; the reference's
+ *   default is 1000).  When the longest image side exceeds it, b2s_compute_disparity* / b2s_get_depth* reduce the pair by
+ *   min(max_size / max(h, w), 1) on the device (cv2.resize INTER_LINEAR semantics, bit-exact for uint8), match at that size and
+ *   return the float disparity at full size times w / sw; the int16 disparity is not defined then and must not be requested.
  * B2S_OPT_AGG_SCHEDULE (default 0): how the eight paths of MODE_HH are scheduled.  0 = two horizontal scans around a
  *   lock-step vertical sweep (20 bytes of DRAM traffic per cost voxel; the fastest for one pair); 1 = two wavefront sweeps of four
  *   paths each in OpenCV's own order (the canonical 8 bytes per voxel; sgbm_wave.cu).  Results are identical; other modes
@@ -198,6 +202,7 @@ int b2s_undistort_img(b2s_handle h, const uint8_t *img1, int cn, uint8_t *out);
 #define B2S_OPT_KEEP_VOLUMES 1
 #define B2S_OPT_FUSE_WTA 2
 #define B2S_OPT_AGG_SCHEDULE 3
+#define B2S_OPT_MAX_SIZE 4
 int b2s_set_option(b2s_handle h, int option, int value);
 /* sha256 (first 16 hex digits) over the CUDA sources this library was built from (calibrating_b200/build.py); ties a
  * profile under profiles/ to the binary it was measured on. */

@@ -37,11 +37,16 @@ class SgbmPlugin:
         self.max_size = max_size
         self.sgbm = cv2.StereoSGBM_create(**p)
 
-    def __call__(self, img1, img2):
-        assert min(self.max_size / max(img1.shape[:2]), 1) == 1, "boxx.resize path is unpinned offline"
-        d = self.sgbm.compute(img1, img2).astype(np.float32).clip(0)
+    def _compute_float(self, a, b):
+        d = self.sgbm.compute(a, b).astype(np.float32).clip(0)
         d[d < self.sgbm.getMinDisparity() * 16] = 0
-        return d / 16.0 * img1.shape[1] / img1.shape[1]
+        return d / 16.0
+
+    def __call__(self, img1, img2):
+        """stereo_matching.py:60-70; the two boxx.resize calls (un-vendored, unpinned) are stood in for by oracle/resize.py
+        (= cv2.resize INTER_LINEAR)."""
+        from . import resize
+        return resize.scaled_matcher(self._compute_float, img1, img2, self.max_size)
 
 
 class RefStereo:

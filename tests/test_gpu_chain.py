@@ -268,3 +268,50 @@ def test_plugin_disparity_shape_is_checked():
     st = cb.Stereo.load(rig).set_stereo_matching(Half(), max_depth=3.5)
     with pytest.raises(ValueError, match="shape"):
         st.get_depth(*synth.render_rig(rig, seed=0))
+
+
+def test_default_max_size_runs_on_the_device():
+    """`calibrating.SemiGlobalBlockMatching()` keeps the reference's default max_size = 1000 (stereo_matching.py:26,60-70): on a
+    1080p pair the matcher works at 1000 x 562.  Down-scale, matcher and up-scale x w/sw are one C-ABI call; against the
+    restatement (oracle/resize.py = cv2.resize INTER_LINEAR for the unpinned boxx.resize; cv2.StereoSGBM live) the float
+    disparity is identical, and against cv2.resize's own float up-scale it is within 1e-6 of the range."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import chain, resize
+    l, r, _ = synth.rectified_pair(1080, 1920, 200, seed=5)
+    sm = cb.SemiGlobalBlockMatching()
+    assert sm.max_size == 1000
+    n0 = sm.stereo_sgbm.handle.launch_count()
+    got = sm(l, r)
+    assert got.shape == (1080, 1920) and got.dtype == np.float32
+    assert sm.stereo_sgbm.handle.launch_count() - n0 >= 12, "the resize kernels and the matcher run on the device"
+    ref = chain.SgbmPlugin()  # reference defaults, max_size 1000
+    exp = ref(l, r)
+    assert np.array_equal(got, exp)
+    sl, sr = (cv2.resize(a, (1000, 562), interpolation=cv2.INTER_LINEAR) for a in (l, r))
+    via_cv2 = cv2.resize(ref._compute_float(sl, sr), (1920, 1080), interpolation=cv2.INTER_LINEAR) * np.float32(1920) / np.float32(1000)
+    assert np.abs(got - via_cv2).max() <= 1e-6 * 1920 * 220 / 1000
+    with pytest.raises(Exception, match="int16 disparity is not defined"):
+        sm.stereo_sgbm.handle.call("b2s_set_option", 4, 1000)
+        try:
+            sm.stereo_sgbm.compute(l, r)
+        finally:
+            sm.stereo_sgbm.handle.call("b2s_set_option", 4, 0)
+    assert np.array_equal(sm.stereo_sgbm.compute(l, r).shape, (1080, 1920))  # the cv2-style object never scales
+
+
+def test_get_depth_with_default_matcher_is_one_call():
+    """Stereo.get_depth with the reference's default matcher (max_size 1000) on a 1280 x 720 rig: one b2s_get_depth call, results
+    equal to the cv2 restatement of the reference chain."""
+    pytest.importorskip("cv2")
+    from oracle import chain
+    rig = synth.rig_dict((1280, 720))
+    img1, img2 = synth.render_rig(rig, seed=4)
+    st = cb.Stereo.load(rig).set_stereo_matching(cb.SemiGlobalBlockMatching(), max_depth=3.5)
+    res = st.get_depth(img1, img2)
+    exp = chain.RefStereo(rig).set_stereo_matching(chain.SgbmPlugin(), max_depth=3.5).get_depth(img1, img2)
+    assert np.array_equal(res["rectify_img1"], exp["rectify_img1"])
+    assert np.array_equal(res["disparity"], exp["disparity"])
+    assert np.array_equal(res["rectify_depth"], exp["rectify_depth"])
+    assert _close_depth(res["unrectify_depth"], exp["unrectify_depth"], 1e-9).all()
+    got = st.get_depth_batch([(img1, img2)] * 2, streams=2, keys=("disparity",))
+    assert np.array_equal(got[1]["disparity"], exp["disparity"])

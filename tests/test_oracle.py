@@ -117,3 +117,22 @@ def test_undistort_oracle_vs_cv2():
     D = np.array([[-0.10, 0.03, 8e-4, -5e-4, 0.0]])
     m1, m2 = cv2.initUndistortRectifyMap(K, D, None, K, (W, H), cv2.CV_16SC2)
     assert np.array_equal(oremap.remap_linear_u8_fixed(src, m1[..., 0], m1[..., 1], m2), cv2.undistort(src, K, D))
+
+
+@pytest.mark.parametrize("hw", [(1080, 1920), (720, 1280), (1200, 1600), (1081, 1923), (333, 2001)])
+def test_resize_restatement_vs_cv2(hw):
+    """oracle/resize.py (the stand-in for the reference's unpinned boxx.resize calls, stereo_matching.py:61-69) against
+    cv2.resize(INTER_LINEAR): uint8 down-scale bit-exact, float32 up-scale within 1e-6 of the value range (cv2's IPP path
+    keeps float64 coefficients; its accumulation order is not public)."""
+    from oracle import resize
+    rng = np.random.default_rng(1)
+    h, w = hw
+    nh, nw = resize.scaled_size(h, w, 1000)
+    assert max(nh, nw) == 1000
+    for cn in (1, 3):
+        img = rng.integers(0, 256, (h, w, cn), dtype=np.uint8).squeeze()
+        assert np.array_equal(resize.resize_u8(img, nh, nw), cv2.resize(img, (nw, nh), interpolation=cv2.INTER_LINEAR))
+    d = (rng.random((nh, nw)) * 200).astype(np.float32)
+    d[rng.random((nh, nw)) < 0.2] = 0
+    assert np.abs(resize.resize_f32(d, h, w) - cv2.resize(d, (w, h), interpolation=cv2.INTER_LINEAR)).max() <= 200 * 1e-6
+    assert resize.scaled_size(480, 640, 1000) == (480, 640)

@@ -222,14 +222,36 @@ def main():
         a[...] = l; b[...] = r
         hp.append((a, b))
     hout = [_ffi.pinned_empty((H, W), np.float32) for _ in range(P)]
+    if world > 1:
+        # BASELINE config 3: the results of a step stay on the device, are all-gathered over NVLink (every rank holds the batch in
+        # global pair order) and each rank reads its own shard back to pinned host memory -- all inside the timed region
+        loc = torch.empty((P, H, W), dtype=torch.float32, device="cuda")
+        gat = torch.empty((world * P, H, W), dtype=torch.float32, device="cuda")
+        hloc = torch.empty((P, H, W), dtype=torch.float32).pin_memory()
+        louts = [loc[i] for i in range(P)]
+        coll_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+        def step_e2e():
+            eng.compute_batch(hp, out=louts)          # H2D of the pinned inputs, kernels, result into `loc`; returns when the streams are idle
+            coll_ev[0].record()
+            dist.all_gather_into_tensor(gat, loc)     # THE all-gather of the step's disparities
+            coll_ev[1].record()
+            hloc.copy_(loc, non_blocking=True)        # D2H of this rank's shard
+            torch.cuda.synchronize()
+    else:
+        def step_e2e():
+            eng.compute_batch(hp, out=hout)
     for _ in range(Wm):
-        eng.compute_batch(hp, out=hout)
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        eng.compute_batch(hp, out=hout)
+        step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
+    if world > 1:
+        allgather_ms = coll_ev[0].elapsed_time(coll_ev[1])
+        assert torch.equal(gat[rank * P:(rank + 1) * P], loc)
     eng.matchers[0].compute(*pairs[0])  # one synchronous call for the per-stage CUDA-event times
     stage = eng.handles[0].timings()
 
@@ -240,55 +262,105 @@ def main():
         rig = synth.rig_dict((W, H))
         raw = [synth.render_rig(rig, seed=rank * 2 + i) for i in range(2)]
         cfg = dict(SGBM, max_size=1 << 20)
-        st = cb.Stereo.load(rig, device=local).set_stereo_matching(cb.SemiGlobalBlockMatching(cfg, device=local), max_depth=4.0)
         cpairs = []
-        for i in range(P):  # pinned host images and result buffers, as in the e2e leg above
+        for i in range(P):  # pinned host images, as in the e2e leg above
             a, b = _ffi.pinned_empty(raw[i % 2][0].shape, np.uint8), _ffi.pinned_empty(raw[i % 2][1].shape, np.uint8)
             a[...] = raw[i % 2][0]; b[...] = raw[i % 2][1]
             cpairs.append((a, b))
-        couts = [{"unrectify_depth": _ffi.pinned_empty((H, W), np.float64)} for _ in range(P)]
-        for _ in range(2):
-            st.get_depth_batch(cpairs, streams=S, out=couts)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(max(K // 2, 2)):
-            st.get_depth_batch(cpairs, streams=S, out=couts)
-        barrier()
-        chain_s = (time.perf_counter() - t0) / max(K // 2, 2)
-        chain = {"value": world * P / chain_s, "unit": "pairs/s",
-                 "what": "undistort+rectify (LANCZOS4) -> SGBM (same parameters) -> depth -> unrectify, host uint8 raw pairs -> host float64 "
-                         "unrectify_depth via Stereo.get_depth_batch; per-rank wall clock, not reduced over ranks",
-                 "h2d_bytes_per_step": P * 2 * H * W * CN, "d2h_bytes_per_step": P * H * W * 8}
+        nrep = max(K // 2, 2)
+        if world > 1:
+            # the product path of config 3: ShardedStereo = ONE rig broadcast from rank 0 (device to device over NVLink), then
+            # per step pairs i % world on S streams per rank and ONE all-gather of the float64 depth maps, all timed
+            from calibrating_b200 import sharded
+            st = None
+            if rank == 0:
+                st = cb.Stereo.load(rig, device=local).set_stereo_matching(cb.SemiGlobalBlockMatching(cfg, device=local), max_depth=4.0)
+            barrier()
+            tb = time.perf_counter()
+            sh = sharded.ShardedStereo(st, engine_factory=lambda: sharded.CudaEngine(local, streams=S))
+            barrier()
+            bcast_s = time.perf_counter() - tb
+            hres = torch.empty((P, H, W), dtype=torch.float64).pin_memory()
 
-    # ---- roofline: the aggregation kernels alone ---------------------------------------------------------------------
-    agg_parts = eng.handles[0].bench_aggregate_parts(10)   # one CUDA-event interval per launch of the group
-    agg_loop_ms = eng.handles[0].bench_aggregate(10)       # the group back to back, with the memsets and launch gaps between kernels
-    agg_ms = float(sum(agg_parts))                         # kernel time of the group: what the roofline is computed from
+            def chain_step():
+                g = sh.get_depth_batch(cpairs)                         # (world*P, H, W) float64 on the device, global pair order
+                hres.copy_(g[rank::world], non_blocking=True)          # this rank's shard back to the host
+                torch.cuda.synchronize()
+            for _ in range(2):
+                chain_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(nrep):
+                chain_step()
+            barrier()
+            chain_s = (time.perf_counter() - t0) / nrep
+            what = ("ShardedStereo.get_depth_batch: undistort+rectify (LANCZOS4) -> SGBM -> depth -> unrectify on %d streams per rank, all-gather of the "
+                    "float64 unrectify_depth of all ranks (%.0f MB per rank and step) inside the timed region, own shard read back to the host; "
+                    "max over ranks" % (S, P * H * W * 8 / 1e6))
+        else:
+            st = cb.Stereo.load(rig, device=local).set_stereo_matching(cb.SemiGlobalBlockMatching(cfg, device=local), max_depth=4.0)
+            couts = [{"unrectify_depth": _ffi.pinned_empty((H, W), np.float64)} for _ in range(P)]
+            for _ in range(2):
+                st.get_depth_batch(cpairs, streams=S, out=couts)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(nrep):
+                st.get_depth_batch(cpairs, streams=S, out=couts)
+            barrier()
+            chain_s = (time.perf_counter() - t0) / nrep
+            bcast_s = None
+            what = ("undistort+rectify (LANCZOS4) -> SGBM (same parameters) -> depth -> unrectify, host uint8 raw pairs -> host float64 "
+                    "unrectify_depth via Stereo.get_depth_batch")
+        chain = {"seconds_per_step": chain_s, "unit": "pairs/s", "what": what, "h2d_bytes_per_step": P * 2 * H * W * CN, "d2h_bytes_per_step": P * H * W * 8}
+        if bcast_s is not None:
+            chain["rig_broadcast_s_incl_setup"] = bcast_s
+            chain["rig_broadcast_bytes"] = sh.rig_bytes
+
+    # ---- roofline: the aggregation group (path aggregation + winner-take-all) alone ---------------------------------------
+    # production form: every repetition re-runs the cost stage first (untimed), so the first launch is the scan that also forms C
+    # from the cost stage's row sums (agg_hscan_vsum_kernel), as in a real pair
+    h0 = eng.handles[0]
+    h0.call("b2s_compute_disparity_dev", ptrs[0][0], ptrs[0][1], H, W, CN, optrs[0], None)
+    h0.sync()
+    agg_parts = h0.bench_aggregate_parts(10)   # one CUDA-event interval per launch of the group
+    agg_loop_ms = h0.bench_aggregate(10)       # one interval around the whole group (with the memsets and launch gaps between kernels)
+    agg_ms = float(sum(agg_parts))             # kernel time of the group: what the roofline is computed from
     n_launch = len(agg_parts)
+    # the other convention (round 1): the cost stage finishes C itself (vsum_kernel) and the first launch is the plain +x scan
+    os.environ["B2S_NO_VSUM_FUSION"] = "1"
+    try:
+        alt_parts = h0.bench_aggregate_parts(10)
+    finally:
+        del os.environ["B2S_NO_VSUM_FUSION"]
+    # several pairs in flight, as in the timed steps above: S handles run the group concurrently (on the finished C)
+    for h in eng.handles:
+        h.enqueue_aggregate(1)
+    for h in eng.handles:
+        h.sync()
+    for h in eng.handles:
+        h.event_record(2)
+    for _ in range(8):
+        for h in eng.handles:
+            h.enqueue_aggregate(1)
+    for h in eng.handles:
+        h.event_record(3)
+    agg_batched_ms = max(eng.handles[0].event_elapsed(2, h, 3) for h in eng.handles) / (8 * S)
+    for h in eng.handles:
+        h.sync()
 
     coll = None
     if world > 1:
-        # the two collectives of the sharded path (calibrating_b200/sharded.py), timed on the device, max over ranks:
-        # one broadcast of a 1080p rig block (maps + mask, ~100 MB) and one all-gather of a step's disparities
-        blk = torch.empty(2 * 4 * 4 * H * W + 2 * 4 * H * W + H * W * 7, dtype=torch.uint8, device="cuda")
-        gat = torch.empty((world * P, H, W), dtype=torch.int16, device="cuda")
-        loc = torch.stack(dout)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        for it in range(3):  # two warm-ups, the third is reported
-            barrier()
-            ev[0].record()
-            dist.broadcast(blk, src=0)
-            ev[1].record()
-            dist.all_gather_into_tensor(gat.view(torch.uint8), loc.view(torch.uint8))  # (NCCL via torch has no int16)
-            ev[2].record()
-            torch.cuda.synchronize()
-        coll = [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])]
-        assert torch.equal(gat[rank * P:(rank + 1) * P], loc)
-        t = torch.tensor([ms, e2e_s] + coll, dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, coll[0], coll[1] = t.tolist()
-        coll = {"rig_broadcast_ms": coll[0], "rig_broadcast_bytes": blk.numel(), "disparity_allgather_ms_per_step": coll[1],
-                "disparity_allgather_bytes_per_rank": loc.numel() * 2, "note": "outside the timed region: once per rig / once per batch"}
+        vals = [ms, e2e_s, allgather_ms, chain["seconds_per_step"] if chain else 0.0, chain.get("rig_broadcast_s_incl_setup", 0.0) if chain else 0.0]
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every multi-GPU number is the max over ranks
+        ms, e2e_s, allgather_ms, chain_max, bcast_max = t.tolist()
+        if chain:
+            chain["seconds_per_step"] = chain_max
+            chain["rig_broadcast_s_incl_setup"] = bcast_max
+        coll = {"disparity_allgather_ms_per_step": allgather_ms, "disparity_allgather_bytes_per_rank": P * H * W * 4,
+                "note": "inside the timed e2e region (last step, CUDA events, max over ranks); the rig broadcast happens once per rig (chain_e2e)"}
+    if chain:
+        chain["value"] = world * P / chain["seconds_per_step"]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -300,15 +372,28 @@ def main():
     except Exception:
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
-    traffic = None
+    # DRAM traffic of the group from the ncu capture under profiles/ -- only if it was taken on THIS build of the library
+    # (scripts/agg_traffic.py records b2s_build_hash() next to the numbers)
+    traffic, traffic_note = None, "no profiles/agg_traffic.json"
+    build_hash = _ffi.lib().b2s_build_hash().decode()
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "agg_traffic.json")))["dram_bytes_per_launch"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "agg_traffic.json")))
+        if tj.get("build_hash") == build_hash:
+            traffic, traffic_note = tj["dram_bytes_per_pair"] / n_launch, "ncu dram__bytes_read+write of the group / launches, %s, build %s" % (tj.get("source"), build_hash)
+        else:
+            traffic_note = "profiles/agg_traffic.json is from build %s, this library is %s: not reported" % (tj.get("build_hash"), build_hash)
     except Exception:
         pass
     achieved = AGG_BYTES_PER_PAIR / (agg_ms * 1e-3) / 1e9  # = (bytes per pair / launches) / (group time / launches)
-    names = ["agg_hscan_kernel<INIT> (+x)", "agg_vsweep_kernel (6 of 8 directions)", "agg_hscan_kernel<ACCUM2, WTA> (-x, folds S2, winner-take-all fused)"] if n_launch == 3 else \
-        ["agg_scan_kernel"] * n_launch
-    dirs = [1, 6, 1] if n_launch == 3 else [1] * n_launch
+    if n_launch == 3:
+        names = ["agg_hscan_vsum_kernel (+x, forms C from the cost stage's row sums)", "agg_vsweep_kernel (6 of 8 directions)",
+                 "agg_hscan_kernel<ACCUM2, WTA> (-x, folds S2, winner-take-all fused)"]
+        dirs = [1, 6, 1]
+    elif n_launch == 2:
+        names = ["agg_wave_kernel (both sweeps of four paths)", "wta_kernel (adds the two sums, winner-take-all)"]
+        dirs = [8, 0]
+    else:
+        names, dirs = ["agg_scan_kernel"] * n_launch, [1] * n_launch
     out = {
         "metric": "stereo pairs/sec @1080p/128-disp SGM", "value": world * K * P / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
         "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -317,15 +402,23 @@ def main():
                    "l2": "working set per pair (C, S, S2 volumes, 1.49 GB) exceeds the 126 MB L2; %d distinct pairs rotate" % P},
         "clocks": clocks, "gpu_launches": int(launches) * world,  # (rank 0's count x ranks: every rank runs the same schedule)
         "e2e": {"value": world * K * P / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": P * 2 * H * W * CN, "d2h_bytes_per_step": P * H * W * 4,
-                "api": "DisparityBatchEngine.compute_batch (host uint8 pairs -> host float32 disparity), wall clock between synchronisations"},
+                "api": "DisparityBatchEngine.compute_batch (host uint8 pairs -> host float32 disparity), wall clock between synchronisations"
+                       + ("; N > 1: results stay on the device, NCCL all-gather of every step's disparities, own shard read back to pinned host memory" if world > 1 else "")},
         "roofline": {"bound": "hbm", "kernel": "aggregation group: %d launches per pair (dominant: agg_vsweep_kernel)" % n_launch,
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note,
+                     "build_hash": build_hash,
+                     "first_launch_plain_scan": {"ms_per_launch": [round(t, 4) for t in alt_parts], "group_ms": round(float(sum(alt_parts)), 4),
+                                                 "frac": AGG_BYTES_PER_PAIR / (float(sum(alt_parts)) * 1e-3) / 1e9 / peak,
+                                                 "note": "round-1 convention: C finished by the cost stage (vsum_kernel), first launch = agg_hscan_kernel<INIT>"},
+                     "batched": {"handles_in_flight": S, "ms_per_pair": round(agg_batched_ms, 4), "achieved": AGG_BYTES_PER_PAIR / (agg_batched_ms * 1e-3) / 1e9,
+                                 "frac": AGG_BYTES_PER_PAIR / (agg_batched_ms * 1e-3) / 1e9 / peak,
+                                 "note": "the group of %d handles enqueued round-robin on their streams (on the finished C), wall = first start to last end" % S},
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy), of measured" if peaks else "fallback 6650 GB/s, of fallback",
                      "algorithmic_bytes_per_launch": AGG_BYTES_PER_PAIR // n_launch, "ms_per_launch": agg_ms / n_launch, "group_back_to_back_ms": agg_loop_ms,
                      "launches": [{"kernel": nm, "ms": round(t, 4), "algorithmic_bytes": AGG_BYTES_PER_PAIR * d // sum(dirs),
                                    "achieved_GBps": round(AGG_BYTES_PER_PAIR * d / sum(dirs) / (t * 1e-3) / 1e9, 1)}
                                   for nm, t, d in zip(names, agg_parts, dirs)],
-                     "timed": "alone, one CUDA-event interval per launch on the engine stream (the last launch includes the winner-take-all); canonical 8 B/voxel (SURVEY 8(d)), this schedule moves 20 B/voxel"},
+                     "timed": "alone in its production form (cost stage re-run untimed before every repetition), one CUDA-event interval per launch on the engine stream; the group includes the winner-take-all; canonical 8 B/voxel (SURVEY 8(d)), this schedule moves 20 B/voxel"},
         "stage_ms_last_pair": {k: round(v, 3) for k, v in stage.items() if k.endswith("_ms")},
     }
     if coll:
@@ -340,6 +433,28 @@ def main():
         t = sum(cpu_round(pairs, T) for _ in range(rounds))
         out["cpu_baseline"] = {"value": T * rounds / t, "unit": "pairs/s", "cores": T, "kind": "reference",
                                "sample": "%d rounds of %d threads x 1 pair (cv2 %s StereoSGBM MODE_HH, same pairs and parameters)" % (rounds, T, cv2.__version__)}
+        if chain:
+            # the reference's whole chain on the host (oracle/chain.py = calibrating's Stereo.get_depth restated with the same cv2 calls;
+            # the real package needs boxx, which is not installable): T threads x 1 raw pair each, one round
+            from oracle import chain as ochain
+            rig = synth.rig_dict((W, H))
+            raws = [synth.render_rig(rig, seed=i) for i in range(2)]
+            refs = [ochain.RefStereo(rig).set_stereo_matching(
+                ochain.SgbmPlugin(max_size=1 << 20, minDisparity=0, numDisparities=D, blockSize=5, P1=600, P2=2400, disp12MaxDiff=1, uniquenessRatio=5,
+                                  speckleWindowSize=200, speckleRange=2, mode=cv2.STEREO_SGBM_MODE_HH), max_depth=4.0) for _ in range(T)]
+            refs[0].get_depth(*raws[0])  # warm-up (builds the maps)
+
+            def cwork(i):
+                with np.errstate(all="ignore"):
+                    refs[i].get_depth(*raws[i % 2])
+            ts = [threading.Thread(target=cwork, args=(i,)) for i in range(T)]
+            t0 = time.perf_counter()
+            [x.start() for x in ts]
+            [x.join() for x in ts]
+            tc = time.perf_counter() - t0
+            out["chain_e2e"]["cpu_baseline"] = {"value": T / tc, "unit": "pairs/s", "cores": T, "kind": "port",
+                                                "sample": "1 round of %d threads x 1 raw 1080p pair through the cv2 restatement of Stereo.get_depth (rectify LANCZOS4 x2, "
+                                                          "StereoSGBM MODE_HH, depth, unrectify, undistort)" % T}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -9,6 +9,12 @@ from . import _ffi
 from .stereo_matching import REFERENCE_DEFAULTS, StereoSGBM
 
 
+def _optr(o):
+    """Address of an output buffer: a numpy array (host, ideally pinned) or anything with data_ptr() (a torch CUDA tensor:
+    the result then stays on the device, e.g. as the input of an NCCL all-gather)."""
+    return ctypes.c_void_p(o.data_ptr()) if hasattr(o, "data_ptr") else _ffi.ptr(o)
+
+
 class DisparityBatchEngine:
     """`streams` independent engine handles (stream + buffers) on one device, fed round-robin."""
 
@@ -40,7 +46,7 @@ class DisparityBatchEngine:
 
     def compute_batch(self, pairs, out=None, as_float=True):
         """pairs: list of (left, right) uint8 host arrays (pinned arrays from `_ffi.pinned_empty` are used in place,
-        others are staged).  Returns a list of (H,W) float32 disparities (reference post-processing applied) or int16
+        others are staged; `out`: one destination per pair, numpy arrays or torch CUDA tensors).  Returns a list of (H,W) float32 disparities (reference post-processing applied) or int16
         16*disparity when as_float=False.  H2D copy, kernels and D2H copy of different pairs overlap across streams."""
         n, S = len(pairs), len(self.handles)
         results = [None] * n
@@ -72,9 +78,9 @@ class DisparityBatchEngine:
                 copy_back.append((i, o))
             # calls on one handle are stream-ordered (upload, kernels, download), so pinned caller buffers need no sync in between
             if as_float:
-                h.call("b2s_compute_disparity_async", _ffi.ptr(left), _ffi.ptr(right), H, W, cn, None, _ffi.ptr(o))
+                h.call("b2s_compute_disparity_async", _ffi.ptr(left), _ffi.ptr(right), H, W, cn, None, _optr(o))
             else:
-                h.call("b2s_compute_disparity_async", _ffi.ptr(left), _ffi.ptr(right), H, W, cn, _ffi.ptr(o), None)
+                h.call("b2s_compute_disparity_async", _ffi.ptr(left), _ffi.ptr(right), H, W, cn, _optr(o), None)
             results[i] = o
             busy[slot] = busy[slot] or staged
         for h in self.handles:

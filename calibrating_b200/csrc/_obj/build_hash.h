@@ -1,1 +1,1 @@
-#define B2S_BUILD_HASH "4b5b68e6506fb446"
+#define B2S_BUILD_HASH "e6b5b39f624ebd3f"

@@ -202,6 +202,8 @@ static int make_geom(b2s_ctx *c, int H, int W, int cn)
 static int matcher_dev(b2s_ctx *c, const uint8_t *dl, const uint8_t *dr, int16_t *d_out16, float *d_outf, bool timed)
 {
     if (timed) cudaEventRecord(c->ev[1], c->stream);
+    c->last_dl = dl;
+    c->last_dr = dr;
     CK(c, launch_cost_volume(c, dl, dr));
     if (timed) cudaEventRecord(c->ev[2], c->stream);
     int nl = 0;
@@ -664,25 +666,39 @@ int b2s_launch_count(b2s_handle c, long long *n)
     return B2S_OK;
 }
 
+// One production repetition of the aggregation group on the handle's stream: the cost stage is re-run first (untimed by the
+// callers: it leaves the row sums the first aggregation launch consumes, exactly as in a real pair), then the group
+// = launch_aggregate + the stand-alone winner-take-all when the last scan did not fuse it.  marks: see launch_aggregate.
+static int agg_repetition(b2s_ctx *c, int *nl, cudaEvent_t *marks, cudaEvent_t before)
+{
+    if (c->last_dl && c->last_dr) CK(c, launch_cost_volume(c, c->last_dl, c->last_dr));
+    CK(c, launch_wta_prepare(c));
+    if (before) CK(c, cudaEventRecord(before, c->stream));
+    CK(c, launch_aggregate(c, nl, marks));
+    if (!c->wta_fused) {
+        CK(c, launch_wta(c));
+        if (marks && *nl < B2S_AGG_MAX_PARTS) CK(c, cudaEventRecord(marks[++*nl], c->stream));
+    }
+    return B2S_OK;
+}
+
 int b2s_bench_aggregate(b2s_handle c, int iters, float *ms_per_iter)
 {
     if (!c || !ms_per_iter || iters <= 0) return B2S_EINVAL;
     if (!c->have_volume) return fail(c, B2S_ESTATE, "no cost volume resident (run a disparity computation first)");
     CK(c, cudaSetDevice(c->device));
-    int nl = 0;
-    // the group = path aggregation + winner-take-all (launch_wta is a no-op when the last scan fused it)
-    CK(c, launch_aggregate(c, &nl)); // warm-up
-    CK(c, launch_wta(c));
-    CK(c, cudaEventRecord(c->ev[0], c->stream));
+    int nl = 0, rc;
+    if ((rc = agg_repetition(c, &nl, nullptr, nullptr))) return rc; // warm-up
+    double total = 0;
     for (int i = 0; i < iters; i++) {
-        CK(c, launch_aggregate(c, &nl));
-        CK(c, launch_wta(c));
+        if ((rc = agg_repetition(c, &nl, nullptr, c->ev[0]))) return rc;
+        CK(c, cudaEventRecord(c->ev[7], c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CK(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[7]));
+        total += ms;
     }
-    CK(c, cudaEventRecord(c->ev[7], c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
-    float ms = 0;
-    CK(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[7]));
-    *ms_per_iter = ms / iters;
+    *ms_per_iter = (float)(total / iters);
     if (int ae = agg_poll_error(c)) return agg_fail(c, ae);
     return B2S_OK;
 }
@@ -692,6 +708,8 @@ int b2s_enqueue_aggregate(b2s_handle c, int iters)
     if (!c || iters <= 0) return B2S_EINVAL;
     if (!c->have_volume) return fail(c, B2S_ESTATE, "no cost volume resident (run a disparity computation first)");
     CK(c, cudaSetDevice(c->device));
+    // (several handles in flight; the cost stage cannot be kept out of this figure, so the group runs on the finished C:
+    // its first launch is then the plain +x scan instead of the scan that also forms C)
     int nl = 0;
     for (int i = 0; i < iters; i++) {
         CK(c, launch_aggregate(c, &nl));
@@ -705,16 +723,11 @@ int b2s_bench_aggregate_parts(b2s_handle c, int iters, float *ms_parts, int max_
     if (!c || !ms_parts || !n_parts || iters <= 0 || max_parts <= 0) return B2S_EINVAL;
     if (!c->have_volume) return fail(c, B2S_ESTATE, "no cost volume resident (run a disparity computation first)");
     CK(c, cudaSetDevice(c->device));
-    int nl = 0;
-    CK(c, launch_aggregate(c, &nl)); // warm-up
-    CK(c, launch_wta(c));
+    int nl = 0, rc;
+    if ((rc = agg_repetition(c, &nl, nullptr, nullptr))) return rc; // warm-up
     for (int k = 0; k < max_parts; k++) ms_parts[k] = 0.f;
     for (int i = 0; i < iters; i++) {
-        CK(c, launch_aggregate(c, &nl, c->aev));
-        if (!c->wta_fused && nl < B2S_AGG_MAX_PARTS) { // the stand-alone winner-take-all is the group's last part
-            CK(c, launch_wta(c));
-            CK(c, cudaEventRecord(c->aev[++nl], c->stream));
-        }
+        if ((rc = agg_repetition(c, &nl, c->aev, nullptr))) return rc;
         CK(c, cudaStreamSynchronize(c->stream));
         for (int k = 0; k < nl && k < max_parts && k < B2S_AGG_MAX_PARTS; k++) {
             float ms = 0;

@@ -60,6 +60,7 @@ struct b2s_ctx {
     b2s_sgbm_params prm{};
     SgbmGeom g{};
     bool have_volume = false;
+    const uint8_t *last_dl = nullptr, *last_dr = nullptr; // device images of the last matcher run (bench: the cost stage is re-run untimed)
     bool keep_volumes = false; // b2s_set_option(B2S_OPT_KEEP_VOLUMES): a fused last pass also stores S
     bool fuse_wta = true;      // b2s_set_option(B2S_OPT_FUSE_WTA): on by default
     int max_size = 0;          // b2s_set_option(B2S_OPT_MAX_SIZE): longest image side the matcher works on (0 = no limit), stereo_matching.py:26,61

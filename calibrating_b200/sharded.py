@@ -129,34 +129,94 @@ def rig_struct(scalars, table, base_address):
     return rig
 
 
-class CudaEngine:
-    """Default per-rank engine: libb2s.so on `device`.  The rig block stays where the broadcast left it (a torch CUDA tensor);
-    results are written straight into the caller's device tensor."""
+def check_pair(img1, img2, scalars):
+    """The checks of `Stereo._prep` / `Stereo._check_raw` against the broadcast rig: C-contiguous uint8 (h,w) or (h,w,3) images of
+    cam1's / cam2's size with equal channel counts.  Returns (img1, img2, cn).  A wrong image would be an out-of-bounds host
+    read inside the engine, so every rank checks its own pairs before the FFI call."""
+    img1, img2 = np.ascontiguousarray(img1), np.ascontiguousarray(img2)
+    for im in (img1, img2):
+        if im.dtype != np.uint8 or im.ndim not in (2, 3) or (im.ndim == 3 and im.shape[2] != 3):
+            raise ValueError("images must be uint8 (h,w) or (h,w,3), got %s %s" % (im.dtype, im.shape))
+    if img1.ndim != img2.ndim:
+        raise ValueError("img1/img2 channel counts differ")
+    if img1.shape[:2] != (scalars["H1"], scalars["W1"]) or img2.shape[:2] != (scalars["H2"], scalars["W2"]):
+        raise ValueError("image sizes %s/%s do not match the rig's cam1/cam2 sizes %s/%s" % (
+            img1.shape, img2.shape, (scalars["H1"], scalars["W1"]), (scalars["H2"], scalars["W2"])))
+    return img1, img2, (1 if img1.ndim == 2 else 3)
 
-    def __init__(self, device):
-        self.handle = _ffi.Handle(device)
+
+class CudaEngine:
+    """Default per-rank engine: libb2s.so on `device`, `streams` engine handles (= CUDA streams) in flight like
+    `Stereo.get_depth_batch`.  The rig block stays where the broadcast left it (a torch CUDA tensor); results are written
+    straight into the caller's device tensor.  The matcher honours the cfg's `max_size` (the reference's default 1000
+    included): the down-scale runs on the device (B2S_OPT_MAX_SIZE), so a sharded batch equals single-GPU `get_depth`."""
+
+    def __init__(self, device, streams=3):
+        self.handles = [_ffi.Handle(device) for _ in range(int(streams))]
+        self.handle = self.handles[0]
         self.device = device
         self._block = None
+        self._pin = [dict() for _ in self.handles]
 
     def set_rig_block(self, block, scalars, matcher_cfg, table):
         from .stereo_matching import SemiGlobalBlockMatching
         self._block = block  # keep the storage alive
-        if scalars.get("map_params"):  # maps="device": the rank generates the maps itself from ~1 KB of parameters
-            self.handle.call("b2s_set_rig_params", ctypes.byref(rig_params_struct(scalars)))
-        else:
-            base = block.data_ptr() if hasattr(block, "data_ptr") else block.ctypes.data
-            self.handle.call("b2s_set_rig", ctypes.byref(rig_struct(scalars, table, base)))
-        self.matcher = SemiGlobalBlockMatching(dict(matcher_cfg, max_size=1 << 30), handle=self.handle)
+        self.matchers = []
+        for h in self.handles:
+            if scalars.get("map_params"):  # maps="device": the rank generates the maps itself from ~1 KB of parameters
+                h.call("b2s_set_rig_params", ctypes.byref(rig_params_struct(scalars)))
+            else:
+                base = block.data_ptr() if hasattr(block, "data_ptr") else block.ctypes.data
+                h.call("b2s_set_rig", ctypes.byref(rig_struct(scalars, table, base)))
+            sm = SemiGlobalBlockMatching(dict(matcher_cfg), handle=h)
+            h.call("b2s_set_option", 4, sm._max_size_option())
+            self.matchers.append(sm)
+        self.matcher = self.matchers[0]
         self.scalars = scalars
 
+    def _pinned(self, slot, key, shape):
+        a = self._pin[slot].get(key)
+        if a is None or a.shape != tuple(shape):
+            if a is not None:
+                _ffi.pinned_free(a)
+            a = self._pin[slot][key] = _ffi.pinned_empty(shape, np.uint8)
+        return a
+
+    def get_depth_batch_into(self, pairs, outs):
+        """pairs: [(img1, img2)] host uint8 arrays; outs: one (H1,W1) float64 destination per pair (torch CUDA tensors or host
+        arrays).  Upload, kernels and the copy into `outs` of different pairs overlap across the handles' streams."""
+        S = len(self.handles)
+        for i, ((a, b), out) in enumerate(zip(pairs, outs)):
+            slot = i % S
+            h = self.handles[slot]
+            a, b, cn = check_pair(a, b, self.scalars)
+            if i >= S:
+                h.sync()  # the slot's staging buffers are still being uploaded by its previous call
+            if a.ctypes.data not in _ffi._PINNED:
+                buf = self._pinned(slot, "a", a.shape)
+                np.copyto(buf, a)
+                a = buf
+            if b.ctypes.data not in _ffi._PINNED:
+                buf = self._pinned(slot, "b", b.shape)
+                np.copyto(buf, b)
+                b = buf
+            o = _ffi.DepthOut()
+            o.unrectify_depth = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+            h.call("b2s_get_depth_async", _ffi.ptr(a), _ffi.ptr(b), cn, 1, ctypes.byref(o))
+        for h in self.handles:
+            h.sync()
+
     def get_depth_into(self, img1, img2, out):
-        """img1/img2: host uint8 arrays; out: (H1,W1) float64 torch CUDA tensor (or host array) for unrectify_depth."""
-        o = _ffi.DepthOut()
-        o.unrectify_depth = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
-        img1, img2 = np.ascontiguousarray(img1), np.ascontiguousarray(img2)
-        cn = 1 if img1.ndim == 2 else img1.shape[2]
-        self.handle.call("b2s_get_depth_async", _ffi.ptr(img1), _ffi.ptr(img2), cn, 1, ctypes.byref(o))
-        self.handle.sync()  # (host images are reused by the caller; one pair per call keeps this simple)
+        """One pair: img1/img2 host uint8 arrays; out: (H1,W1) float64 torch CUDA tensor (or host array) for unrectify_depth."""
+        self.get_depth_batch_into([(img1, img2)], [out])
+
+    def close(self):
+        for pins in self._pin:
+            for a in pins.values():
+                _ffi.pinned_free(a)
+            pins.clear()
+        for h in self.handles:
+            h.close()
 
 
 class ShardedStereo:
@@ -205,11 +265,15 @@ class ShardedStereo:
         torch, dist = self.torch, self.dist
         n, H1, W1 = len(local_pairs), self.scalars["H1"], self.scalars["W1"]
         dev = torch.device("cuda", self.device) if self.cuda else torch.device("cpu")
-        local = torch.zeros((n, H1, W1), dtype=torch.float64, device=dev)
-        for k, (a, b) in enumerate(local_pairs):
-            self.engine.get_depth_into(a, b, local[k] if self.cuda else local[k].numpy())
+        # (torch.empty launches nothing, so the engine's own streams need no ordering against torch's; every pixel is written)
+        local = torch.empty((n, H1, W1), dtype=torch.float64, device=dev)
+        outs = [local[k] if self.cuda else local[k].numpy() for k in range(n)]
+        if hasattr(self.engine, "get_depth_batch_into"):
+            self.engine.get_depth_batch_into(local_pairs, outs)  # returns after the engine's streams are idle
+        else:
+            for (a, b), o in zip(local_pairs, outs):
+                a, b, _ = check_pair(a, b, self.scalars)
+                self.engine.get_depth_into(a, b, o)
         gathered = torch.empty((self.world, n, H1, W1), dtype=torch.float64, device=dev)
-        if self.cuda:
-            torch.cuda.current_stream().synchronize()
         dist.all_gather_into_tensor(gathered.view(self.world * n, H1, W1), local, group=self.group)  # THE depth all-gather
         return gathered.transpose(0, 1).reshape(self.world * n, H1, W1)  # (rank, k) -> global index k*world + rank

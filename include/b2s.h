@@ -211,17 +211,19 @@ int b2s_volume_dims(b2s_handle h, int *H, int *width1, int *D, int *Dp);
 int b2s_debug_fetch(b2s_handle h, int which, void *dst, size_t bytes);
 int b2s_timings(b2s_handle h, b2s_timing *t);      /* CUDA-event stage times of the last synchronous call */
 int b2s_launch_count(b2s_handle h, long long *n);  /* kernels launched by this handle since creation */
-/* Timed loop of the aggregation GROUP (path aggregation + winner-take-all: everything between the cost volume C and the raw
- * winner map) alone on the resident cost volume of the last call (bench.py roofline): runs `iters` repetitions on the
- * handle's stream between two CUDA events, returns the mean ms per repetition. */
+/* The aggregation GROUP (path aggregation + winner-take-all: everything between the cost stage and the raw winner map) timed
+ * alone, in its production form, on the images of the last call (which must still be valid device memory: the handle's own
+ * copies after b2s_compute_disparity, the caller's after b2s_compute_disparity_dev): every repetition re-runs the cost stage
+ * first, outside the timed interval, so that the first aggregation launch is the one a real pair runs (the +x scan that also
+ * forms C from the cost stage's row sums).  Returns the mean ms per repetition over `iters` CUDA-event intervals. */
 int b2s_bench_aggregate(b2s_handle h, int iters, float *ms_per_iter);
 /* Same, with one CUDA-event interval per kernel launch of the group in launch order (wavefront schedule, MODE_HH: the
  * two-sweep launch, then the winner-take-all that adds the two sums; MODE_SGBM: the top-down sweep, then the (-1,0) scan with
  * the fused winner-take-all; B2S_AGG_SCHEDULE=sweep: +x scan, fused vertical sweep, -x scan).  ms_parts[k] = mean ms of
  * launch k over `iters` repetitions, *n_parts = number of launches (<= max_parts). */
 int b2s_bench_aggregate_parts(b2s_handle h, int iters, float *ms_parts, int max_parts, int *n_parts);
-/* Enqueue `iters` repetitions of the group on the handle's stream without waiting (several handles in flight: the batched
- * figure of bench.py; bracket with b2s_event_record / b2s_event_elapsed). */
+/* Enqueue `iters` repetitions of the group on the handle's stream without waiting (several handles in flight; bracket with
+ * b2s_event_record / b2s_event_elapsed).  Runs on the finished cost volume: the first launch is the plain +x scan. */
 int b2s_enqueue_aggregate(b2s_handle h, int iters);
 /* User CUDA events on the handle's stream (slot 0..3), for device-side timing of caller-defined regions. */
 int b2s_event_record(b2s_handle h, int slot);

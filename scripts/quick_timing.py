@@ -19,5 +19,7 @@ V = 1080 * 1792 * 128
 print("aggregate alone: %.3f ms  -> canonical %.1f GB/s (8 B/voxel)" % (ms, V * 8 / ms / 1e6))
 parts = m.handle.bench_aggregate_parts(10)
 import hashlib
+from calibrating_b200 import _ffi
+print("build_hash", _ffi.lib().b2s_build_hash().decode())
 print("disp md5", hashlib.md5(d.tobytes()).hexdigest())
 print("aggregation launches (ms):", ["%.3f" % p for p in parts], "sum %.3f" % sum(parts))

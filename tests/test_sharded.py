@@ -145,3 +145,55 @@ def test_cuda_engine_nccl_world1():
         assert np.allclose(got, exp, rtol=1e-9, atol=0)
     finally:
         dist.destroy_process_group()
+
+
+def _nccl_worker(rank, world, port, n_pairs, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        rig = synth.rig_dict(RIG_XY)
+        st = None
+        if rank == 0:
+            st = cb.Stereo.load(rig, device=0).set_stereo_matching(cb.SemiGlobalBlockMatching(dict(CFG), device=0), max_depth=3.5)
+        sh = sharded.ShardedStereo(st)
+        mine = sh.shard(n_pairs)
+        got = sh.get_depth_batch([synth.render_rig(rig, seed=i) for i in mine])
+        bad = None
+        try:
+            sh.engine.get_depth_batch_into([(np.zeros((10, 10, 3), np.uint8),) * 2], [got[0]])
+        except ValueError as e:
+            bad = str(e)
+        q.put((rank, sh.rig_bytes, got.cpu().numpy(), bad))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_cuda_engine_nccl_multi_rank():
+    """BASELINE config 3 in small: ShardedStereo on every GPU of the box (>= 2), one process per GPU over NCCL: rig block
+    broadcast from rank 0 into device memory, pairs i % world per rank on several streams, depth all-gathered into global pair
+    order on every rank; equal to the single-process chain.  Skipped on a one-GPU box (gpurun --gpus N runs it)."""
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 CUDA devices")
+    n_pairs = 2 * world
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, n_pairs, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    exp = _expected(synth.rig_dict(RIG_XY), n_pairs)
+    for rank, rig_bytes, got, bad in res:
+        assert got.shape == exp.shape and got.dtype == np.float64
+        assert np.allclose(got, exp, rtol=1e-9, atol=0), "rank %d: gathered depth differs from the single-process chain" % rank
+        assert np.array_equal(got, res[0][2]), "ranks disagree"
+        assert bad and "do not match the rig" in bad, "a wrong-sized image must be rejected before the FFI call"

@@ -1,1 +1,1 @@
-#define B2S_BUILD_HASH "e6b5b39f624ebd3f"
+#define B2S_BUILD_HASH "3e0771ccefce18bd"

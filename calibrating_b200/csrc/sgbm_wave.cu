@@ -40,6 +40,7 @@ constexpr int WV_K = 8;      // pixels per state ring (power of two)
 constexpr int WV_CPX = 4;    // pixels per bulk-copy chunk
 constexpr int WV_KG = 32;    // pixels per band hand-over ring in global memory (power of two)
 constexpr int WV_KS = 16;    // pixels of the hand-over staging ring in shared memory (power of two)
+constexpr int WV_L2AHEAD = 24; // chunks of C pulled into L2 ahead of the copy into shared memory
 constexpr int WV_PF = 6;     // prefetch distance of the hand-over (pixels; < WV_KS - 3)
 template <int NP> struct WvCfg {
     static constexpr int rows = NP <= 2 ? 16 : 8;   // image rows (= warps) per CTA
@@ -190,6 +191,18 @@ __global__ void __launch_bounds__(WvCfg<NP>::rows * 32, 1) agg_wave_kernel(WaveA
             else bulk_g2s(slot + (WV_CPX - (ub - ua)) * CH, Crow + (size_t)(W - ub) * Dp, bytes, mb); // memory order = reversed pixel order
         }
     };
+    // DRAM latency (~2 us under load) against a prefetch distance of (CSLOTS - 1) * CPX = 8 pixels in shared memory would hold a
+    // row at ~500 cycles per pixel: chunks are pulled into L2 WV_L2AHEAD chunks ahead (cp.async.bulk.prefetch.L2), so that the
+    // copy into shared memory only pays the L2 latency
+    auto l2_prefetch = [&](int j) {
+        if (lane == 0 && j < nchunks) {
+            const int ua = WV_CPX * j, ub = min(ua + WV_CPX, W);
+            const int16_t *src = dir == 0 ? Crow + (size_t)ua * Dp : Crow + (size_t)(W - ub) * Dp;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(ub - ua) * CH) : "memory");
+        }
+    };
+#pragma unroll 1
+    for (int j = 0; j < WV_L2AHEAD; j++) l2_prefetch(j);
 #pragma unroll 1
     for (int j = 0; j < CSLOTS - 1 && j < nchunks; j++) issue(j);
 
@@ -273,6 +286,7 @@ __global__ void __launch_bounds__(WvCfg<NP>::rows * 32, 1) agg_wave_kernel(WaveA
     for (int j = 0; j < nchunks; j++) {
         __syncwarp(); // every lane is done with the slot of chunk j-1: it is refilled now
         if (j + CSLOTS - 1 < nchunks) issue(j + CSLOTS - 1);
+        l2_prefetch(j + WV_L2AHEAD);
         mbar_wait_sleep(cbar + (j % CSLOTS) * 8, (uint32_t)(j / CSLOTS) & 1u, a.err);
         const int np = min(WV_CPX, W - j * WV_CPX);
         const uint32_t cslot = cring + (j % CSLOTS) * CSLOTB + li * N * 4;

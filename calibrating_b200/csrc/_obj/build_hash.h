@@ -1,1 +1,1 @@
-#define B2S_BUILD_HASH "3e0771ccefce18bd"
+#define B2S_BUILD_HASH "13a7dfea0fc94d8e"

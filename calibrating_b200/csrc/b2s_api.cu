@@ -83,6 +83,15 @@ int b2s_create(int device, b2s_handle *out)
         b2s_destroy(c);
         return fail(nullptr, B2S_ECUDA, "b2s_create: %s", cudaGetErrorString(e));
     }
+    {   // rows padded to 144 bytes for the shared-memory copy of remap_lz4_kernel (remap.cu)
+        std::vector<unsigned char> padded(1024 * 144, 0);
+        for (int r = 0; r < 1024; r++) memcpy(&padded[(size_t)r * 144], &tab[(size_t)r * 64], 128);
+        if ((e = c->lanczos_tabp.ensure(padded.size())) != cudaSuccess ||
+            (e = cudaMemcpy(c->lanczos_tabp.p, padded.data(), padded.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
+            b2s_destroy(c);
+            return fail(nullptr, B2S_ECUDA, "b2s_create: %s", cudaGetErrorString(e));
+        }
+    }
     *out = c;
     return B2S_OK;
 }
@@ -95,7 +104,7 @@ int b2s_destroy(b2s_handle c)
     DevBuf *bufs[] = {&c->left, &c->right, &c->planesL, &c->planesR, &c->C, &c->S, &c->S2, &c->raw, &c->disp16, &c->disp2key, &c->labels,
                       &c->sizes, &c->med, &c->dispf, &c->sleft, &c->sright, &c->sdispf, &c->agg_ho, &c->agg_errbuf, &c->map1x, &c->map1y, &c->map2x, &c->map2y, &c->vmask, &c->umapx, &c->umapy,
                       &c->und_xy, &c->und_fxy, &c->img1, &c->img2, &c->rect1, &c->rect2, &c->und1, &c->dispfinal, &c->rdepth,
-                      &c->udepth, &c->lanczos_tab, &c->stage_f32, &c->dkey, &c->ddepth, &c->pkey, &c->pin, &c->pout};
+                      &c->udepth, &c->lanczos_tab, &c->lanczos_tabp, &c->stage_f32, &c->dkey, &c->ddepth, &c->pkey, &c->pin, &c->pout};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -340,6 +349,7 @@ int b2s_set_rig(b2s_handle c, const b2s_rig *r)
     c->r_m[0] = r->unrect_m[0]; c->r_m[1] = r->unrect_m[1]; c->r_m[2] = r->unrect_m[2];
     c->r_fxb = r->fx_baseline; c->r_max_depth = r->max_depth;
     c->have_rig = true;
+    c->have_map_params = false;
     CK(c, c->dispfinal.ensure(n * 4));
     CK(c, c->rdepth.ensure(n * 8));
     CK(c, c->udepth.ensure(n1 * 8));
@@ -369,6 +379,9 @@ int b2s_set_rig_params(b2s_handle c, const b2s_rig_params *r)
     c->r_m[0] = r->unrect_m[0]; c->r_m[1] = r->unrect_m[1]; c->r_m[2] = r->unrect_m[2];
     c->r_fxb = r->fx_baseline; c->r_max_depth = r->max_depth;
     c->have_rig = true;
+    c->have_map_params = true;
+    c->mp_rect1 = r->rect1;
+    c->mp_rect2 = r->rect2;
     c->cam1_f[0] = r->undist.fx; c->cam1_f[1] = r->undist.fy; c->cam1_f[2] = r->undist.cx; c->cam1_f[3] = r->undist.cy;
     memcpy(c->cam1_k, r->undist.k, sizeof c->cam1_k);
     c->have_cam1 = true;
@@ -431,10 +444,11 @@ static int rectify_dev(b2s_ctx *c, const uint8_t *img1, const uint8_t *img2, int
     CK(c, c->rect2.ensure(n));
     CK(c, cudaMemcpyAsync(c->img1.p, img1, n1, cudaMemcpyDefault, c->stream));
     CK(c, cudaMemcpyAsync(c->img2.p, img2, n2, cudaMemcpyDefault, c->stream));
+    const bool analytic = c->have_map_params && c->r_interp == 0; // rig given by parameters: the remap evaluates the maps itself
     CK(c, launch_remap_u8(c, c->img1.as<uint8_t>(), c->rH1, c->rW1, cn, c->map1x.as<float>(), c->map1y.as<float>(), c->rH, c->rW, 0,
-                          c->r_interp, c->rect1.as<uint8_t>()));
+                          c->r_interp, c->rect1.as<uint8_t>(), analytic ? &c->mp_rect1 : nullptr));
     CK(c, launch_remap_u8(c, c->img2.as<uint8_t>(), c->rH2, c->rW2, cn, c->map2x.as<float>(), c->map2y.as<float>(), c->rH, c->rW,
-                          c->r_min_disp, c->r_interp, c->rect2.as<uint8_t>()));
+                          c->r_min_disp, c->r_interp, c->rect2.as<uint8_t>(), analytic ? &c->mp_rect2 : nullptr));
     return B2S_OK;
 }
 

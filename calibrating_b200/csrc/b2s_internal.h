@@ -93,6 +93,9 @@ struct b2s_ctx {
     DevBuf img1, img2, rect1, rect2, und1; // raw inputs and remapped outputs
     DevBuf dispfinal, rdepth, udepth;      // (H,W) f32, (H,W) f64, (H1,W1) f64
     DevBuf lanczos_tab;                    // (1024, 8, 8) int16
+    DevBuf lanczos_tabp;                   // the same with rows padded to 144 bytes (remap_lz4_kernel's shared-memory copy)
+    bool have_map_params = false;          // rig set by b2s_set_rig_params: rectification evaluates the maps analytically
+    b2s_map_params mp_rect1{}, mp_rect2{};
     DevBuf pkey, pin, pout;                // project_depth: winner key per target pixel, staged input / output
     DevBuf dkey, ddepth;                   // distort_depth: winner index per target pixel (+ the 12 coefficients); (H1,W1) f64 result
     bool have_cam1 = false;
@@ -123,7 +126,7 @@ cudaError_t launch_post(b2s_ctx *c, int16_t *d_out_disp16, float *d_out_disp);
 // remap.cu
 void build_lanczos4_table(int16_t *tab /* 1024*64 */);
 cudaError_t launch_remap_u8(b2s_ctx *c, const uint8_t *src, int sH, int sW, int cn, const float *mapx, const float *mapy,
-                            int dH, int dW, int xshift, int interp, uint8_t *dst);
+                            int dH, int dW, int xshift, int interp, uint8_t *dst, const b2s_map_params *prm = nullptr);
 cudaError_t launch_undistort_u8(b2s_ctx *c, const uint8_t *src, int H, int W, int cn, const int16_t *xy, const uint16_t *fxy,
                                 uint8_t *dst);
 cudaError_t launch_depth(b2s_ctx *c, const float *d_disp_in, int add_min_disp, int want_unrectify);

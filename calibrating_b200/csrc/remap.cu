@@ -8,6 +8,10 @@
 #include <math.h>
 #include <string.h>
 
+#include <stdlib.h>
+
+#include <mutex>
+
 #include "b2s_internal.h"
 
 // ---- host: cv::initInterTab2D(INTER_LANCZOS4, fixpt) restated ------------------------------------------------------
@@ -191,6 +195,136 @@ __global__ void remap_u8_kernel(const uint8_t *__restrict__ src, int sH, int sW,
     for (int c = 0; c < CN; c++) o[c] = fix_cast(acc[c]);
 }
 
+// ---- LANCZOS4, production version: persistent CTAs, the fixed-point weight table in shared memory ------------------------
+// remap_u8_kernel<CN, 0> above is bound by its weight fetch: every pixel reads the 128-byte row (fy*32+fx) of the 128 KB table,
+// 8 x LDG.128 per thread with 32 different cache lines per warp instruction.  Here every CTA first pulls the whole table into
+// shared memory with bulk copies (cp.async.bulk -> UBLKCP, one mbarrier), rows padded to 144 bytes so that the 8 lanes of a
+// quarter-warp reading the same 16-byte column of 8 different rows hit 8 different bank groups, then walks destination tiles of
+// 32 x RL_WARPS pixels (warp = 32 consecutive pixels of a row: their 8-row source windows overlap, and so do those of the
+// neighbouring rows held by the other warps of the CTA, which keeps the source reads in L1).
+// ANALYTIC (rig set by parameters, b2s_set_rig_params): the map pixel is evaluated on the spot in float64 -- cv2's operation
+// order, rounded to float32 exactly like the stored planes -- so that no map plane is read at all (the
+// fused undistort + rectify remap).
+__device__ __forceinline__ void map_eval(const b2s_map_params &p, int j, int i, double &u, double &v); // (below, with gen_maps_kernel)
+constexpr int RL_WARPS = 16;
+constexpr int RL_ROWB = 144;                 // padded bytes of one table row
+constexpr int RL_TABB = 1024 * RL_ROWB;      // 147,456 bytes
+template <int CN, bool ANALYTIC>
+__global__ void __launch_bounds__(RL_WARPS * 32, 1) remap_lz4_kernel(const uint8_t *__restrict__ src, int sH, int sW, const float *__restrict__ mapx,
+                                                                    const float *__restrict__ mapy, b2s_map_params prm, int dH, int dW, int xshift,
+                                                                    const unsigned char *__restrict__ tabp, uint8_t *__restrict__ dst)
+{
+    extern __shared__ __align__(128) unsigned char rl_smem[];
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(rl_smem), mb = sm0 + RL_TABB;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(mb), "r"((uint32_t)RL_TABB) : "memory");
+#pragma unroll 1
+        for (int k = 0; k < RL_TABB; k += 16384) {
+            const uint32_t bytes = min(16384, RL_TABB - k);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sm0 + k), "l"(tabp + k), "r"(bytes), "r"(mb)
+                         : "memory");
+        }
+    }
+    __syncthreads();
+    {
+        uint32_t ok;
+        do {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(mb) : "memory");
+        } while (!ok);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tx_n = (dW + 31) / 32, ty_n = (dH + RL_WARPS - 1) / RL_WARPS;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < tx_n * ty_n; tile += gridDim.x) {
+        const int x = (tile % tx_n) * 32 + lane, y = (tile / tx_n) * RL_WARPS + wid;
+        if (x >= dW || y >= dH) continue;
+        uint8_t *o = dst + ((size_t)y * dW + x) * CN;
+        const int xm = x - xshift;
+        int acc[CN];
+#pragma unroll
+        for (int c = 0; c < CN; c++) acc[c] = 0;
+        bool zero = xm < 0 || xm >= dW;
+        int x0 = 0, y0 = 0, fx = 0, fy = 0;
+        if (!zero) {
+            float mu, mv;
+            if (ANALYTIC) {
+                double u, v;
+                map_eval(prm, xm, y, u, v);
+                mu = (float)u;
+                mv = (float)v;
+            } else {
+                const size_t mi = (size_t)y * dW + xm;
+                mu = mapx[mi];
+                mv = mapy[mi];
+            }
+            const int sx = __float2int_rn(mu * 32.f), sy = __float2int_rn(mv * 32.f);
+            x0 = sat_short(sx >> 5) - 3;
+            y0 = sat_short(sy >> 5) - 3;
+            fx = sx & 31;
+            fy = sy & 31;
+            zero = x0 >= sW || x0 + 8 <= 0 || y0 >= sH || y0 + 8 <= 0;
+        }
+        if (zero) {
+#pragma unroll
+            for (int c = 0; c < CN; c++) o[c] = 0;
+            continue;
+        }
+        const uint32_t wrow = sm0 + (uint32_t)(fy * 32 + fx) * RL_ROWB;
+        if (x0 >= 0 && x0 + 8 <= sW && y0 >= 0 && y0 + 8 <= sH) {
+            constexpr int NW = 2 * CN; // 32-bit words of one window row
+            const size_t a0 = ((size_t)y0 * sW + x0) * CN, rstep = (size_t)sW * CN;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                int wpair[4]; // taps (0,1) (2,3) (4,5) (6,7) as packed int16 pairs
+                asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(wpair[0]), "=r"(wpair[1]), "=r"(wpair[2]), "=r"(wpair[3]) : "r"(wrow + r * 16));
+                const size_t a = a0 + r * rstep;
+                const uint32_t *wp = (const uint32_t *)(src + (a & ~(size_t)3));
+                const unsigned s = (unsigned)(a & 3) * 8;
+                uint32_t Wd[NW + 1], B[NW];
+#pragma unroll
+                for (int i = 0; i < NW; i++) Wd[i] = __ldg(wp + i);
+                Wd[NW] = s ? __ldg(wp + NW) : 0u; // (an aligned row ends with its last word: nothing is read past the window)
+#pragma unroll
+                for (int i = 0; i < NW; i++) B[i] = __funnelshift_r(Wd[i], Wd[i + 1], s);
+                if (CN == 1) {
+                    acc[0] = dp2a_lo(wpair[0], B[0], acc[0]);
+                    acc[0] = dp2a_hi(wpair[1], B[0], acc[0]);
+                    acc[0] = dp2a_lo(wpair[2], B[1], acc[0]);
+                    acc[0] = dp2a_hi(wpair[3], B[1], acc[0]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+#pragma unroll
+                        for (int c = 0; c < CN; c++) {
+                            const int ja = 2 * q * CN + c, jb = ja + CN; // bytes of taps 2q and 2q+1 of channel c in the window row
+                            const uint32_t pr = __byte_perm(B[ja >> 2], B[jb >> 2], (ja & 3) | (((jb & 3) + 4) << 4));
+                            acc[c] = dp2a_lo(wpair[q], pr, acc[c]);
+                        }
+                }
+            }
+        } else { // window crosses the image border: taps outside contribute 0 (BORDER_CONSTANT)
+#pragma unroll 1
+            for (int r = 0; r < 8; r++) {
+                const int yy = y0 + r;
+                if (yy < 0 || yy >= sH) continue;
+                const uint8_t *row = src + ((size_t)yy * sW + x0) * CN;
+#pragma unroll 1
+                for (int k = 0; k < 8; k++) {
+                    if (x0 + k < 0 || x0 + k >= sW) continue;
+                    short wv;
+                    asm volatile("ld.shared.s16 %0, [%1];" : "=h"(wv) : "r"(wrow + (r * 8 + k) * 2));
+#pragma unroll
+                    for (int c = 0; c < CN; c++) acc[c] += (int)row[k * CN + c] * (int)wv;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CN; c++) o[c] = fix_cast(acc[c]);
+    }
+}
+
 // cv2.undistort: pre-quantised CV_16SC2 maps (xy = integer part, fxy = fy*32+fx), bilinear, border 0
 template <int CN>
 __global__ void undistort_u8_kernel(const uint8_t *__restrict__ src, int H, int W, const short2 *__restrict__ xy,
@@ -264,11 +398,9 @@ __global__ void unrectify_kernel(const double *__restrict__ depth, int H, int W,
 namespace {
 // cv2.initUndistortRectifyMap restated, float64 without fused multiply-add so that every
 // operation rounds exactly where OpenCV's scalar code does; thread = one map pixel.
-__global__ void gen_maps_kernel(b2s_map_params p, float *__restrict__ mapx, float *__restrict__ mapy, uint8_t *__restrict__ mask,
-                                int mW, int mH, short2 *__restrict__ xy16, unsigned short *__restrict__ fxy16)
+// one map pixel (j, i): the float64 source coordinates (u, v) of cv2.initUndistortRectifyMap
+__device__ __forceinline__ void map_eval(const b2s_map_params &p, int j, int i, double &u, double &v)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
-    if (j >= p.W) return;
     const double dj = (double)j, di = (double)i;
     const double X = __dadd_rn(__dmul_rn(dj, p.iR[0]), __dadd_rn(__dmul_rn(di, p.iR[1]), p.iR[2]));
     const double Y = __dadd_rn(__dmul_rn(dj, p.iR[3]), __dadd_rn(__dmul_rn(di, p.iR[4]), p.iR[5]));
@@ -289,7 +421,17 @@ __global__ void gen_maps_kernel(b2s_map_params p, float *__restrict__ mapx, floa
     yd = __dadd_rn(yd, __dmul_rn(p2, _2xy));
     yd = __dadd_rn(yd, __dmul_rn(s3, r2));
     yd = __dadd_rn(yd, __dmul_rn(__dmul_rn(s4, r2), r2));
-    const double u = __dadd_rn(__dmul_rn(p.fx, xd), p.cx), v = __dadd_rn(__dmul_rn(p.fy, yd), p.cy);
+    u = __dadd_rn(__dmul_rn(p.fx, xd), p.cx);
+    v = __dadd_rn(__dmul_rn(p.fy, yd), p.cy);
+}
+
+__global__ void gen_maps_kernel(b2s_map_params p, float *__restrict__ mapx, float *__restrict__ mapy, uint8_t *__restrict__ mask,
+                                int mW, int mH, short2 *__restrict__ xy16, unsigned short *__restrict__ fxy16)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= p.W) return;
+    double u, v;
+    map_eval(p, j, i, u, v);
     const size_t o = (size_t)i * p.W + j;
     if (mapx) {
         const float fu = (float)u, fv = (float)v;
@@ -435,9 +577,27 @@ cudaError_t launch_gen_maps(b2s_ctx *c, const b2s_map_params &p, float *mapx, fl
     return cudaGetLastError();
 }
 
+// prm != NULL: evaluate the map from its parameters inside the kernel (LANCZOS4 only; mapx / mapy are not read)
 cudaError_t launch_remap_u8(b2s_ctx *c, const uint8_t *src, int sH, int sW, int cn, const float *mapx, const float *mapy, int dH,
-                            int dW, int xshift, int interp, uint8_t *dst)
+                            int dW, int xshift, int interp, uint8_t *dst, const b2s_map_params *prm)
 {
+    if (interp == 0 && c->lanczos_tabp.p && (cn == 1 || cn == 3) && !getenv("B2S_REMAP_SIMPLE")) {
+        const size_t smem = RL_TABB + 16;
+        static std::once_flag once[64][4];
+        cudaError_t e = cudaSuccess;
+        auto go = [&](auto kern, int slot) -> cudaError_t {
+            std::call_once(once[c->device & 63][slot], [&] { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+            if (e != cudaSuccess) return e;
+            const int tiles = ((dW + 31) / 32) * ((dH + RL_WARPS - 1) / RL_WARPS);
+            const int grid = tiles < c->num_sms ? tiles : c->num_sms;
+            static const b2s_map_params none = {};
+            kern<<<grid, RL_WARPS * 32, smem, c->stream>>>(src, sH, sW, mapx, mapy, prm ? *prm : none, dH, dW, xshift, c->lanczos_tabp.as<unsigned char>(), dst);
+            c->launches++;
+            return cudaGetLastError();
+        };
+        if (cn == 3) return prm ? go(remap_lz4_kernel<3, true>, 0) : go(remap_lz4_kernel<3, false>, 1);
+        return prm ? go(remap_lz4_kernel<1, true>, 2) : go(remap_lz4_kernel<1, false>, 3);
+    }
     dim3 b(128), g((dW + 127) / 128, dH);
     const int16_t *tab = c->lanczos_tab.as<int16_t>();
     if (cn == 3 && interp == 0) remap_u8_kernel<3, 0><<<g, b, 0, c->stream>>>(src, sH, sW, mapx, mapy, dH, dW, xshift, tab, dst);

@@ -800,12 +800,9 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
 
 bool sweep_plain_launch()
 {
-    static const bool v = [] {
-        const char *e = getenv("B2S_SWEEP_COOPERATIVE");
-        if (e) return atoi(e) == 0;
-        return getenv("CUDA_MPS_PIPE_DIRECTORY") == nullptr; // shared through MPS: other clients' kernels hold SMs we cannot see
-    }();
-    return v;
+    const char *e = getenv("B2S_SWEEP_COOPERATIVE");
+    if (e) return atoi(e) == 0;
+    return getenv("CUDA_MPS_PIPE_DIRECTORY") == nullptr; // shared through MPS: other clients' kernels hold SMs we cannot see
 }
 
 template <int NP, bool PAD, int JW, int R> cudaError_t launch_vsweep_t(b2s_ctx *c, const VsArgs &a, int G, size_t smem)

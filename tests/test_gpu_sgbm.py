@@ -358,3 +358,15 @@ def test_cost_domain_is_checked(handle, schedule, monkeypatch):
     ref = osgbm.sgbm_compute(l, r, want_volumes=True, **ok)
     assert ref["C"].min() >= 0
     assert np.array_equal(cb.StereoSGBM(handle=handle, **ok).compute(l, r), ref["disp"])  # (the failed call cleared the sticky flag)
+
+
+def test_cooperative_sweep_launch(handle, monkeypatch):
+    """B2S_SWEEP_COOPERATIVE=1 (automatic under MPS): the lock-step sweep is launched cooperatively, so the driver guarantees the
+    co-residency its spin-waits need; same results."""
+    monkeypatch.setenv("B2S_SWEEP_COOPERATIVE", "1")
+    l, r, _ = synth.rectified_pair(120, 700, 128, seed=9)
+    p = dict(min_disparity=0, num_disparities=128, block_size=5, P1=600, P2=2400, disp12_max_diff=1, uniqueness_ratio=5,
+             speckle_window_size=100, speckle_range=2, mode=1)
+    ref = osgbm.sgbm_compute(l, r, want_volumes=True, **p)
+    got = cb.StereoSGBM(handle=handle, **p).compute(l, r)
+    assert np.array_equal(handle.fetch_volume(1), ref["S"]) and np.array_equal(got, ref["disp"])

@@ -80,6 +80,9 @@ SIGNATURES = {
                                   ctypes.POINTER(c_double), c_int, c_int, c_void_p]),
     "b2s_set_option": (c_int, [c_void_p, c_int, c_int]),
     "b2s_build_hash": (ctypes.c_char_p, []),
+    "b2s_depth_to_point_cloud": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, ctypes.POINTER(c_double), c_int, c_void_p, ctypes.c_ulonglong,
+                                         ctypes.POINTER(ctypes.c_ulonglong)]),
+    "b2s_point_cloud_to_depth": (c_int, [c_void_p, c_void_p, ctypes.c_ulonglong, ctypes.POINTER(c_double), c_int, c_int, c_double, c_void_p]),
     "b2s_volume_dims": (c_int, [c_void_p] + [ctypes.POINTER(c_int)] * 4),
     "b2s_debug_fetch": (c_int, [c_void_p, c_int, c_void_p, c_size_t]),
     "b2s_timings": (c_int, [c_void_p, ctypes.POINTER(Timing)]),

@@ -104,7 +104,7 @@ int b2s_destroy(b2s_handle c)
     DevBuf *bufs[] = {&c->left, &c->right, &c->planesL, &c->planesR, &c->C, &c->S, &c->S2, &c->raw, &c->disp16, &c->disp2key, &c->labels,
                       &c->sizes, &c->med, &c->dispf, &c->sleft, &c->sright, &c->sdispf, &c->agg_ho, &c->agg_errbuf, &c->map1x, &c->map1y, &c->map2x, &c->map2y, &c->vmask, &c->umapx, &c->umapy,
                       &c->und_xy, &c->und_fxy, &c->img1, &c->img2, &c->rect1, &c->rect2, &c->und1, &c->dispfinal, &c->rdepth,
-                      &c->udepth, &c->lanczos_tab, &c->lanczos_tabp, &c->stage_f32, &c->dkey, &c->ddepth, &c->pkey, &c->pin, &c->pout};
+                      &c->udepth, &c->lanczos_tab, &c->lanczos_tabp, &c->stage_f32, &c->dkey, &c->ddepth, &c->pkey, &c->pin, &c->pout, &c->cl_pts, &c->cl_aux};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -404,6 +404,51 @@ int b2s_project_depth(b2s_handle c, const double *depth2, int W2, int H2, double
     CK(c, cudaMemcpyAsync(c->pin.p, depth2, n2 * 8, cudaMemcpyDefault, c->stream));
     CK(c, launch_project_depth(c, c->pin.as<double>(), W2, H2, rate, K2inv, T, K1, W1, H1, c->pkey.as<unsigned long long>(), c->pout.as<double>()));
     CK(c, cudaMemcpyAsync(out, c->pout.p, n1 * 8, cudaMemcpyDefault, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return B2S_OK;
+}
+
+int b2s_depth_to_point_cloud(b2s_handle c, const double *depth, int H, int W, double rate, const double Kinv[9], int with_uv, double *out,
+                             unsigned long long capacity, unsigned long long *n_out)
+{
+    if (!c || !depth || !Kinv || !out || !n_out) return B2S_EINVAL;
+    if (W <= 0 || H <= 0 || !(rate > 0) || rate > 64) return fail(c, B2S_EINVAL, "b2s_depth_to_point_cloud: bad size or rate");
+    CK(c, cudaSetDevice(c->device));
+    const int cols = with_uv ? 5 : 3;
+    const int Hu = rate == 1.0 ? H : (int)nearbyint(H * rate), Wu = rate == 1.0 ? W : (int)nearbyint(W * rate);
+    if (Hu <= 0 || Wu <= 0) return fail(c, B2S_EINVAL, "b2s_depth_to_point_cloud: rate %g leaves no image", rate);
+    const unsigned long long maxn = (unsigned long long)Hu * Wu, cap = capacity < maxn ? capacity : maxn;
+    CK(c, c->pin.ensure((size_t)H * W * 8));
+    CK(c, c->cl_pts.ensure((size_t)(cap ? cap : 1) * cols * 8));
+    CK(c, c->cl_aux.ensure((size_t)Hu * 4 + 256 + ((size_t)Hu + 1) * 8));
+    unsigned *rowcount = c->cl_aux.as<unsigned>();
+    unsigned long long *rowoff = (unsigned long long *)((char *)c->cl_aux.p + (((size_t)Hu * 4 + 255) / 256) * 256);
+    CK(c, cudaMemcpyAsync(c->pin.p, depth, (size_t)H * W * 8, cudaMemcpyDefault, c->stream));
+    int hu = 0;
+    CK(c, launch_depth_to_cloud(c, c->pin.as<double>(), H, W, rate, Kinv, cols, c->cl_pts.as<double>(), cap, rowcount, rowoff, &hu));
+    unsigned long long n = 0;
+    CK(c, cudaMemcpyAsync(&n, rowoff + hu, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    *n_out = n;
+    if (n > capacity) return fail(c, B2S_ESIZE, "b2s_depth_to_point_cloud: %llu points, capacity %llu", n, capacity);
+    if (n) CK(c, cudaMemcpy(out, c->cl_pts.p, (size_t)n * cols * 8, cudaMemcpyDefault));
+    return B2S_OK;
+}
+
+int b2s_point_cloud_to_depth(b2s_handle c, const double *points, unsigned long long n, const double K[9], int W, int H, double bg_value, double *out)
+{
+    if (!c || (!points && n) || !K || !out) return B2S_EINVAL;
+    if (W <= 0 || H <= 0) return fail(c, B2S_EINVAL, "b2s_point_cloud_to_depth: bad size");
+    CK(c, cudaSetDevice(c->device));
+    const size_t npx = (size_t)W * H;
+    CK(c, c->cl_pts.ensure((size_t)(n ? n : 1) * 24));
+    CK(c, c->cl_aux.ensure(256));
+    CK(c, c->pkey.ensure(npx * 8));
+    CK(c, c->pout.ensure(npx * 8));
+    if (n) CK(c, cudaMemcpyAsync(c->cl_pts.p, points, (size_t)n * 24, cudaMemcpyDefault, c->stream));
+    CK(c, cudaMemcpyAsync(c->cl_aux.p, K, 72, cudaMemcpyHostToDevice, c->stream));
+    CK(c, launch_cloud_to_depth(c, c->cl_pts.as<double>(), n, c->cl_aux.as<double>(), W, H, c->pkey.as<unsigned long long>(), c->pout.as<double>(), bg_value));
+    CK(c, cudaMemcpyAsync(out, c->pout.p, npx * 8, cudaMemcpyDefault, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return B2S_OK;
 }

@@ -96,6 +96,7 @@ struct b2s_ctx {
     DevBuf lanczos_tabp;                   // the same with rows padded to 144 bytes (remap_lz4_kernel's shared-memory copy)
     bool have_map_params = false;          // rig set by b2s_set_rig_params: rectification evaluates the maps analytically
     b2s_map_params mp_rect1{}, mp_rect2{};
+    DevBuf cl_pts, cl_aux;                 // depth_to_point_cloud / point_cloud_to_depth: points, row counts + offsets + K
     DevBuf pkey, pin, pout;                // project_depth: winner key per target pixel, staged input / output
     DevBuf dkey, ddepth;                   // distort_depth: winner index per target pixel (+ the 12 coefficients); (H1,W1) f64 result
     bool have_cam1 = false;
@@ -138,5 +139,10 @@ cudaError_t launch_gen_maps(b2s_ctx *c, const b2s_map_params &p, float *mapx, fl
 // resize.cu
 cudaError_t launch_resize_u8(b2s_ctx *c, const uint8_t *src, int sH, int sW, int cn, uint8_t *dst, int dH, int dW);
 cudaError_t launch_resize_f32(b2s_ctx *c, const float *src, int sH, int sW, float *dst, int dH, int dW, float mul, float div);
+// cloud.cu
+cudaError_t launch_depth_to_cloud(b2s_ctx *c, const double *d_depth, int H, int W, double rate, const double *Kinv, int cols, double *d_out,
+                                  unsigned long long capacity, unsigned *d_rowcount, unsigned long long *d_rowoff, int *Hu_out);
+cudaError_t launch_cloud_to_depth(b2s_ctx *c, const double *d_pts, unsigned long long n, const double *d_K, int W, int H, unsigned long long *d_key,
+                                  double *d_out, double bg);
 cudaError_t launch_depth_bare(b2s_ctx *c, const float *d_disp, double *d_depth);
 cudaError_t launch_unrectify(b2s_ctx *c, const double *d_depth, double *d_out);

@@ -203,6 +203,17 @@ int b2s_undistort_img(b2s_handle h, const uint8_t *img1, int cn, uint8_t *out);
 #define B2S_OPT_FUSE_WTA 2
 #define B2S_OPT_AGG_SCHEDULE 3
 #define B2S_OPT_MAX_SIZE 4
+/* calibrating/utils.py:213-250 depth_to_point_cloud: the non-zero pixels of `depth` ((H,W) f64 host; the caller applies the
+ * reference's uint16 -> float32(depth / 1000) rule first), optionally nearest-neighbour up-sampled by `rate` (cv2.resize
+ * INTER_NEAREST to (round(W*rate), round(H*rate))), un-projected with Kinv = inv(K) in NumPy's row-major order:
+ * out[k] = Kinv @ (u z, v z, z) [+ (u, v) when with_uv], u = column / rate.  `capacity` = rows of `out`; *n_out = points found
+ * (B2S_ESIZE when it exceeds the capacity).  z within 1e-12 of the reference (its 3x3 product goes through BLAS). */
+int b2s_depth_to_point_cloud(b2s_handle h, const double *depth, int H, int W, double rate, const double Kinv[9], int with_uv, double *out,
+                             unsigned long long capacity, unsigned long long *n_out);
+/* calibrating/utils.py:254-317 point_cloud_to_depth (= point_cloud_to_arr2d without values): points (n,3) f64 projected with K,
+ * rounded half-to-even to the pixel grid of (W,H); of the points landing on a pixel the smallest z survives (the reference
+ * writes in the order of descending z), pixels without a point get bg_value. */
+int b2s_point_cloud_to_depth(b2s_handle h, const double *points, unsigned long long n, const double K[9], int W, int H, double bg_value, double *out);
 int b2s_set_option(b2s_handle h, int option, int value);
 /* sha256 (first 16 hex digits) over the CUDA sources this library was built from (calibrating_b200/build.py); ties a
  * profile under profiles/ to the binary it was measured on. */

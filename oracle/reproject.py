@@ -47,3 +47,38 @@ def project_cam2_depth(K1, xy1, K2, depth2, T, interpolation=1.5):
     ok = (xs >= 0) & (xs < w) & (ys >= 0) & (ys < h)
     out[ys[ok], xs[ok]] = xyz[ok, 2]
     return out
+
+
+def depth_to_point_cloud(depth, K, interpolation_rate=1, return_xyzuv=False):
+    """calibrating/utils.py:213-250 restated."""
+    K = np.float64(K)
+    y, x = depth.shape
+    if depth.dtype == np.uint16:
+        depth = np.float32(depth / 1000.0)
+    if interpolation_rate == 1:
+        mask = depth != 0
+        vs, us = np.mgrid[:y, :x][:, mask]
+        pts = (np.array([us, vs, np.ones_like(us)]) * depth[mask]).T
+    else:
+        y_, x_ = int(round(y * interpolation_rate)), int(round(x * interpolation_rate))
+        depth_ = cv2.resize(depth, (x_, y_), interpolation=cv2.INTER_NEAREST)
+        mask = depth_ != 0
+        vs, us = np.mgrid[:y_, :x_][:, mask] / interpolation_rate
+        pts = (np.array([us, vs, np.ones_like(us)]) * depth_[mask]).T
+    cloud = (np.linalg.inv(K) @ pts.T).T
+    return np.concatenate([cloud, us[:, None], vs[:, None]], -1) if return_xyzuv else cloud
+
+
+def point_cloud_to_depth(points, K, xy):
+    """calibrating/utils.py:254-317 restated (values=None, bg_value=0)."""
+    xyz = np.float64(points) @ np.float64(K).T
+    with np.errstate(all="ignore"):
+        xyz[:, :2] /= xyz[:, 2:]
+    xyz = xyz[np.argsort(-xyz[:, 2])]
+    w, h = xy
+    out = np.ones((h, w), xyz.dtype) * 0
+    with np.errstate(all="ignore"):
+        xs, ys = np.int32(xyz[:, :2].round()).T
+    ok = (xs >= 0) & (xs < w) & (ys >= 0) & (ys < h)
+    out[ys[ok], xs[ok]] = xyz[ok, 2]
+    return out

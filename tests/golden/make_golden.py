@@ -116,6 +116,19 @@ def main():
         depth1 = cam1.project_cam2_depth(cam2, depth2, T=T)
     np.savez_compressed(os.path.join(HERE, "rig320_project.npz"), depth2=depth2, T=T, depth1=depth1,
                         rate=calibrating.utils._get_appropriate_interpolation_rate(cam1, cam2, 1.5))
+    # --- case F: utils.depth_to_point_cloud / point_cloud_to_depth (utils.py:213-317) of the real reference on a small seeded
+    # depth image: rate 1 on float64 metres, rate 1.5 on uint16 millimetres with (u, v) appended, and the z-buffered way back
+    rng = np.random.default_rng(11)
+    Kc = np.float64([[210.0, 0, 81.5], [0, 209.0, 58.25], [0, 0, 1]])
+    dm = rng.random((120, 160)) * 2.5 + 0.4
+    dm[rng.random((120, 160)) < 0.25] = 0
+    d16 = np.uint16(dm * 1000)
+    pc1 = calibrating.utils.depth_to_point_cloud(dm, Kc)
+    pc2 = calibrating.utils.depth_to_point_cloud(d16, Kc, interpolation_rate=1.5, return_xyzuv=True)
+    Rc = cv2.Rodrigues(np.float64([0.03, -0.08, 0.02]))[0]
+    moved = pc1 @ Rc.T + np.float64([0.05, -0.02, 0.1])
+    back = calibrating.utils.point_cloud_to_depth(moved.copy(), Kc, (160, 120))
+    np.savez_compressed(os.path.join(HERE, "cloud_small.npz"), K=Kc, depth=dm, depth16=d16, cloud_rate1=pc1, xyzuv_rate15=pc2, moved=moved, depth_back=back)
     # --- case C: raw cv2.StereoSGBM outputs on a small rectified pair, MODE_SGBM / MODE_HH / MODE_HH4 (pins oracle/sgbm_ref.c)
     l, r, _ = synth.rectified_pair(96, 200, 48, seed=3)
     for mode, name in ((0, "sgbm"), (1, "hh"), (3, "hh4")):

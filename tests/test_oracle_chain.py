@@ -62,3 +62,12 @@ def test_project_cam2_depth_matches_reference(golden_dir):
     got = reproject.project_cam2_depth(K(rig["cam1"]), rig["cam1"]["xy"], K(rig["cam2"]), g["depth2"], g["T"])
     assert np.array_equal(got, g["depth1"])
     assert abs(reproject.interpolation_rate(K(rig["cam1"]), K(rig["cam2"])) - float(g["rate"])) == 0
+
+
+def test_point_cloud_restatements_match_reference(golden_dir):
+    """oracle.reproject.depth_to_point_cloud / point_cloud_to_depth against the real reference's utils.py:213-317 outputs."""
+    from oracle import reproject
+    g = np.load(os.path.join(golden_dir, "cloud_small.npz"))
+    assert np.array_equal(reproject.depth_to_point_cloud(g["depth"], g["K"]), g["cloud_rate1"])
+    assert np.array_equal(reproject.depth_to_point_cloud(g["depth16"], g["K"], 1.5, True), g["xyzuv_rate15"])
+    assert np.array_equal(reproject.point_cloud_to_depth(g["moved"], g["K"], (160, 120)), g["depth_back"])

@@ -139,8 +139,7 @@ int b2s_set_sgbm_params(b2s_handle c, const b2s_sgbm_params *p)
 {
     if (!c || !p) return B2S_EINVAL;
     if (p->num_disparities <= 0) return fail(c, B2S_EINVAL, "numDisparities must be > 0 (got %d)", p->num_disparities);
-    if (p->num_disparities > 256) return fail(c, B2S_EINVAL, "numDisparities > 256 is not supported yet (got %d)", p->num_disparities);
-    if (p->min_disparity < 0) return fail(c, B2S_EINVAL, "negative minDisparity is not supported (got %d)", p->min_disparity);
+    if (p->num_disparities > 512) return fail(c, B2S_EINVAL, "numDisparities > 512 is not supported (got %d)", p->num_disparities);
     if (p->mode != 0 && p->mode != 1 && p->mode != 3)
         return fail(c, B2S_EINVAL, "mode must be 0 (MODE_SGBM), 1 (MODE_HH) or 3 (MODE_HH4), got %d (MODE_SGBM_3WAY = 2 depends on cv2's thread count and is not offered)", p->mode);
     if (p->cost != 0 && p->cost != 1) return fail(c, B2S_EINVAL, "cost must be 0 (Birchfield-Tomasi, cv2) or 1 (census), got %d", p->cost);
@@ -169,7 +168,7 @@ static int make_geom(b2s_ctx *c, int H, int W, int cn)
     g.minD = p.min_disparity;
     g.maxD = g.minD + p.num_disparities;
     g.D = p.num_disparities;
-    g.layout = agg_wave_selected(c, p.mode) ? 1 : 0;
+    g.layout = (agg_wave_selected(c, p.mode) && g.D <= 256) ? 1 : 0;
     g.NP = g.layout == 1 ? 2 * ((g.D + 127) / 128) : (g.D + 63) / 64; // the wavefront kernel takes whole blocks of 128 disparities
     g.Dp = 64 * g.NP;
     int bs = p.block_size > 0 ? p.block_size : 5;
@@ -180,15 +179,15 @@ static int make_geom(b2s_ctx *c, int H, int W, int cn)
     g.P1 = p.P1 > 0 ? p.P1 : 2;
     g.P2 = p.P2 > 0 ? p.P2 : 5;
     if (g.P2 < g.P1 + 1) g.P2 = g.P1 + 1;
-    g.minX1 = g.maxD;
-    g.width1 = W - g.maxD;
+    g.minX1 = g.maxD > 0 ? g.maxD : 0;                        // A.1: minX1 = max(maxD, 0), maxX1 = W + min(minD, 0)
+    g.width1 = (W + (g.minD < 0 ? g.minD : 0)) - g.minX1;
     g.invalid = (g.minD - 1) * 16;
     g.speckle_window = p.speckle_window_size;
     g.speckle_range = p.speckle_range;
     g.mode = p.mode;
-    if (W - g.maxD <= g.SW2) return fail(c, B2S_ESIZE, "input images are too small for your window size and max disparity");
+    if (W - g.maxD <= g.SW2 || g.width1 <= 0) return fail(c, B2S_ESIZE, "input images are too small for your window size and max disparity");
     if (g.ftzero > 127) return fail(c, B2S_EINVAL, "preFilterCap %d too large", p.pre_filter_cap);
-    if ((g.layout == 0 ? (64 + 2 * g.SW2 + g.D - 1) / 2 + 2 : (64 + 2 * g.SW2 + g.Dp + 1) / 2) > 168) // shared-memory tile of the cost kernel (sgbm_cost.cu: TX, NRP)
+    if ((g.layout == 0 ? (64 + 2 * g.SW2 + g.D - 1) / 2 + 2 : (64 + 2 * g.SW2 + g.Dp + 1) / 2) > (g.D > 256 ? 296 : 168)) // shared-memory tile of the cost kernel (sgbm_cost.cu: TX, NRP)
         return fail(c, B2S_EINVAL, "blockSize %d is too large for numDisparities %d (supported: blockSize + numDisparities <= 269)", bs, g.D);
     c->g = g;
     size_t npx = (size_t)H * W, vol = (size_t)H * g.width1 * g.Dp * sizeof(int16_t);

@@ -427,6 +427,26 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_vsum_kernel(AggArgs a)
     if (ovf & 0x80008000u) a.err[1] = 1;
 }
 
+// the generic one-direction scan (any direction; the only aggregation kernel instantiated for more than 256 disparities)
+template <int NP, bool PAD, int MODE> cudaError_t launch_generic(b2s_ctx *c, const AggArgs &a)
+{
+    constexpr int STAGE_BYTES = 128 * NP * (MODE == AGG_ACCUM2 ? 3 : (MODE == AGG_ACCUM ? 2 : 1));
+    const int nlines = a.my == 0 ? a.H : a.width1;
+    const size_t smem = (size_t)WARPS * Stages<NP>::value * STAGE_BYTES;
+    static std::once_flag once[64];
+    cudaError_t e = cudaSuccess;
+    std::call_once(once[c->device & 63], [&] { e = cudaFuncSetAttribute(agg_scan_kernel<NP, PAD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    if (e != cudaSuccess) return e;
+    agg_scan_kernel<NP, PAD, MODE><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
+    c->launches++;
+    return cudaGetLastError();
+}
+template <int NP, bool PAD> cudaError_t launch_dir_wide(b2s_ctx *c, const AggArgs &a, int mode, int wta)
+{
+    if (wta != 0 || mode == AGG_ACCUM2) return cudaErrorInvalidValue;
+    return mode == AGG_INIT ? launch_generic<NP, PAD, AGG_INIT>(c, a) : launch_generic<NP, PAD, AGG_ACCUM>(c, a);
+}
+
 template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *c, const AggArgs &a)
 {
     constexpr int STAGE_BYTES = 128 * NP * (MODE == AGG_ACCUM2 ? 3 : (MODE == AGG_ACCUM ? 2 : 1));
@@ -442,12 +462,7 @@ template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *
     } else if constexpr (WTA != 0) {
         return cudaErrorInvalidValue; // the generic scan has no fused winner-take-all (launch_aggregate never asks for one)
     } else {
-        const size_t smem = (size_t)WARPS * Stages<NP>::value * STAGE_BYTES;
-        static std::once_flag once[64];
-        cudaError_t e = cudaSuccess;
-        std::call_once(once[c->device & 63], [&] { e = cudaFuncSetAttribute(agg_scan_kernel<NP, PAD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
-        if (e != cudaSuccess) return e;
-        agg_scan_kernel<NP, PAD, MODE><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
+        return launch_generic<NP, PAD, MODE>(c, a);
     }
     c->launches++;
     return cudaGetLastError();
@@ -469,6 +484,11 @@ cudaError_t launch_dir_np(b2s_ctx *c, const AggArgs &a, int mode, int wta = 0)
     case 2: return pad ? launch_dir<2, true>(c, a, mode, wta) : launch_dir<2, false>(c, a, mode, wta);
     case 3: return pad ? launch_dir<3, true>(c, a, mode, wta) : launch_dir<3, false>(c, a, mode, wta);
     case 4: return pad ? launch_dir<4, true>(c, a, mode, wta) : launch_dir<4, false>(c, a, mode, wta);
+    // 257 .. 512 disparities: the generic per-direction scan only (launch_aggregate selects the legacy schedule)
+    case 5: return pad ? launch_dir_wide<5, true>(c, a, mode, wta) : launch_dir_wide<5, false>(c, a, mode, wta);
+    case 6: return pad ? launch_dir_wide<6, true>(c, a, mode, wta) : launch_dir_wide<6, false>(c, a, mode, wta);
+    case 7: return pad ? launch_dir_wide<7, true>(c, a, mode, wta) : launch_dir_wide<7, false>(c, a, mode, wta);
+    case 8: return pad ? launch_dir_wide<8, true>(c, a, mode, wta) : launch_dir_wide<8, false>(c, a, mode, wta);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -864,7 +884,7 @@ template <int NP, bool PAD> cudaError_t launch_vsweep_j(b2s_ctx *c, VsArgs &a, i
 int vsweep_cols(const b2s_ctx *c)
 {
     const SgbmGeom &g = c->g;
-    if (getenv("B2S_AGG_LEGACY")) return 0;
+    if (getenv("B2S_AGG_LEGACY") || g.NP > 4) return 0; // (more than 256 disparities: the generic scans only)
     int n = (g.width1 + c->num_sms - 1) / c->num_sms;
     if (n < 8) n = g.width1 < 8 ? g.width1 : 8;
     if (const char *e = getenv("B2S_VSWEEP_COLS")) { // test hook: force narrow strips so that small images span several CTAs
@@ -1046,11 +1066,11 @@ cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
         // MODE_HH4 (cv2 pass 1: (+1,0) (0,+1); pass 2: (-1,0) (0,-1)): the vertical paths do not couple columns, so each is one
         // launch of the generic scan with a warp per column; the horizontal ones use the fast row scan
         static const int dirs4[4][2] = {{1, 0}, {0, 1}, {0, -1}, {-1, 0}};
-        c->agg_legacy = false;
+        c->agg_legacy = g.NP > 4;
         for (int i = 0; i < 4; i++) {
             a.mx = dirs4[i][0];
             a.my = dirs4[i][1];
-            const int wta = (i == 3 && can_fuse) ? (c->keep_volumes ? 2 : 1) : 0;
+            const int wta = (i == 3 && can_fuse && g.NP <= 4) ? (c->keep_volumes ? 2 : 1) : 0;
             if ((e = launch_dir_np(c, a, i == 0 ? AGG_INIT : AGG_ACCUM, wta)) != cudaSuccess) return e;
             if (wta) c->wta_fused = true;
             mark();

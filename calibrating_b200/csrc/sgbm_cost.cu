@@ -67,6 +67,7 @@ constexpr int TX = 64;
 constexpr int COST_THREADS = 256;
 constexpr int BT_BIAS = 256;
 constexpr int NRP_MAX = (TX + 2 * 5 + 256) / 2 + 3; // packed right-pixel pairs per copy; compile-time strides (template NRP): 104 for D <= 128, NRP_MAX for D <= 256
+constexpr int NRP_WIDE = (TX + 2 * 5 + 512) / 2 + 3; // ... and for D <= 512
 
 // LAYOUT 1 (block layout of the wavefront kernel: a word = disparities (d, d+8)): the right-pixel table holds ONE entry per
 // reversed index m = (pixel m, pixel m+8) instead of the two alignment copies of neighbouring pairs; 2*NRP entries per plane.
@@ -293,8 +294,8 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
         planes_kernel<1><<<pg, pb, 0, c->stream>>>(d_right, PR, g.H, g.W, g.ftzero);
     }
     const int TXH = TX + 2 * g.SW2, need = g.layout == 0 ? (TXH + g.D - 1) / 2 + 2 : (TXH + g.Dp + 1) / 2;
-    if (need > NRP_MAX) return cudaErrorInvalidValue; // (b2s_api.cu rejects such block sizes with a message)
-    const int nrp = need <= 104 ? 104 : NRP_MAX;
+    if (need > NRP_WIDE) return cudaErrorInvalidValue; // (b2s_api.cu rejects such block sizes with a message)
+    const int nrp = need <= 104 ? 104 : (need <= NRP_MAX ? NRP_MAX : NRP_WIDE);
     size_t smem = (size_t)NPL * TXH * sizeof(uint4) + (size_t)NPL * 2 * nrp * sizeof(uint4) + (size_t)TXH * g.Dp * sizeof(int16_t);
     dim3 cg((g.width1 + TX - 1) / TX, g.H);
     // row sums: into S (free until aggregation starts), or into S2 when the first horizontal scan takes over the vertical half of
@@ -321,7 +322,8 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
     };
     cudaError_t e;
     if (g.layout == 0) {
-        if (g.cn == 3) e = nrp == 104 ? launch(pixcost_hsum_kernel<3, 104, 0>) : launch(pixcost_hsum_kernel<3, NRP_MAX, 0>);
+        if (nrp == NRP_WIDE) e = g.cn == 3 ? launch(pixcost_hsum_kernel<3, NRP_WIDE, 0>) : launch(pixcost_hsum_kernel<1, NRP_WIDE, 0>);
+        else if (g.cn == 3) e = nrp == 104 ? launch(pixcost_hsum_kernel<3, 104, 0>) : launch(pixcost_hsum_kernel<3, NRP_MAX, 0>);
         else e = nrp == 104 ? launch(pixcost_hsum_kernel<1, 104, 0>) : launch(pixcost_hsum_kernel<1, NRP_MAX, 0>);
     } else {
         if (g.cn == 3) e = nrp == 104 ? launch(pixcost_hsum_kernel<3, 104, 1>) : launch(pixcost_hsum_kernel<3, NRP_MAX, 1>);

@@ -330,6 +330,10 @@ cudaError_t launch_wta(b2s_ctx *c)
     case 2: B2S_WTA(2) break;
     case 3: B2S_WTA(3) break;
     case 4: B2S_WTA(4) break;
+    case 5: B2S_WTA(5) break;
+    case 6: B2S_WTA(6) break;
+    case 7: B2S_WTA(7) break;
+    case 8: B2S_WTA(8) break;
     default: return cudaErrorInvalidValue;
     }
 #undef B2S_WTA

@@ -46,7 +46,8 @@ def sgbm_compute(left, right, *, min_disparity=0, num_disparities=16, block_size
     prm = SgbmParams(min_disparity, num_disparities, block_size, P1, P2, disp12_max_diff,
                      pre_filter_cap, uniqueness_ratio, speckle_window_size, speckle_range, mode, cost)
     disp = np.empty((H, W), np.int16)
-    width1 = W - (min_disparity + num_disparities)
+    maxd = min_disparity + num_disparities
+    width1 = (W + min(min_disparity, 0)) - max(maxd, 0)  # maxX1 - minX1
     C = S = raw = None
     if want_volumes and width1 > 0:
         C = np.empty((H, width1, num_disparities), np.int16)

@@ -8,7 +8,7 @@
  * MODE_SGBM=0 / MODE_HH=1), followed by medianBlur(3) and filterSpeckles inside StereoSGBM::compute.
  * The source is not vendored under /root/reference; this file restates the published algorithm as
  * specified in SURVEY.md Appendix A and is pinned by differential tests against the installed cv2
- * (tests/test_oracle_vs_cv2.py) and by the committed golden vectors in tests/golden/.
+ * (tests/test_oracle.py) and by the committed golden vectors in tests/golden/.
  *
  * Build: gcc -O2 -shared -fPIC -o oracle/_build/libsgbm_ref.so oracle/sgbm_ref.c   (oracle/build.py)
  */
@@ -145,7 +145,8 @@ void oracle_filter_speckles(int16_t *img, int H, int W, int newVal, int maxSpeck
  * Full StereoSGBM::compute.  left/right: (H,W,cn) uint8.  disp: (H,W) int16 = 16*disparity.
  * Optional outputs (NULL to skip): C_out, S_out: (H,width1,D) int16;  raw_out: (H,W) int16 disparity before
  * median/speckle.  Returns 0, or -1 for the cv2 precondition failure (W - maxD > SW2 violated), -2 for
- * unsupported parameters (negative min_disparity is not restated).
+ * unsupported parameters.  Negative min_disparity (minX1 = max(maxD, 0), maxX1 = W + min(minD, 0), A.1) is covered and pinned
+ * against cv2 in tests/test_oracle.py.
  */
 int oracle_sgbm_compute(const uint8_t *left, const uint8_t *right, int H, int W, int cn,
                         const sgbm_params *prm, int16_t *disp, int16_t *C_out, int16_t *S_out, int16_t *raw_out)
@@ -159,7 +160,6 @@ int oracle_sgbm_compute(const uint8_t *left, const uint8_t *right, int H, int W,
     int d12 = prm->disp12_max_diff > 0 ? prm->disp12_max_diff : 1;
     int P1 = prm->P1 > 0 ? prm->P1 : 2;
     int P2 = imax(prm->P2 > 0 ? prm->P2 : 5, P1 + 1);
-    if (minD < 0) return -2;
     if (prm->mode != 0 && prm->mode != 1 && prm->mode != 3) return -2; /* MODE_SGBM_3WAY depends on cv2's thread count: not restated */
     int minX1 = imax(maxD, 0), maxX1 = W + imin(minD, 0);
     int D = maxD - minD, width1 = maxX1 - minX1;

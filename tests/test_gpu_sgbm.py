@@ -370,3 +370,39 @@ def test_cooperative_sweep_launch(handle, monkeypatch):
     ref = osgbm.sgbm_compute(l, r, want_volumes=True, **p)
     got = cb.StereoSGBM(handle=handle, **p).compute(l, r)
     assert np.array_equal(handle.fetch_volume(1), ref["S"]) and np.array_equal(got, ref["disp"])
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_negative_min_disparity(handle, seed):
+    """cv2 accepts a negative minDisparity (the search range reaches to the right of the left pixel); so does the engine: C, S and
+    the disparity equal the oracle's, which is pinned against cv2 for these parameters (tests/test_oracle.py)."""
+    rng = np.random.default_rng(700 + seed)
+    c = _case(rng, minD=int(rng.choice([-1, -3, -16, -40, -64, -130])))
+    l, r, _ = synth.rectified_pair(c["h"], c["w"] + 140, c["p"]["num_disparities"], seed, c["cn"])
+    if seed % 3 == 0:
+        r = np.roll(r, -int(rng.integers(1, 12)), axis=1)  # true disparities on both sides of zero
+    ref = osgbm.sgbm_compute(l, r, want_volumes=True, **c["p"])
+    got = cb.StereoSGBM(handle=handle, **c["p"]).compute(l, r)
+    assert np.array_equal(handle.fetch_volume(0), ref["C"]), "cost volume"
+    assert np.array_equal(handle.fetch_volume(1), ref["S"]), "aggregated volume"
+    assert np.array_equal(got, ref["disp"])
+
+
+@pytest.mark.parametrize("D,mode,cn,bs", [(300, 1, 1, 5), (384, 0, 3, 3), (512, 1, 3, 7), (260, 3, 1, 9), (512, 0, 1, 11)])
+def test_more_than_256_disparities(handle, D, mode, cn, bs):
+    """cv2 takes any numDisparities; above 256 the engine runs the generic one-scan-per-direction schedule (NP = 5..8 packed
+    registers per lane).  Bit-exact against the oracle and, live, against cv2."""
+    cv2 = pytest.importorskip("cv2")
+    l, r, _ = synth.rectified_pair(40, D + 120, D, seed=D, cn=cn)
+    p = dict(min_disparity=2, num_disparities=D, block_size=bs, P1=8 * cn * bs * bs, P2=32 * cn * bs * bs, disp12_max_diff=1, uniqueness_ratio=5,
+             speckle_window_size=30, speckle_range=2, mode=mode)
+    ref = osgbm.sgbm_compute(l, r, want_volumes=True, **p)
+    got = cb.StereoSGBM(handle=handle, **p).compute(l, r)
+    assert np.array_equal(handle.fetch_volume(0), ref["C"]), "cost volume"
+    assert np.array_equal(handle.fetch_volume(1), ref["S"]), "aggregated volume"
+    assert np.array_equal(got, ref["disp"])
+    live = cv2.StereoSGBM_create(minDisparity=2, numDisparities=D, blockSize=bs, P1=p["P1"], P2=p["P2"], disp12MaxDiff=1, uniquenessRatio=5,
+                                 speckleWindowSize=30, speckleRange=2, mode=mode).compute(l, r)
+    assert np.array_equal(got, live)
+    with pytest.raises(ValueError, match="numDisparities > 512"):
+        cb.StereoSGBM(handle=handle, **dict(p, num_disparities=528)).compute(np.zeros((8, 700), np.uint8), np.zeros((8, 700), np.uint8))

@@ -136,3 +136,21 @@ def test_resize_restatement_vs_cv2(hw):
     d[rng.random((nh, nw)) < 0.2] = 0
     assert np.abs(resize.resize_f32(d, h, w) - cv2.resize(d, (w, h), interpolation=cv2.INTER_LINEAR)).max() <= 200 * 1e-6
     assert resize.scaled_size(480, 640, 1000) == (480, 640)
+
+
+@pytest.mark.parametrize("minD", [-1, -3, -16, -40, -64])
+def test_negative_min_disparity_vs_cv2(minD):
+    """SURVEY.md Appendix A.1 left negative minDisparity unverified (minX1 = max(maxD, 0), maxX1 = W + min(minD, 0)); the reference
+    has the matching negative-shift branch (stereo_camera.py:236-240).  The restatement equals cv2 there too, including
+    maxD < 0 (the whole disparity range to the right)."""
+    for mode in (0, 1, 3):
+        for D, cn in ((16, 1), (48, 3), (70, 1)):
+            l, r, _ = synth.rectified_pair(30, 180, 48, seed=3 + D, cn=cn)
+            if (minD + D) % 2:
+                l = np.random.default_rng(1).integers(0, 256, l.shape, dtype=np.uint8)
+            kw = dict(minDisparity=minD, numDisparities=D, blockSize=5, P1=8 * cn * 25, P2=32 * cn * 25, disp12MaxDiff=1, uniquenessRatio=5,
+                      speckleWindowSize=20, speckleRange=2, mode=mode)
+            ref = cv2.StereoSGBM_create(**kw).compute(l, r)
+            got = osgbm.sgbm_compute(l, r, min_disparity=minD, num_disparities=D, block_size=5, P1=8 * cn * 25, P2=32 * cn * 25, disp12_max_diff=1,
+                                     uniqueness_ratio=5, speckle_window_size=20, speckle_range=2, mode=mode)
+            assert np.array_equal(got, ref), (minD, mode, D, cn)

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 OUT = os.path.join(PKG, "libb2s.so")
-SOURCES = ["b2s_api.cu", "sgbm_cost.cu", "sgbm_agg.cu", "sgbm_wave.cu", "sgbm_post.cu", "remap.cu", "resize.cu", "cloud.cu"]
+SOURCES = ["b2s_api.cu", "sgbm_cost.cu", "sgbm_agg.cu", "sgbm_wave.cu", "sgbm_sweep6.cu", "sgbm_post.cu", "remap.cu", "resize.cu", "cloud.cu"]
 HEADERS = [os.path.join(CSRC, "b2s_internal.h"), os.path.join(CSRC, "sgm_common.cuh"), os.path.join(ROOT, "include", "b2s.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

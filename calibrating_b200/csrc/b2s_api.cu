@@ -168,8 +168,13 @@ static int make_geom(b2s_ctx *c, int H, int W, int cn)
     g.minD = p.min_disparity;
     g.maxD = g.minD + p.num_disparities;
     g.D = p.num_disparities;
+    g.mode = p.mode;
+    g.minX1 = g.maxD > 0 ? g.maxD : 0;                        // A.1: minX1 = max(maxD, 0), maxX1 = W + min(minD, 0)
+    g.width1 = (W + (g.minD < 0 ? g.minD : 0)) - g.minX1;
+    // the block layout: the wavefront schedule, or the default schedule when its six-path sweep applies (sgbm_sweep6.cu)
     g.layout = (agg_wave_selected(c, p.mode) && g.D <= 256) ? 1 : 0;
-    g.NP = g.layout == 1 ? 2 * ((g.D + 127) / 128) : (g.D + 63) / 64; // the wavefront kernel takes whole blocks of 128 disparities
+    if (g.layout == 0 && p.cost == 0 && vsweep6_cols(c, g) > 0) g.layout = 1;
+    g.NP = g.layout == 1 ? 2 * ((g.D + 127) / 128) : (g.D + 63) / 64; // the block layout takes whole blocks of 128 disparities
     g.Dp = 64 * g.NP;
     int bs = p.block_size > 0 ? p.block_size : 5;
     g.SW2 = g.SH2 = bs / 2;

@@ -118,6 +118,9 @@ bool agg_fuses_vsum(const b2s_ctx *c);
 bool agg_wave_selected(const b2s_ctx *c, int mode); // the wavefront schedule (sgbm_wave.cu) applies to this matcher mode (decides SgbmGeom::layout)
 // sgbm_wave.cu
 cudaError_t launch_wave(b2s_ctx *c, int ndirs);
+// sgbm_sweep6.cu: the six row-crossing paths of MODE_HH, path-parallel (block layout, 65..128 disparities)
+int vsweep6_cols(const b2s_ctx *c, const SgbmGeom &g); // columns per CTA, 0 = not applicable
+cudaError_t launch_vsweep6(b2s_ctx *c, int n, bool cooperative);
 cudaError_t agg_error_flags(b2s_ctx *c); // creates the handle's device error flags (c->agg_err) on first use
 int agg_poll_error(b2s_ctx *c); // after a stream sync: bit 0 = a wait of the aggregation kernels timed out, bit 1 = cost volume outside the int16 exactness domain
 // sgbm_post.cu

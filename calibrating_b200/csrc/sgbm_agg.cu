@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(WARPS * 32) agg_scan_kernel(AggArgs a)
 // WTA: 0 = store S; 1 = winner-take-all fused (A.5), S not stored; 2 = both (B2S_OPT_KEEP_VOLUMES: S stays fetchable)
 template <int NP> struct HsChunk { static constexpr int px = NP == 1 ? 16 : (NP == 2 ? 8 : 4); }; // pixels per bulk copy (<= 2 KB per source)
 constexpr int HS_SLOTS = 4;                                                                       // ring slots (chunks) per warp
-template <int NP, bool PAD, int MODE, int WTA>
+// BLK: the volumes are in the block layout (SgbmGeom::layout 1: word = disparities (16b+j, 16b+8+j)) instead of pairs (2q, 2q+1)
+template <int NP, bool PAD, int MODE, int WTA, bool BLK = false>
 __global__ void __launch_bounds__(WARPS * 32) agg_hscan_kernel(AggArgs a)
 {
     constexpr int CH = 128 * NP;                       // bytes of one pixel's d-chunk
@@ -215,8 +216,8 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_kernel(AggArgs a)
     uint32_t padmask[NP];
 #pragma unroll
     for (int i = 0; i < NP; i++) {
-        int d0 = (lane * NP + i) * 2;
-        padmask[i] = PAD ? ((d0 >= a.D ? 0x00007FFFu : 0u) | (d0 + 1 >= a.D ? 0x7FFF0000u : 0u)) : 0u;
+        const int d0 = b2s_word_d0(BLK ? 1 : 0, lane * NP + i), d1 = d0 + (BLK ? 8 : 1);
+        padmask[i] = PAD ? ((d0 >= a.D ? 0x00007FFFu : 0u) | (d1 >= a.D ? 0x7FFF0000u : 0u)) : 0u;
     }
     const uint32_t P1v = (uint32_t)a.P1 * 0x10001u, P2mP1v = (uint32_t)(a.P2 - a.P1) * 0x10001u;
     const uint32_t BIG = 0x7FFF7FFFu;
@@ -234,8 +235,8 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_kernel(AggArgs a)
     uint32_t dd[NP], prev[NP], kmin = 0;
 #pragma unroll
     for (int i = 0; i < NP; i++) {
-        const uint32_t d0 = (uint32_t)(lane * NP + i) * 2;
-        dd[i] = d0 | ((d0 + 1) << 16);
+        const uint32_t d0 = (uint32_t)b2s_word_d0(BLK ? 1 : 0, lane * NP + i);
+        dd[i] = d0 | ((d0 + (BLK ? 8 : 1)) << 16);
         prev[i] = 0;
     }
     const int thr = 100 - a.uniq;
@@ -270,16 +271,17 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_kernel(AggArgs a)
         bool bad = false;
 #pragma unroll
         for (int i = 0; i < NP; i++) {
-            const int e = (lane * NP + i) * 2 - best; // d - best of the low half
+            const int e = b2s_word_d0(BLK ? 1 : 0, lane * NP + i) - best; // d - best of the low half; the high half is (BLK ? 8 : 1) further
             // (the low 16 bits do not matter against a multiple of 65536; padded halves, d >= D, are not candidates)
             bad |= ((prev[i] << 16) < Tkey) && ((unsigned)(e + 1) > 2u) && !(PAD && (padmask[i] & 0xFFFFu));
-            bad |= (prev[i] < Tkey) && ((unsigned)(e + 2) > 2u) && !(PAD && (padmask[i] >> 16));
+            bad |= (prev[i] < Tkey) && ((unsigned)(e + (BLK ? 8 : 1) + 1) > 2u) && !(PAD && (padmask[i] >> 16));
         }
         // S(best-1), S(best+1) for the sub-pixel fit: every lane reads the same two halves (broadcast), the recording lane keeps them
-        const uint32_t nb = xbase + (kp & 1) * CH + (uint32_t)min(max(best, 1), a.D - 2) * 2;
+        const int bc = min(max(best, 1), a.D - 2);
+        const uint32_t nb = xbase + (kp & 1) * CH;
         unsigned short lo, hi;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(lo) : "r"(nb - 2) : "memory");
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hi) : "r"(nb + 2) : "memory");
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(lo) : "r"(nb + (uint32_t)b2s_dindex(BLK ? 1 : 0, bc - 1) * 2) : "memory");
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hi) : "r"(nb + (uint32_t)b2s_dindex(BLK ? 1 : 0, bc + 1) * 2) : "memory");
         const bool rej = __any_sync(0xffffffffu, bad);
         const bool rec = lane == (kp & 31);
         my_best = rec ? (rej ? -2 : best) : my_best;
@@ -308,7 +310,8 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_kernel(AggArgs a)
 #pragma unroll
                 for (int i = 0; i < NP; i++) sv[i] = __viaddmin_u16x2(sv[i], s2[i], BIG);
             }
-            sgm_step<NP, PAD>(T, c, L, padmask, P1v, P2mP1v, lane);
+            if constexpr (BLK) sgm_step_b32<NP, PAD>(T, c, L, padmask, P1v, P2mP1v, lane);
+            else sgm_step<NP, PAD>(T, c, L, padmask, P1v, P2mP1v, lane);
 #pragma unroll
             for (int i = 0; i < NP; i++) out[i] = (MODE != AGG_INIT) ? __viaddmin_u16x2(sv[i], L[i], BIG) : L[i];
             if (WTA != 1) stcg_regs<NP>(sp, out);
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_kernel(AggArgs a)
 // re-read of hs rows by neighbouring warps is served by L2.
 template <int NP> struct HvChunk { static constexpr int px = NP == 1 ? 12 : (NP == 2 ? 6 : (NP == 3 ? 4 : 3)); }; // 1.5 KB per hs row
 constexpr int HV_SLOTS = 3;
-template <int NP, bool PAD, int NV>
+template <int NP, bool PAD, int NV, bool BLK = false>
 __global__ void __launch_bounds__(WARPS * 32) agg_hscan_vsum_kernel(AggArgs a)
 {
     constexpr int CH = 128 * NP;
@@ -384,8 +387,8 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_vsum_kernel(AggArgs a)
     uint32_t padmask[NP];
 #pragma unroll
     for (int i = 0; i < NP; i++) {
-        int d0 = (lane * NP + i) * 2;
-        padmask[i] = PAD ? ((d0 >= a.D ? 0x00007FFFu : 0u) | (d0 + 1 >= a.D ? 0x7FFF0000u : 0u)) : 0u;
+        const int d0 = b2s_word_d0(BLK ? 1 : 0, lane * NP + i), d1 = d0 + (BLK ? 8 : 1);
+        padmask[i] = PAD ? ((d0 >= a.D ? 0x00007FFFu : 0u) | (d1 >= a.D ? 0x7FFF0000u : 0u)) : 0u;
     }
     const uint32_t P1v = (uint32_t)a.P1 * 0x10001u, P2mP1v = (uint32_t)(a.P2 - a.P1) * 0x10001u;
 #pragma unroll 1
@@ -417,7 +420,8 @@ __global__ void __launch_bounds__(WARPS * 32) agg_hscan_vsum_kernel(AggArgs a)
             stcg_regs<NP>(cp, c);
 #pragma unroll
             for (int i = 0; i < NP; i++) ovf |= c[i]; // a wrapped block sum (C < 0) has bit 15 of its half set
-            sgm_step<NP, PAD>(T, c, L, padmask, P1v, P2mP1v, lane);
+            if constexpr (BLK) sgm_step_b32<NP, PAD>(T, c, L, padmask, P1v, P2mP1v, lane);
+            else sgm_step<NP, PAD>(T, c, L, padmask, P1v, P2mP1v, lane);
             stcg_regs<NP>(sp, L);
             sp += Dp;
             cp += Dp;
@@ -454,9 +458,19 @@ template <int NP, bool PAD, int MODE, int WTA> cudaError_t launch_scan(b2s_ctx *
     if (a.my == 0 && !c->agg_legacy) {
         // horizontal scans: bulk-copy rings + the fused WTA's exchange buffers + one mbarrier per ring slot
         const size_t smem_h = (size_t)WARPS * HS_SLOTS * (STAGE_BYTES * HsChunk<NP>::px) + (WTA != 0 ? (size_t)WARPS * 2 * 128 * NP : 0) + WARPS * HS_SLOTS * 8;
-        static std::once_flag once_h[64]; // per instantiation and device (the attribute belongs to the device's context)
+        static std::once_flag once_h[64][2]; // per instantiation and device (the attribute belongs to the device's context)
         cudaError_t e = cudaSuccess;
-        std::call_once(once_h[c->device & 63], [&] { e = cudaFuncSetAttribute(agg_hscan_kernel<NP, PAD, MODE, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h); });
+        if constexpr (NP == 2) {
+            if (c->g.layout == 1) { // (the block layout reaches the scans only with NP = 2: the six-path sweep of agg_vsweep6_kernel)
+                std::call_once(once_h[c->device & 63][1], [&] { e = cudaFuncSetAttribute(agg_hscan_kernel<NP, PAD, MODE, WTA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h); });
+                if (e != cudaSuccess) return e;
+                agg_hscan_kernel<NP, PAD, MODE, WTA, true><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem_h, c->stream>>>(a);
+                c->launches++;
+                return cudaGetLastError();
+            }
+        }
+        if (c->g.layout != 0) return cudaErrorInvalidValue;
+        std::call_once(once_h[c->device & 63][0], [&] { e = cudaFuncSetAttribute(agg_hscan_kernel<NP, PAD, MODE, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h); });
         if (e != cudaSuccess) return e;
         agg_hscan_kernel<NP, PAD, MODE, WTA><<<(nlines + WARPS - 1) / WARPS, WARPS * 32, smem_h, c->stream>>>(a);
     } else if constexpr (WTA != 0) {
@@ -496,9 +510,19 @@ cudaError_t launch_dir_np(b2s_ctx *c, const AggArgs &a, int mode, int wta = 0)
 template <int NP, bool PAD, int NV> cudaError_t launch_hscan_vsum_t(b2s_ctx *c, const AggArgs &a)
 {
     const size_t smem = (size_t)WARPS * HV_SLOTS * NV * HvChunk<NP>::px * 128 * NP + WARPS * HV_SLOTS * 8;
-    static std::once_flag once[64]; // per instantiation and device (the attribute belongs to the device's context)
+    static std::once_flag once[64][2]; // per instantiation and device (the attribute belongs to the device's context)
     cudaError_t e = cudaSuccess;
-    std::call_once(once[c->device & 63], [&] { e = cudaFuncSetAttribute(agg_hscan_vsum_kernel<NP, PAD, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    if constexpr (NP == 2) {
+        if (c->g.layout == 1) {
+            std::call_once(once[c->device & 63][1], [&] { e = cudaFuncSetAttribute(agg_hscan_vsum_kernel<NP, PAD, NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+            if (e != cudaSuccess) return e;
+            agg_hscan_vsum_kernel<NP, PAD, NV, true><<<(a.H + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
+            c->launches++;
+            return cudaGetLastError();
+        }
+    }
+    if (c->g.layout != 0) return cudaErrorInvalidValue;
+    std::call_once(once[c->device & 63][0], [&] { e = cudaFuncSetAttribute(agg_hscan_vsum_kernel<NP, PAD, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
     if (e != cudaSuccess) return e;
     agg_hscan_vsum_kernel<NP, PAD, NV><<<(a.H + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(a);
     c->launches++;
@@ -885,6 +909,7 @@ int vsweep_cols(const b2s_ctx *c)
 {
     const SgbmGeom &g = c->g;
     if (getenv("B2S_AGG_LEGACY") || g.NP > 4) return 0; // (more than 256 disparities: the generic scans only)
+    if (g.layout == 1) return vsweep6_cols(c, g);            // block layout: the six-path sweep's strip width
     int n = (g.width1 + c->num_sms - 1) / c->num_sms;
     if (n < 8) n = g.width1 < 8 ? g.width1 : 8;
     if (const char *e = getenv("B2S_VSWEEP_COLS")) { // test hook: force narrow strips so that small images span several CTAs
@@ -939,7 +964,8 @@ cudaError_t launch_vsweep(b2s_ctx *c, int n, int J)
             if ((e = cudaEventCreateWithFlags(evp, cudaEventDisableTiming)) != cudaSuccess) return e;
         } else if ((e = cudaStreamWaitEvent(c->stream, *evp, 0)) != cudaSuccess) return e;
     }
-    switch (g.NP) {
+    if (g.layout == 1) e = launch_vsweep6(c, n, !chained); // (block layout: only reached when vsweep6_cols(c, g) == n > 0)
+    else switch (g.NP) {
     case 1: e = pad ? launch_vsweep_j<1, true>(c, a, G, J) : launch_vsweep_j<1, false>(c, a, G, J); break;
     case 2: e = pad ? launch_vsweep_j<2, true>(c, a, G, J) : launch_vsweep_j<2, false>(c, a, G, J); break;
     case 3: e = pad ? launch_vsweep_j<3, true>(c, a, G, J) : launch_vsweep_j<3, false>(c, a, G, J); break;
@@ -970,7 +996,8 @@ bool agg_wave_selected(const b2s_ctx *c, int mode)
 bool agg_fuses_vsum(const b2s_ctx *c)
 {
     if (getenv("B2S_NO_VSUM_FUSION")) return false;
-    if (c->g.layout != 0) return false;
+    if (c->g.layout != 0 && vsweep6_cols(c, c->g) == 0) return false; // (block layout: only with the six-path sweep schedule)
+    if (c->g.layout != 0 && agg_wave_selected(c, c->g.mode)) return false;
     return c->prm.cost == 0 && c->g.SH2 <= 2 && c->g.mode != 3 && vsweep_cols(c) > 0;
 }
 
@@ -1021,6 +1048,7 @@ cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
     // (sticky: cleared when the buffer is created and by agg_poll_error after it reported, never per launch -- several pairs may be
     // queued on the stream between two polls)
     cudaError_t e;
+    if ((e = wait_timeout_init()) != cudaSuccess) return e;
     if ((e = agg_error_flags(c)) != cudaSuccess) return e;
     a.err = c->agg_err;
     const int thr = 100 - g.uniq;
@@ -1028,7 +1056,7 @@ cudaError_t launch_aggregate(b2s_ctx *c, int *n_launches, cudaEvent_t *marks)
     const bool can_fuse = c->fuse_wta && thr >= 1 && thr <= 100; // (uniquenessRatio >= 100 goes through wta_kernel)
     c->wta_fused = false;
     c->wta_adds_s2 = false;
-    if (g.layout == 1) { // the wavefront schedule, MODE_HH: both sweeps in one launch; wta_kernel forms sat(S + S2)
+    if (g.layout == 1 && (agg_wave_selected(c, g.mode) || vsweep6_cols(c, g) == 0)) { // the wavefront schedule, MODE_HH: both sweeps in one launch; wta_kernel forms sat(S + S2)
         c->agg_legacy = false;
         if ((e = launch_wave(c, 2)) != cudaSuccess) return e;
         c->wta_adds_s2 = true;

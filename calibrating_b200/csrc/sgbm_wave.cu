@@ -73,46 +73,6 @@ template <int N> __device__ __forceinline__ void sts_n(uint32_t addr, const uint
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr + 4 * i), "r"(v[i]), "r"(v[i + 1]), "r"(v[i + 2]), "r"(v[i + 3]) : "memory");
 }
 
-// One SGM step of an 8-lane group in the block layout: T = normalised state of the predecessor pixel (in/out), c = C of this
-// pixel, L = L_r of this pixel.  Word i of a lane = word li*N + i of the pixel; word w holds disparities (16b+j, 16b+8+j),
-// b = w/8, j = w%8.  The d-1 neighbour of word j > 0 is word j-1, of word 0 it is (hi of the previous block's word 7, lo of
-// this block's word 7); the d+1 neighbour of word j < 7 is word j+1, of word 7 it is (hi of this block's word 0, lo of the next
-// block's word 0).  Same arithmetic as sgm_step (sgm_common.cuh).
-template <int N, bool PAD>
-__device__ __forceinline__ void sgm_step_b(uint32_t (&T)[N], const uint32_t (&c)[N], uint32_t (&L)[N], const uint32_t (&padmask)[N],
-                                           uint32_t P1v, uint32_t P2mP1v, uint32_t ku, uint32_t au, uint32_t kd, uint32_t ad)
-{
-    static_assert(N % 8 == 0, "whole blocks of 16 disparities per lane");
-    uint32_t up = __shfl_up_sync(0xffffffffu, T[N - 1], 1, 8);
-    uint32_t dn = __shfl_down_sync(0xffffffffu, T[0], 1, 8);
-    up = up * ku + au; // first / last lane of the group: the d = -1 / d = D sentinels (multiply-add: FMA pipe, the ALU pipe is the busy one)
-    dn = dn * kd + ad;
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        uint32_t lft, rgt;
-        if (i % 8 == 0) lft = __byte_perm(i == 0 ? up : T[i - 1], T[i + 7], 0x5432);
-        else lft = T[i - 1];
-        if (i % 8 == 7) rgt = __byte_perm(T[i - 7], i == N - 1 ? dn : T[i + 1], 0x5432);
-        else rgt = T[i + 1];
-        uint32_t t = __vimin3_s16x2(lft, rgt, P2mP1v);
-        t = __viaddmin_s16x2(t, P1v, T[i]);
-        L[i] = c[i] + t; // 0 <= t <= P2 and C >= 0: no carry between the halves
-        if (PAD) L[i] |= padmask[i];
-    }
-    uint32_t m = __vimin3_s16x2(L[0], L[1], L[2]);
-#pragma unroll
-    for (int i = 3; i + 1 < N; i += 2) m = __vimin3_s16x2(m, L[i], L[i + 1]);
-    m = __vmins2(m, L[N - 1]);
-    m = __vmins2(m, __byte_perm(m, m, 0x1032));
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) m = __vmins2(m, __shfl_xor_sync(0xffffffffu, m, o, 8));
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        T[i] = L[i] - m; // both halves of L are >= their half of m: no borrow
-        if (PAD) T[i] |= padmask[i];
-    }
-}
-
 template <int NP, bool PAD>
 __global__ void __launch_bounds__(WvCfg<NP>::rows * 32, 1) agg_wave_kernel(WaveArgs a)
 {
@@ -325,7 +285,7 @@ __global__ void __launch_bounds__(WvCfg<NP>::rows * 32, 1) agg_wave_kernel(WaveA
                 if (lane == 0 && (s & 7) == 7) *gcons_mine = s; // pixels <= s-1 of the predecessor's ring are no longer needed
             }
             // ---- all four paths of pixel s ----
-            sgm_step_b<N, PAD>(T, c, L, padmask, P1v, P2mP1v, ku, au, kd, ad);
+            sgm_step_blk<N, 8, PAD>(T, c, L, padmask, P1v, P2mP1v, ku, au, kd, ad);
             // ---- publish the row-crossing states of pixel s ----
             if (gives) {
                 const int need = s - WV_KG + 9; // the slot held pixel s-KG; the consumer reports its progress every 8 pixels
@@ -405,6 +365,7 @@ cudaError_t launch_wave(b2s_ctx *c, int ndirs)
 {
     const SgbmGeom &g = c->g;
     if (g.layout != 1 || (g.NP != 2 && g.NP != 4)) return cudaErrorInvalidValue;
+    if (cudaError_t te = wait_timeout_init()) return te;
     WaveArgs a;
     a.C = c->C.as<int16_t>();
     a.S = c->S.as<int16_t>();

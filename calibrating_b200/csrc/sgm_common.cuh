@@ -2,6 +2,9 @@
 // SGM step, cp.async / bulk-copy / mbarrier wrappers and the bounded spin-wait.  Not part of the public ABI.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
+
+#include <mutex>
 
 #include "b2s_internal.h"
 
@@ -113,9 +116,115 @@ __device__ __forceinline__ void sgm_step(uint32_t (&T)[NP], const uint32_t (&c)[
     }
 }
 
+// One SGM step of an LPP-lane group (LPP = 4 or 8) in the block layout (SgbmGeom::layout 1): T = normalised state of the predecessor pixel (in/out), c = C of this
+// pixel, L = L_r of this pixel.  Word i of a lane = word li*N + i of the pixel; word w holds disparities (16b+j, 16b+8+j),
+// b = w/8, j = w%8.  The d-1 neighbour of word j > 0 is word j-1, of word 0 it is (hi of the previous block's word 7, lo of
+// this block's word 7); the d+1 neighbour of word j < 7 is word j+1, of word 7 it is (hi of this block's word 0, lo of the next
+// block's word 0).  Same arithmetic as sgm_step (sgm_common.cuh).
+template <int N, int LPP, bool PAD>
+__device__ __forceinline__ void sgm_step_blk(uint32_t (&T)[N], const uint32_t (&c)[N], uint32_t (&L)[N], const uint32_t (&padmask)[N],
+                                           uint32_t P1v, uint32_t P2mP1v, uint32_t ku, uint32_t au, uint32_t kd, uint32_t ad)
+{
+    static_assert(N % 8 == 0, "whole blocks of 16 disparities per lane");
+    uint32_t up = __shfl_up_sync(0xffffffffu, T[N - 1], 1, LPP);
+    uint32_t dn = __shfl_down_sync(0xffffffffu, T[0], 1, LPP);
+    up = up * ku + au; // first / last lane of the group: the d = -1 / d = D sentinels (multiply-add: FMA pipe, the ALU pipe is the busy one)
+    dn = dn * kd + ad;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        uint32_t lft, rgt;
+        if (i % 8 == 0) lft = __byte_perm(i == 0 ? up : T[i - 1], T[i + 7], 0x5432);
+        else lft = T[i - 1];
+        if (i % 8 == 7) rgt = __byte_perm(T[i - 7], i == N - 1 ? dn : T[i + 1], 0x5432);
+        else rgt = T[i + 1];
+        uint32_t t = __vimin3_s16x2(lft, rgt, P2mP1v);
+        t = __viaddmin_s16x2(t, P1v, T[i]);
+        L[i] = c[i] + t; // 0 <= t <= P2 and C >= 0: no carry between the halves
+        if (PAD) L[i] |= padmask[i];
+    }
+    uint32_t m = __vimin3_s16x2(L[0], L[1], L[2]);
+#pragma unroll
+    for (int i = 3; i + 1 < N; i += 2) m = __vimin3_s16x2(m, L[i], L[i + 1]);
+    m = __vmins2(m, L[N - 1]);
+    m = __vmins2(m, __byte_perm(m, m, 0x1032));
+#pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1) m = __vmins2(m, __shfl_xor_sync(0xffffffffu, m, o, LPP));
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        T[i] = L[i] - m; // both halves of L are >= their half of m: no borrow
+        if (PAD) T[i] |= padmask[i];
+    }
+}
+
+// The same step for a whole warp per pixel (the horizontal scans) in the block layout: a lane holds NP = 2 or 4 consecutive
+// words, so a block of 8 words spans LB = 8 / NP lanes.  Word 0 of a block (register 0 of the lanes with lane % LB == 0) takes its
+// d-1 neighbour from (hi of the previous word, lo of the block's word 7 = last register of lane + LB - 1); word 7 takes its d+1
+// neighbour from (hi of the block's word 0, lo of the next word): two extra shuffles and two PRMTs with a per-lane selector
+// (identity for the lanes in the middle of a block) instead of the 2 PRMTs per register of the pair layout.
+template <int NP, bool PAD>
+__device__ __forceinline__ void sgm_step_b32(uint32_t (&T)[NP], const uint32_t (&c)[NP], uint32_t (&L)[NP], const uint32_t (&padmask)[NP],
+                                             uint32_t P1v, uint32_t P2mP1v, int lane)
+{
+    static_assert(NP == 2 || NP == 4, "block layout: 2 or 4 words per lane");
+    constexpr int LB = 8 / NP;
+    const uint32_t BIG = 0x7FFF7FFFu;
+    uint32_t up = __shfl_up_sync(0xffffffffu, T[NP - 1], 1);       // word w-1 of register 0
+    uint32_t dn = __shfl_down_sync(0xffffffffu, T[0], 1);          // word w+1 of the last register
+    const uint32_t w7 = __shfl_down_sync(0xffffffffu, T[NP - 1], LB - 1); // the block's word 7 (for the lanes that hold word 0)
+    const uint32_t w0 = __shfl_up_sync(0xffffffffu, T[0], LB - 1);        // the block's word 0 (for the lanes that hold word 7)
+    uint32_t ku = lane != 0 ? 1u : 0u, kd = lane != 31 ? 1u : 0u;
+    asm("" : "+r"(ku));
+    asm("" : "+r"(kd));
+    up = up * ku + (lane == 0 ? BIG : 0u);  // d = -1 / d = Dp sentinels (multiply-add: FMA pipe)
+    dn = dn * kd + (lane == 31 ? BIG : 0u);
+    const int p = lane % LB;
+    const uint32_t lft0 = __byte_perm(up, w7, p == 0 ? 0x5432u : 0x3210u);          // (hi of previous word, lo of word 7) or the previous word
+    const uint32_t rgtN = __byte_perm(w0, dn, p == LB - 1 ? 0x5432u : 0x7654u);     // (hi of word 0, lo of next word) or the next word
+    uint32_t m = BIG;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        const uint32_t lft = i == 0 ? lft0 : T[i - 1], rgt = i == NP - 1 ? rgtN : T[i + 1];
+        uint32_t t = __vimin3_s16x2(lft, rgt, P2mP1v);
+        t = __viaddmin_s16x2(t, P1v, T[i]);
+        L[i] = c[i] + t;
+        if (PAD) L[i] |= padmask[i];
+        m = __vmins2(m, L[i]);
+    }
+    m = __vmins2(m, __byte_perm(m, m, 0x1032));
+    m = (uint32_t)__reduce_min_sync(0xffffffffu, (int)m);
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        T[i] = L[i] - m;
+        if (PAD) T[i] |= padmask[i];
+    }
+}
+
 // ---- spin-wait guard and mbarrier helpers (fused vertical sweep and the bulk-copy pipeline of the horizontal scans) ----
 constexpr int HO_SLOTS = 4;
-constexpr unsigned long long WAIT_TIMEOUT_NS = 2000000000ull; // a hand-over / neighbour wait longer than 2 s is a lost strip: flag it, do not hang
+// a hand-over / neighbour wait longer than this is a lost strip: flag it, do not hang.  2 s by default; B2S_WAIT_TIMEOUT_S=<seconds>
+// raises it (compute-sanitizer slows the kernels down a thousandfold).  One copy per translation unit, set by wait_timeout_init().
+__device__ unsigned long long b2s_wait_timeout_ns = 2000000000ull;
+inline cudaError_t wait_timeout_init()
+{
+    static std::once_flag once;
+    static cudaError_t e = cudaSuccess;
+    std::call_once(once, [] {
+        const char *s = getenv("B2S_WAIT_TIMEOUT_S");
+        if (s && atof(s) > 0) {
+            const unsigned long long ns = (unsigned long long)(atof(s) * 1e9);
+            int ndev = 0;
+            cudaGetDeviceCount(&ndev);
+            int cur = 0;
+            cudaGetDevice(&cur);
+            for (int d = 0; d < ndev && e == cudaSuccess; d++) {
+                cudaSetDevice(d);
+                e = cudaMemcpyToSymbol(b2s_wait_timeout_ns, &ns, sizeof ns);
+            }
+            cudaSetDevice(cur);
+        }
+    });
+    return e;
+}
 __device__ __forceinline__ unsigned long long global_ns()
 {
     unsigned long long t;
@@ -129,7 +238,7 @@ __device__ __forceinline__ bool wait_expired(int spins, unsigned long long &t0, 
     if (*(volatile int *)err != 0) return true;
     const unsigned long long now = global_ns();
     if (t0 == 0) t0 = now;
-    return now - t0 > WAIT_TIMEOUT_NS;
+    return now - t0 > b2s_wait_timeout_ns;
 }
 
 __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count)

@@ -406,3 +406,27 @@ def test_more_than_256_disparities(handle, D, mode, cn, bs):
     assert np.array_equal(got, live)
     with pytest.raises(ValueError, match="numDisparities > 512"):
         cb.StereoSGBM(handle=handle, **dict(p, num_disparities=528)).compute(np.zeros((8, 700), np.uint8), np.zeros((8, 700), np.uint8))
+
+
+@pytest.mark.parametrize("cols", ["2", "3", "5", "16", "default", "old"])
+@pytest.mark.parametrize("seed", range(6))
+def test_six_path_sweep(handle, seed, cols, monkeypatch):
+    """agg_vsweep6_kernel (sgbm_sweep6.cu: MODE_HH, 65..128 disparities, block layout, all six row-crossing paths of a column in
+    one warp): strips of 2..16 columns (several CTAs exchanging diagonal states through the global hand-over rings), padded
+    disparity ranges, images narrower than a strip; `old` = the same cases through the default agg_vsweep_kernel."""
+    if cols != "old":
+        monkeypatch.setenv("B2S_SWEEP6", "1")  # (opt-in: the kernel is exact but slower than agg_vsweep_kernel)
+    if cols not in ("old", "default"):
+        monkeypatch.setenv("B2S_VSWEEP_COLS", cols)
+    rng = np.random.default_rng(900 + seed)
+    D = [70, 100, 128, 65, 127, 96][seed]
+    c = _case(rng, D=D, mode=1)
+    if seed == 4:
+        c["w"] = D + c["p"]["min_disparity"] + 7  # 7 cost columns
+    l, r, _ = synth.rectified_pair(c["h"], c["w"], D, seed, c["cn"])
+    ref = osgbm.sgbm_compute(l, r, want_volumes=True, **c["p"])
+    got = cb.StereoSGBM(handle=handle, **c["p"]).compute(l, r)
+    assert (handle.volume_dims()[3] == 128) == (cols != "old" or D > 64), "block layout (Dp = 128) <-> six-path sweep"
+    assert np.array_equal(handle.fetch_volume(0), ref["C"]), "cost volume"
+    assert np.array_equal(handle.fetch_volume(1), ref["S"]), "aggregated volume"
+    assert np.array_equal(got, ref["disp"])

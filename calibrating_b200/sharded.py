@@ -219,6 +219,21 @@ class CudaEngine:
             h.close()
 
 
+class PendingBatch:
+    """A batch whose depth all-gather is still in flight (`ShardedStereo.get_depth_batch(..., wait=False)`): the collective runs
+    on NCCL's stream while the caller already computes the next batch.  `result()` waits and returns the gathered tensor."""
+
+    def __init__(self, gathered, work, world, n, H1, W1):
+        self.gathered, self.work, self.shape = gathered, work, (world, n, H1, W1)
+
+    def result(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        world, n, H1, W1 = self.shape
+        return self.gathered.transpose(0, 1).reshape(world * n, H1, W1)  # (rank, k) -> global index k*world + rank
+
+
 class ShardedStereo:
     """Rank-local front end of a pair batch sharded over `torch.distributed` ranks (module docstring)."""
 
@@ -258,10 +273,11 @@ class ShardedStereo:
     def shard(self, n):
         return shard_indices(n, self.rank, self.world)
 
-    def get_depth_batch(self, local_pairs):
+    def get_depth_batch(self, local_pairs, wait=True):
         """local_pairs: this rank's [(img1, img2)] (pair k of this rank is global pair k*world + rank).
         Returns the gathered `unrectify_depth` of the whole batch, (world * n_local, H1, W1) float64 in global pair order,
-        on every rank (device tensor with nccl, host tensor with gloo).  All ranks must pass the same number of pairs."""
+        on every rank (device tensor with nccl, host tensor with gloo).  All ranks must pass the same number of pairs.
+        wait=False returns a `PendingBatch` right after the all-gather was enqueued, so that the next batch's kernels overlap it."""
         torch, dist = self.torch, self.dist
         n, H1, W1 = len(local_pairs), self.scalars["H1"], self.scalars["W1"]
         dev = torch.device("cuda", self.device) if self.cuda else torch.device("cpu")
@@ -275,5 +291,6 @@ class ShardedStereo:
                 a, b, _ = check_pair(a, b, self.scalars)
                 self.engine.get_depth_into(a, b, o)
         gathered = torch.empty((self.world, n, H1, W1), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(gathered.view(self.world * n, H1, W1), local, group=self.group)  # THE depth all-gather
-        return gathered.transpose(0, 1).reshape(self.world * n, H1, W1)  # (rank, k) -> global index k*world + rank
+        work = dist.all_gather_into_tensor(gathered.view(self.world * n, H1, W1), local, group=self.group, async_op=not wait)  # THE depth all-gather
+        pending = PendingBatch(gathered, None if wait else work, self.world, n, H1, W1)
+        return pending.result() if wait else pending

@@ -457,6 +457,49 @@ int b2s_point_cloud_to_depth(b2s_handle c, const double *points, unsigned long l
     return B2S_OK;
 }
 
+int b2s_resize_nearest_f32(b2s_handle c, const float *src, int sH, int sW, float *dst, int dH, int dW, float mul)
+{
+    if (!c || !src || !dst) return B2S_EINVAL;
+    if (sH <= 0 || sW <= 0 || dH <= 0 || dW <= 0) return fail(c, B2S_EINVAL, "b2s_resize_nearest_f32: bad sizes");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, c->pin.ensure((size_t)sH * sW * 4));
+    CK(c, c->pout.ensure((size_t)dH * dW * 4));
+    CK(c, cudaMemcpyAsync(c->pin.p, src, (size_t)sH * sW * 4, cudaMemcpyDefault, c->stream));
+    CK(c, launch_resize_nearest_f32(c, c->pin.as<float>(), sH, sW, c->pout.as<float>(), dH, dW, mul));
+    CK(c, cudaMemcpyAsync(dst, c->pout.p, (size_t)dH * dW * 4, cudaMemcpyDefault, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return B2S_OK;
+}
+
+int b2s_interpolate_sparse(b2s_handle c, int inter_type, const double *uvz, int n, const double abc[3], const uint8_t *mask, int H, int W,
+                           double distance, float *out)
+{
+    if (!c || !out) return B2S_EINVAL;
+    if (W <= 0 || H <= 0) return fail(c, B2S_EINVAL, "b2s_interpolate_sparse: bad size");
+    if (inter_type != 0 && inter_type != 1) return fail(c, B2S_EINVAL, "b2s_interpolate_sparse: inter_type 0 (lstsq plane) or 1 (nearest), got %d", inter_type);
+    if (inter_type == 0 && !abc) return fail(c, B2S_EINVAL, "b2s_interpolate_sparse: the plane coefficients are missing");
+    if (inter_type == 1 && (n < 0 || (n > 0 && !uvz))) return fail(c, B2S_EINVAL, "b2s_interpolate_sparse: the points are missing");
+    CK(c, cudaSetDevice(c->device));
+    const size_t npx = (size_t)W * H;
+    CK(c, c->pout.ensure(npx * 8));
+    uint8_t *dmask = nullptr;
+    if (mask) {
+        CK(c, c->pin.ensure(npx));
+        CK(c, cudaMemcpyAsync(c->pin.p, mask, npx, cudaMemcpyDefault, c->stream));
+        dmask = c->pin.as<uint8_t>();
+    }
+    if (inter_type == 0) {
+        CK(c, launch_plane_fill(c, dmask, H, W, abc[0], abc[1], abc[2], c->pout.as<float>()));
+    } else {
+        CK(c, c->cl_pts.ensure((size_t)(n ? n : 1) * 24));
+        if (n) CK(c, cudaMemcpyAsync(c->cl_pts.p, uvz, (size_t)n * 24, cudaMemcpyDefault, c->stream));
+        CK(c, launch_nearest_fill(c, c->cl_pts.as<double>(), n, dmask, H, W, distance, c->pout.as<float>()));
+    }
+    CK(c, cudaMemcpyAsync(out, c->pout.p, npx * 4, cudaMemcpyDefault, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return B2S_OK;
+}
+
 int b2s_set_cam1_model(b2s_handle c, double fx, double fy, double cx, double cy, const double k[12])
 {
     if (!c || !k) return B2S_EINVAL;

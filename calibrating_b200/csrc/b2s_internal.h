@@ -141,11 +141,14 @@ cudaError_t launch_gen_maps(b2s_ctx *c, const b2s_map_params &p, float *mapx, fl
                             uint16_t *fxy16);
 // resize.cu
 cudaError_t launch_resize_u8(b2s_ctx *c, const uint8_t *src, int sH, int sW, int cn, uint8_t *dst, int dH, int dW);
+cudaError_t launch_resize_nearest_f32(b2s_ctx *c, const float *src, int sH, int sW, float *dst, int dH, int dW, float mul);
 cudaError_t launch_resize_f32(b2s_ctx *c, const float *src, int sH, int sW, float *dst, int dH, int dW, float mul, float div);
 // cloud.cu
 cudaError_t launch_depth_to_cloud(b2s_ctx *c, const double *d_depth, int H, int W, double rate, const double *Kinv, int cols, double *d_out,
                                   unsigned long long capacity, unsigned *d_rowcount, unsigned long long *d_rowoff, int *Hu_out);
 cudaError_t launch_cloud_to_depth(b2s_ctx *c, const double *d_pts, unsigned long long n, const double *d_K, int W, int H, unsigned long long *d_key,
                                   double *d_out, double bg);
+cudaError_t launch_plane_fill(b2s_ctx *c, const uint8_t *d_mask, int H, int W, double a, double b, double cc, float *d_out);
+cudaError_t launch_nearest_fill(b2s_ctx *c, const double *d_uvz, int n, const uint8_t *d_mask, int H, int W, double distance, float *d_out);
 cudaError_t launch_depth_bare(b2s_ctx *c, const float *d_disp, double *d_depth);
 cudaError_t launch_unrectify(b2s_ctx *c, const double *d_depth, double *d_out);

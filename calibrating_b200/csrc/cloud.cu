@@ -135,7 +135,62 @@ __global__ void cloud_resolve_kernel(const unsigned long long *__restrict__ key,
     out[i] = k == 0xFFFFFFFFFFFFFFFFull ? bg : zunkey(k);
 }
 
+// ---- calibrating/utils.py:347-415 interpolate_uvzs, the dense half: one thread per pixel of the (h, w) output ----
+// "lstsq": z = a u + b v + c on the pixels of the mask (float64 like NumPy's promotion of float32 @ float64, stored float32)
+__global__ void plane_fill_kernel(const uint8_t *__restrict__ mask, int H, int W, double a, double b, double c, float *__restrict__ out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const size_t i = (size_t)y * W + x;
+    // unfused, left to right: the float64 evaluation order of the reference's `output_uvzs @ abc` as numpy runs it
+    out[i] = (!mask || mask[i]) ? (float)__dadd_rn(__dadd_rn(__dmul_rn((double)x, a), __dmul_rn((double)y, b)), c) : 0.f;
+}
+// "nearest": the z of the nearest sparse point if it is closer than `distance`, else 0 (KDTree.query + the distance test);
+// brute force over the points, staged through shared memory in tiles (a few hundred to a few thousand points)
+__global__ void __launch_bounds__(256) nearest_fill_kernel(const double *__restrict__ uvz, int n, const uint8_t *__restrict__ mask, int H, int W,
+                                                           double distance, float *__restrict__ out)
+{
+    __shared__ double su[256], sv[256], sz[256];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const double px = (double)x, py = (double)y;
+    double best = 1e300, bz = 0.0;
+    for (int base = 0; base < n; base += 256) {
+        const int k = base + threadIdx.x;
+        if (k < n) {
+            su[threadIdx.x] = uvz[3 * k];
+            sv[threadIdx.x] = uvz[3 * k + 1];
+            sz[threadIdx.x] = uvz[3 * k + 2];
+        }
+        __syncthreads();
+        const int m = min(256, n - base);
+        for (int j = 0; j < m; j++) {
+            const double du = su[j] - px, dv = sv[j] - py, d2 = __dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv));
+            if (d2 < best) { // (strict: of equally near points the first one wins)
+                best = d2;
+                bz = sz[j];
+            }
+        }
+        __syncthreads();
+    }
+    if (x >= W) return;
+    const size_t i = (size_t)y * W + x;
+    out[i] = ((!mask || mask[i]) && sqrt(best) < distance) ? (float)bz : 0.f;
+}
+
 } // namespace
+
+cudaError_t launch_plane_fill(b2s_ctx *c, const uint8_t *d_mask, int H, int W, double a, double b, double cc, float *d_out)
+{
+    plane_fill_kernel<<<dim3((W + 255) / 256, H), 256, 0, c->stream>>>(d_mask, H, W, a, b, cc, d_out);
+    c->launches++;
+    return cudaGetLastError();
+}
+cudaError_t launch_nearest_fill(b2s_ctx *c, const double *d_uvz, int n, const uint8_t *d_mask, int H, int W, double distance, float *d_out)
+{
+    nearest_fill_kernel<<<dim3((W + 255) / 256, H), 256, 0, c->stream>>>(d_uvz, n, d_mask, H, W, distance, d_out);
+    c->launches++;
+    return cudaGetLastError();
+}
 
 // d_depth (H, W) f64 -> d_out (n, cols) f64 (cols = 3, or 5 with u, v appended), n written to d_rowoff[Hu] (device); Hu returned
 cudaError_t launch_depth_to_cloud(b2s_ctx *c, const double *d_depth, int H, int W, double rate, const double *Kinv, int cols, double *d_out,

@@ -74,7 +74,25 @@ __global__ void __launch_bounds__(256) resize_f32_kernel(const float *__restrict
     dst[(size_t)dy * dW + dx] = __fdiv_rn(__fmul_rn(v, mul), div);
 }
 
+// cv2.resize(float32, INTER_NEAREST) times a factor: source index = min(floor(dst * scale), size - 1)
+__global__ void __launch_bounds__(256) resize_nearest_f32_kernel(const float *__restrict__ src, int sH, int sW, float *__restrict__ dst, int dH, int dW,
+                                                                 double scale_x, double scale_y, float mul)
+{
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y;
+    if (dx >= dW) return;
+    const int sx = min((int)floor(dx * scale_x), sW - 1), sy = min((int)floor(dy * scale_y), sH - 1);
+    dst[(size_t)dy * dW + dx] = __fmul_rn(src[(size_t)sy * sW + sx], mul);
+}
+
 } // namespace
+
+cudaError_t launch_resize_nearest_f32(b2s_ctx *c, const float *src, int sH, int sW, float *dst, int dH, int dW, float mul)
+{
+    const dim3 b(256), g((dW + 255) / 256, dH);
+    resize_nearest_f32_kernel<<<g, b, 0, c->stream>>>(src, sH, sW, dst, dH, dW, 1.0 / ((double)dW / sW), 1.0 / ((double)dH / sH), mul);
+    c->launches++;
+    return cudaGetLastError();
+}
 
 cudaError_t launch_resize_u8(b2s_ctx *c, const uint8_t *src, int sH, int sW, int cn, uint8_t *dst, int dH, int dW)
 {

@@ -127,3 +127,68 @@ class SemiGlobalBlockMatching(MetaStereoMatching):
 
 
 B200StereoMatching = SemiGlobalBlockMatching
+
+
+class MatchingByBoard(MetaStereoMatching):
+    """calibrating/stereo_matching.py:73-110: disparity from a calibration board's corners seen in both rectified images, densified
+    over the board's convex hull.  The board (any object with the reference's `find_image_points(d)`, e.g. `calibrating.Chessboard`)
+    and its detector stay on the host -- a few hundred points; the dense disparity is evaluated on the device
+    (`utils.interpolate_sparse2d` -> b2s_interpolate_sparse)."""
+
+    def __init__(self, board, dense_predict=True, device=0):
+        self.board = board
+        self.dense_predict = dense_predict
+        self.device = device
+
+    def __call__(self, img1, img2):
+        from .utils import interpolate_sparse2d
+        d1, d2 = dict(img=img1), dict(img=img2)
+        self.board.find_image_points(d1)
+        self.board.find_image_points(d2)
+        p1, p2 = d1["image_points"], d2["image_points"]
+        if isinstance(p1, dict):
+            keys = sorted(set(p1).intersection(p2))
+            p1 = np.concatenate([d1["image_points"][k] for k in keys], 0)
+            p2 = np.concatenate([d2["image_points"][k] for k in keys], 0)
+        rectify_std = np.std((p2 - p1)[:, 1])
+        xyds = np.append(p1, (p1 - p2)[:, :1], axis=-1)
+        h, w = img1.shape[:2]
+        sparse = np.zeros((h, w), xyds.dtype)  # uvzs_to_arr2d (utils.py:291-317): rounded pixel, later points overwrite earlier ones
+        xs, ys = np.int32(xyds[:, :2].round()).T
+        ok = (xs >= 0) & (xs < w) & (ys >= 0) & (ys < h)
+        sparse[ys[ok], xs[ok]] = xyds[ok, 2]
+        if not self.dense_predict:
+            return dict(disparity=sparse, rectify_std=rectify_std)
+        with np.errstate(divide="ignore"):
+            dense = 1 / interpolate_sparse2d(1 / sparse, "convex_hull", device=self.device)
+        return dict(disparity=dense, rectify_std=rectify_std)
+
+
+class FeatureMatchingAsStereoMatching(MetaStereoMatching):
+    """calibrating/stereo_matching.py:113-142: sparse matches of a learned feature matcher (`feature_matching(img1, img2)` ->
+    dict(uvs1, uvs2) in normalised coordinates, cfg["shape"]) -> nearest-neighbour densification at 1/8 resolution -> up-scale.
+    The matcher is the user's; densification and up-scale run on the device."""
+
+    def __init__(self, feature_matching, device=0):
+        self.feature_matching = feature_matching
+        self.device = device
+
+    def __call__(self, img1, img2):
+        from .utils import interpolate_uvzs
+        matched = self.feature_matching(img1, img2)
+        hw = img1.shape[:2]
+        shape = self.feature_matching.cfg.get("shape", hw)
+        small = (shape[0] // 8, shape[1] // 8)
+        uvs1, uvs2 = matched["uvs1"] * small[::-1], matched["uvs2"] * small[::-1]
+        uvds = np.concatenate((uvs1, (uvs1 - uvs2)[:, :1]), 1)
+        disparity = interpolate_uvzs(uvds, small, constrained_type=None, inter_type="nearest", device=self.device)
+        if tuple(small) != tuple(hw):
+            from .stereo_camera import _module_handle
+            # `disparity * hw[1] / resize_shape[1]` (stereo_matching.py:133-137) is evaluated left to right on the host so that
+            # the two roundings stay two; the nearest-neighbour up-scale runs on the device.
+            src = np.ascontiguousarray(disparity * hw[1] / small[1], np.float32)
+            out = np.empty(tuple(hw), np.float32)
+            _module_handle(self.device).call("b2s_resize_nearest_f32", _ffi.ptr(src), small[0], small[1], _ffi.ptr(out), hw[0], hw[1], 1.0)
+            disparity = out
+        return dict(disparity=disparity, matched=matched)
+

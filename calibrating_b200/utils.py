@@ -58,4 +58,48 @@ def point_cloud_to_depth(points, K, xy, device=0):
     return point_cloud_to_arr2d(points, K, xy, device=device)
 
 
-__all__ = ["depth_to_point_cloud", "point_cloud_to_depth", "point_cloud_to_arr2d"]
+
+
+def interpolate_uvzs(uvzs, hw=None, constrained_type=None, inter_type="lstsq", distance=2, device=0):
+    """calibrating/utils.py:356-411: densify sparse (u, v, z) samples to an (h, w) float32 image.  The sparse half (a 3-parameter
+    least-squares fit on a few hundred points, the convex hull of the samples) stays on the host like the reference's; the dense
+    half -- one value per pixel -- runs on the device.  inter_type "lstsq" or "nearest" ("rbf" needs scipy's thin-plate solver and
+    is not offered)."""
+    import cv2
+    uvzs = np.asarray(uvzs)
+    if hw is None:
+        hw = int(uvzs[:, 1].max()) + 2, int(uvzs[:, 0].max()) + 2
+    hw = (int(hw[0]), int(hw[1]))
+    if not uvzs.size:
+        return np.zeros(hw, uvzs.dtype)
+    mask = None
+    if constrained_type is not None and constrained_type:
+        mask = np.zeros(hw, np.uint8)
+        hull = cv2.convexHull(np.int32(uvzs[:, :2].round()))
+        cv2.drawContours(mask, [hull], -1, 1, -1)
+    out = np.empty(hw, np.float32)
+    h = _handle(device)
+    if inter_type == "lstsq":
+        A = np.float64(uvzs).copy()
+        A[:, 2] = 1
+        abc = np.linalg.lstsq(A, np.float64(uvzs[:, 2]), rcond=None)[0]
+        h.call("b2s_interpolate_sparse", 0, None, 0, (ctypes.c_double * 3)(*abc), None if mask is None else _ffi.ptr(mask), hw[0], hw[1], 0.0, _ffi.ptr(out))
+    elif inter_type == "nearest":
+        pts = np.ascontiguousarray(uvzs[:, :3], np.float64)
+        h.call("b2s_interpolate_sparse", 1, _ffi.ptr(pts), len(pts), None, None if mask is None else _ffi.ptr(mask), hw[0], hw[1], float(distance),
+               _ffi.ptr(out))
+    else:
+        raise NotImplementedError("inter_type %r: only 'lstsq' and 'nearest' run on the device" % (inter_type,))
+    return out
+
+
+def interpolate_sparse2d(sparse2d, constrained_type=None, inter_type="lstsq", device=0):
+    """calibrating/utils.py:347-353: the non-zero finite pixels of `sparse2d` as samples of interpolate_uvzs."""
+    sparse2d = np.asarray(sparse2d)
+    m = (sparse2d != 0) & np.isfinite(sparse2d)
+    ys, xs = np.nonzero(m)  # row-major, the order of arr2d_to_uvzs (utils.py:318-328)
+    uvzs = np.array([xs, ys, sparse2d[m]]).T
+    return interpolate_uvzs(uvzs, sparse2d.shape[:2], constrained_type, inter_type, device=device)
+
+
+__all__ = ["depth_to_point_cloud", "point_cloud_to_depth", "point_cloud_to_arr2d", "interpolate_uvzs", "interpolate_sparse2d"]

@@ -63,10 +63,40 @@ def import_reference():
     return calibrating
 
 
+def sparse_case(calibrating):
+    """case G: utils.interpolate_uvzs / interpolate_sparse2d (utils.py:347-411) of the real reference on seeded sparse samples.
+    `np.bool8` (utils.py:324) left NumPy in 2.0; it is aliased to np.bool_ here so the convex-hull branch runs unmodified."""
+    if not hasattr(np, "bool8"):
+        np.bool8 = np.bool_
+    rng = np.random.default_rng(23)
+    hw = (90, 140)
+    n = 300
+    uv = np.stack([rng.random(n) * (hw[1] - 21) + 10, rng.random(n) * (hw[0] - 17) + 8], 1)
+    z = 0.004 * uv[:, 0] - 0.007 * uv[:, 1] + 2.5 + rng.normal(0, 0.01, n)
+    uvzs = np.concatenate([uv, z[:, None]], 1)
+    U = calibrating.utils
+    sparse = np.zeros(hw, np.float32)
+    sel = rng.random(hw) < 0.02
+    sel[:12] = sel[-9:] = False
+    sel[:, :15] = sel[:, -11:] = False
+    sparse[sel] = (40 + 0.05 * np.mgrid[:hw[0], :hw[1]][1] + rng.normal(0, 0.2, hw))[sel]
+    with np.errstate(divide="ignore"):
+        board = 1 / U.interpolate_sparse2d(1 / sparse, "convex_hull")  # MatchingByBoard's dense_predict (stereo_matching.py:105)
+    np.savez_compressed(os.path.join(HERE, "sparse_small.npz"), uvzs=uvzs, hw=np.int32(hw), sparse=sparse,
+                        lstsq=U.interpolate_uvzs(uvzs.copy(), hw), lstsq_hull=U.interpolate_uvzs(uvzs.copy(), hw, "convex_hull"),
+                        lstsq_nohw=U.interpolate_uvzs(uvzs.copy()),
+                        nearest2=U.interpolate_uvzs(uvzs.copy(), hw, None, "nearest"),
+                        nearest6_hull=U.interpolate_uvzs(uvzs.copy(), hw, True, "nearest", distance=6),
+                        sparse2d_hull=U.interpolate_sparse2d(sparse.copy(), "convex_hull"), board_dense=board)
+
+
 def main():
     import cv2
     from calibrating_b200 import synth
     calibrating = import_reference()
+    if sys.argv[1:] == ["sparse"]:
+        sparse_case(calibrating)
+        return
 
     class Param64(calibrating.MetaStereoMatching):
         """BASELINE config 1 matcher: the reference's parameters with numDisparities=64."""
@@ -139,6 +169,7 @@ def main():
                               uniquenessRatio=5, speckleWindowSize=200, speckleRange=2)
     np.savez_compressed(os.path.join(HERE, "sgbm_small.npz"), left=l, right=r, disp_sgbm=out["sgbm"], disp_hh=out["hh"], disp_hh4=out["hh4"],
                         disp_refparams=m.compute(l, r), cv2_version=cv2.__version__)
+    sparse_case(calibrating)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")), "cv2", cv2.__version__)
 
 

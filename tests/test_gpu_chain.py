@@ -342,3 +342,66 @@ def test_point_cloud_functions(golden_dir):
     assert got.shape == exp.shape and np.allclose(got, exp, rtol=1e-12, atol=1e-15)
     z = cb.point_cloud_to_depth(got, K, (1920, 1080))
     assert np.allclose(z, np.float64(d), rtol=1e-12, atol=0), "un-project and project back is the identity on the pixel grid"
+
+
+def test_sparse_interpolation_and_sparse_matchers(golden_dir):
+    """interpolate_uvzs / interpolate_sparse2d (utils.py:347-411) with the dense half on the device,
+    bit-equal to the real reference's outputs, and the two sparse matcher plugins built on them (stereo_matching.py:73-142)."""
+    from oracle import sparse
+    g = np.load(os.path.join(golden_dir, "sparse_small.npz"))
+    hw = tuple(int(v) for v in g["hw"])
+    assert np.array_equal(cb.interpolate_uvzs(g["uvzs"], hw), g["lstsq"])
+    assert np.array_equal(cb.interpolate_uvzs(g["uvzs"], hw, "convex_hull"), g["lstsq_hull"])
+    assert np.array_equal(cb.interpolate_uvzs(g["uvzs"]), g["lstsq_nohw"])
+    assert np.array_equal(cb.interpolate_uvzs(g["uvzs"], hw, None, "nearest"), g["nearest2"])
+    assert np.array_equal(cb.interpolate_uvzs(g["uvzs"], hw, True, "nearest", distance=6), g["nearest6_hull"])
+    assert np.array_equal(cb.interpolate_sparse2d(g["sparse"], "convex_hull"), g["sparse2d_hull"])
+    out = cb.interpolate_uvzs(np.zeros((0, 3)), (4, 5))
+    assert out.shape == (4, 5) and not out.any()
+    with pytest.raises(NotImplementedError):
+        cb.interpolate_uvzs(g["uvzs"], hw, inter_type="rbf")
+    # 1080p, 2000 samples (more than one shared-memory tile of the nearest search), against the restatement
+    rng = np.random.default_rng(4)
+    uvz = np.stack([rng.random(2000) * 1900 + 5, rng.random(2000) * 1060 + 5, rng.random(2000) * 50 + 1], 1)
+    assert np.array_equal(cb.interpolate_uvzs(uvz, (1080, 1920), True, "nearest", distance=25), sparse.interpolate_uvzs(uvz, (1080, 1920), True, "nearest", 25))
+    assert np.array_equal(cb.interpolate_uvzs(uvz, (1080, 1920), True), sparse.interpolate_uvzs(uvz, (1080, 1920), True))
+
+    # MatchingByBoard: a stand-in board whose "detector" returns seeded corners with a known disparity plane
+    class Board:
+        def __init__(self):
+            gy, gx = np.mgrid[20:80:7j, 25:120:9j]
+            self.p1 = np.float32(np.stack([gx.ravel(), gy.ravel()], 1))
+            self.p2 = self.p1 - np.float32(np.stack([8 + 0.02 * self.p1[:, 0], 0.01 * np.sin(self.p1[:, 1])], 1))
+        def find_image_points(self, d):
+            d["image_points"] = self.p1 if d["img"][0, 0, 0] == 1 else self.p2
+    b = Board()
+    img1, img2 = np.ones((90, 140, 3), np.uint8), np.zeros((90, 140, 3), np.uint8)
+    got = cb.MatchingByBoard(b)(img1, img2)
+    sp = np.zeros((90, 140), np.float32)
+    sp[np.int32(b.p1[:, 1].round()), np.int32(b.p1[:, 0].round())] = (b.p1 - b.p2)[:, 0]
+    with np.errstate(divide="ignore"):
+        exp = 1 / sparse.interpolate_sparse2d(1 / sp, "convex_hull")
+    assert np.array_equal(got["disparity"], exp) and got["rectify_std"] > 0
+    assert np.count_nonzero(cb.MatchingByBoard(b, dense_predict=False)(img1, img2)["disparity"]) == len(b.p1)
+
+    # FeatureMatchingAsStereoMatching: a stand-in matcher returning normalised matches; 1/8-resolution nearest fill, then up-scale
+    class FM:
+        cfg = dict(shape=(240, 320))
+        def __call__(self, a, b):
+            r = np.random.default_rng(9)
+            uv1 = np.float32(r.random((400, 2)))
+            uv2 = uv1.copy()
+            uv2[:, 0] -= np.float32(0.02 + 0.05 * uv1[:, 1])
+            return dict(uvs1=uv1, uvs2=uv2)
+    fm = FM()
+    a = np.zeros((240, 320, 3), np.uint8)
+    got = cb.FeatureMatchingAsStereoMatching(fm)(a, a)
+    m = fm(a, a)
+    small = (30, 40)
+    uvs1, uvs2 = m["uvs1"] * small[::-1], m["uvs2"] * small[::-1]
+    uvds = np.concatenate((uvs1, (uvs1 - uvs2)[:, :1]), 1)
+    d = sparse.interpolate_uvzs(uvds, small, None, "nearest")
+    d = d * 320 / 40
+    import cv2
+    exp = cv2.resize(d, (320, 240), interpolation=cv2.INTER_NEAREST)
+    assert got["disparity"].shape == (240, 320) and np.array_equal(got["disparity"], exp)

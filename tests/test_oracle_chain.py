@@ -71,3 +71,20 @@ def test_point_cloud_restatements_match_reference(golden_dir):
     assert np.array_equal(reproject.depth_to_point_cloud(g["depth"], g["K"]), g["cloud_rate1"])
     assert np.array_equal(reproject.depth_to_point_cloud(g["depth16"], g["K"], 1.5, True), g["xyzuv_rate15"])
     assert np.array_equal(reproject.point_cloud_to_depth(g["moved"], g["K"], (160, 120)), g["depth_back"])
+
+
+def test_sparse_interpolation_restatement_matches_reference(golden_dir):
+    """oracle.sparse against the real reference's interpolate_uvzs / interpolate_sparse2d (utils.py:347-411): plane fit with and
+    without the convex-hull mask, default hw, nearest sample within 2 and 6 px, and MatchingByBoard's 1/interp(1/sparse)."""
+    from oracle import sparse
+    g = np.load(os.path.join(golden_dir, "sparse_small.npz"))
+    hw = tuple(int(v) for v in g["hw"])
+    assert np.array_equal(sparse.interpolate_uvzs(g["uvzs"], hw), g["lstsq"])
+    assert np.array_equal(sparse.interpolate_uvzs(g["uvzs"], hw, "convex_hull"), g["lstsq_hull"])
+    assert np.array_equal(sparse.interpolate_uvzs(g["uvzs"]), g["lstsq_nohw"])
+    assert np.array_equal(sparse.interpolate_uvzs(g["uvzs"], hw, None, "nearest"), g["nearest2"])
+    assert np.array_equal(sparse.interpolate_uvzs(g["uvzs"], hw, True, "nearest", 6), g["nearest6_hull"])
+    assert np.array_equal(sparse.interpolate_sparse2d(g["sparse"], "convex_hull"), g["sparse2d_hull"])
+    with np.errstate(divide="ignore"):
+        assert np.array_equal(1 / sparse.interpolate_sparse2d(1 / g["sparse"], "convex_hull"), g["board_dense"])
+    assert sparse.interpolate_uvzs(np.zeros((0, 3)), (4, 5)).shape == (4, 5)

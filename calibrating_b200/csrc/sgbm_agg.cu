@@ -23,6 +23,8 @@
 #include <string.h>
 
 #include <mutex>
+#include <set>
+#include <utility>
 #include <type_traits>
 
 #include "b2s_internal.h"
@@ -649,7 +651,7 @@ template <int NP> __device__ __forceinline__ void ho_write(uint32_t *p, uint32_t
 // writes the sum of its three paths to S2 without reading anything but C, so the two sweeps share no data at all.
 // Warps synchronise only with their two neighbour columns (one mbarrier per warp, phase = row), so the warps of an SM
 // drift apart by up to a row per column and keep the issue slots busy while others wait.
-template <int NP, bool PAD, int JW, int R>
+template <int NP, bool PAD, int JW, int R, unsigned WH = 0>
 __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
 {
     constexpr int DW = 32 * NP;           // 32-bit words of one pixel's d-chunk
@@ -663,8 +665,21 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
     const int lane = threadIdx.x & 31;
     const int wi = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); // warp-uniform by construction
     const int n = a.n, G = gridDim.x, H = a.H, Dp = 64 * NP;
-    const int jl = JW == 2 ? (wi >= n ? 1 : 0) : 0; // sweep slot inside the CTA
-    const int w = wi - jl * n;                      // column inside the strip
+    int jl = JW == 2 ? (wi >= n ? 1 : 0) : 0; // sweep slot inside the CTA
+    int w = wi - jl * n;                      // column inside the strip
+    if constexpr ((WH & 2u) != 0 && JW == 2) {
+        // the four warps on the strip's boundaries carry the hand-over to the neighbour CTAs and are the slowest of the strip: one per
+        // scheduler (warp id mod 4) instead of two on scheduler 0 and two on scheduler 1
+        if (n >= 3) {
+            if (wi < 4) {
+                jl = wi >> 1;
+                w = (wi & 1) ? n - 1 : 0;
+            } else {
+                jl = (wi - 4) / (n - 2);
+                w = 1 + (wi - 4) % (n - 2);
+            }
+        }
+    }
     const bool up = JW == 2 ? jl == 1 : a.up != 0;  // bottom-up sweep?
     const bool acc = !up;                           // top-down: S += paths; bottom-up: S2 = paths
     const int x = blockIdx.x * n + w;
@@ -782,7 +797,7 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
                     for (int i = 0; i < NP; i++) T0[i] = padmask[i];
                 } else ho_read<NP>(in_g[0] + ((t - 1) & (HO_SLOTS - 1)) * DW, (((t - 1) >> 2) & 1) ? 0x80008000u : 0u, T0, a.err);
             } else {
-                if (in_mb[0]) mbar_wait(in_mb[0] + mb_off, par_in, a.err);
+                if (in_mb[0]) mbar_wait_hint<WH>(in_mb[0] + mb_off, par_in, a.err);
                 lds_s<NP>(in_s[0] + pin, T0);
             }
             if (EDGE && polls) {
@@ -799,7 +814,7 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
                 }
                 sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
             } else {
-                if (in_mb[1]) mbar_wait(in_mb[1] + mb_off, par_in, a.err);
+                if (in_mb[1]) mbar_wait_hint<WH>(in_mb[1] + mb_off, par_in, a.err);
                 lds_s<NP>(in_s[1] + pin, T1);
                 sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
                 sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
@@ -842,6 +857,279 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
     else rows(std::false_type{});
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// agg_vsweep2_kernel: the sweep of agg_vsweep_kernel<NP, PAD, 2, R> (both sweeps in one CTA) after its round-2 profile
+// (profiles/r02_agg_raw.csv, source page): the strip runs at the pace of its slowest warp, and the slowest warps were the two per
+// sweep on the CTA boundaries (211 instructions per row against 150, busy all 1500 cycles of a row while the other 24 warps
+// spent 58 % of their time in the neighbour waits).  Three changes, same arithmetic, same hand-over rings:
+//   * a boundary column is split between two warps: the column warp keeps the two diagonal paths and the hand-over to the
+//     neighbour CTA and passes sat(L0 + L1) of every row through an 8-deep shared-memory ring to a helper warp, which runs the
+//     vertical path of that column, forms the sums and owns the S / S2 traffic.  The eight boundary / helper warps are warps
+//     0..7 of the CTA, i.e. two per scheduler.
+//   * a warp owns ONE pair of mbarriers (even / odd rows) on which BOTH neighbours arrive, instead of waiting on each
+//     neighbour's barrier in turn: one TRYWAIT round trip per row instead of two on the critical path.
+//   * the row loop is unrolled by two so that barrier parities and slot parities are immediates, ring stages advance by mask
+//     arithmetic, and the retry path of the waits is the 2.75-instruction loop of mbar_wait_tight.
+// Needs 2n + 4 <= 32 warps and n >= 3 columns per strip; everything else stays with agg_vsweep_kernel.
+template <int NP, bool PAD, int R>
+__global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
+{
+    static_assert(NP == 1 || NP == 2 || NP == 4, "ring stages advance by mask arithmetic");
+    constexpr int XR = 8;                 // depth of the column -> helper ring
+    constexpr int DW = 32 * NP;           // 32-bit words of one pixel's d-chunk
+    constexpr int CHB = DW * 4;           // ... in bytes
+    constexpr int HO_DIR = HO_SLOTS * DW; // words of one direction's hand-over ring
+    constexpr int NSEG = 2 * DW / 4;      // 16-byte segments of one ring stage: [C | S]
+    constexpr int NLD = (NSEG + 31) / 32; // cp.async instructions per lane and step
+    constexpr uint32_t SB = 2 * CHB, RMASK = R * SB - 1; // bytes of one ring stage, mask of the whole ring
+    // [column mbarriers 2n x 2][helper-ring mbarriers 4 x XR][helper progress 4 x u32][diagonal slots][helper rings][C/S rings]
+    extern __shared__ __align__(16) uint32_t vs_smem[];
+
+    const int lane = threadIdx.x & 31;
+    const int wi = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); // warp-uniform by construction
+    const int n = a.n, G = gridDim.x, H = a.H, Dp = 64 * NP;
+    int jl, w;
+    bool helper = false;
+    if (wi < 8) { // the strip's boundary columns and their helpers
+        jl = (wi >> 1) & 1;
+        w = (wi & 1) ? n - 1 : 0;
+        helper = wi >= 4;
+    } else {
+        jl = (wi - 8) / (n - 2);
+        w = 1 + (wi - 8) % (n - 2);
+    }
+    const bool up = jl == 1, acc = !up;
+    const int x = blockIdx.x * n + w;
+    const uint32_t BIG = 0x7FFF7FFFu;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(vs_smem);
+    const uint32_t OFF_XF = 2 * n * 16, OFF_PROG = OFF_XF + 4 * XR * 8, OFF_SLOT = OFF_PROG + 16;
+    const int NSLOT = 2 * 2 * 2 * (n + 2);
+    const uint32_t OFF_X = OFF_SLOT + NSLOT * CHB, OFF_RING = OFF_X + 4 * XR * CHB;
+    uint32_t *slots = vs_smem + OFF_SLOT / 4;
+
+    uint32_t padmask[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        int d0 = (lane * NP + i) * 2;
+        padmask[i] = PAD ? ((d0 >= a.D ? 0x00007FFFu : 0u) | (d0 + 1 >= a.D ? 0x7FFF0000u : 0u)) : 0u;
+    }
+    for (int q = wi; q < NSLOT; q += blockDim.x >> 5) {
+#pragma unroll
+        for (int i = 0; i < NP; i++) slots[q * DW + lane * NP + i] = padmask[i];
+    }
+    if ((int)threadIdx.x < 4 * n) { // column barriers: one arrival per neighbour that lives in this CTA
+        const int col = (threadIdx.x >> 1) % n, xx = blockIdx.x * n + col;
+        const int cnt = (col > 0 ? 1 : 0) + (col < n - 1 && xx + 1 < a.width1 ? 1 : 0);
+        mbar_init(sbase + threadIdx.x * 8, cnt > 0 ? cnt : 1);
+    }
+    if (threadIdx.x < 4 * XR) mbar_init(sbase + OFF_XF + threadIdx.x * 8, 1);
+    if (threadIdx.x < 4) vs_smem[OFF_PROG / 4 + threadIdx.x] = 0;
+    __syncthreads();
+    if (x >= a.width1) return; // idle columns of the last strip
+    const bool first_col = x == 0, last_col = x == a.width1 - 1;
+    const bool glob_l = w == 0 && !first_col, glob_r = w == n - 1 && !last_col; // hand-over to / from the neighbour CTA on that side
+    const bool split = glob_l || glob_r;                                         // this column is shared with a helper warp
+    if (helper && !split) return;
+    const bool has_l = w > 0, has_r = w < n - 1 && x + 1 < a.width1; // neighbours inside the CTA
+    const uint32_t P1v = (uint32_t)a.P1 * 0x10001u, P2mP1v = (uint32_t)(a.P2 - a.P1) * 0x10001u;
+
+    const uint32_t my_mb = sbase + (jl * n + w) * 16;
+    constexpr uint32_t PSB = CHB; // the two parities of a slot are neighbours: [jl][dir][column + 1][parity][DW]
+    uint32_t in_s[2], out_s[2];             // slot read / written (parity 0), dir 0 arrives from column x-1, dir 1 from x+1
+#pragma unroll
+    for (int dir = 0; dir < 2; dir++) {
+        const uint32_t sl = sbase + OFF_SLOT + ((jl * 2 + dir) * (n + 2)) * 2 * CHB + lane * NP * 4;
+        in_s[dir] = sl + (dir == 0 ? w : w + 2) * 2 * CHB;
+        out_s[dir] = sl + (w + 1) * 2 * CHB;
+    }
+    const int xi = wi & 3; // column <-> helper pair
+    const uint32_t xslot = sbase + OFF_X + xi * XR * CHB + lane * NP * 4, xfull = sbase + OFF_XF + xi * XR * 8, xprog = sbase + OFF_PROG + xi * 4;
+
+    // C (and S) rows stream through a private cp.async ring of R stages per warp
+    const uint32_t ring = sbase + OFF_RING + wi * (R * SB);
+    const long long rs = (long long)a.width1 * Dp * (up ? -1 : 1); // int16 elements to the next row of this sweep
+    const long long o0 = (long long)x * Dp + (up ? (long long)(H - 1) * a.width1 * Dp : 0);
+    const bool wantS = acc && !(split && !helper); // the column warp of a split column never touches S
+    const int16_t *src[NLD];
+    uint32_t dsto[NLD];
+    bool ldok[NLD];
+#pragma unroll
+    for (int q = 0; q < NLD; q++) {
+        const int seg = lane + 32 * q;
+        const int isS = seg / (DW / 4), r = seg % (DW / 4);
+        src[q] = (isS ? a.S : a.C) + o0 + r * 8;
+        dsto[q] = ring + seg * 16;
+        ldok[q] = seg < NSEG && (wantS || !isS);
+    }
+    uint32_t o_iss = 0; // stage (byte offset) the next row is loaded into
+    // rows past the end of the sweep are "loaded" with a source size of 0 (nothing is read, the stage is zero-filled): no branch
+    auto issue = [&](bool live) {
+        const uint32_t sz = live ? 16u : 0u;
+#pragma unroll
+        for (int q = 0; q < NLD; q++) {
+            if (ldok[q]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dsto[q] + o_iss), "l"(src[q]), "r"(sz) : "memory");
+            src[q] += rs;
+        }
+        o_iss = (o_iss + SB) & RMASK;
+    };
+#pragma unroll 1
+    for (int p = 0; p < R - 1; p++) {
+        issue(p < H);
+        cp_async_commit();
+    }
+    int16_t *sp = (acc ? a.S : a.S2) + o0 + lane * 2 * NP; // this lane's output words in the row of step t
+    const uint32_t cur0 = ring + lane * NP * 4;
+    uint32_t o_cur = 0; // stage of row t
+
+    uint32_t c[NP], s[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) s[i] = padmask[i];
+    cp_async_wait<R - 2>();
+    __syncwarp();
+    lds_s<NP>(cur0, c);
+    if (wantS) lds_s<NP>(cur0 + CHB, s);
+
+    // end of a row: start the load of row t+R-1, wait for row t+1, fetch it
+    auto next_row = [&](int t) {
+        __syncwarp();
+        issue(t + R - 1 < H);
+        cp_async_commit();
+        cp_async_wait<R - 2>(); // row t+1 has landed
+        __syncwarp();
+        o_cur = (o_cur + SB) & RMASK;
+        lds_s<NP>(cur0 + o_cur, c);
+        if (wantS) lds_s<NP>(cur0 + o_cur + CHB, s);
+    };
+
+    if (helper) {
+        // ---- helper of a boundary column: vertical path, sums, S / S2 -------------------------------------------------
+        uint32_t Td[NP], L2[NP], v[NP];
+#pragma unroll
+        for (int i = 0; i < NP; i++) Td[i] = padmask[i];
+#pragma unroll 1
+        for (int t = 0; t < H; t++) {
+            sgm_step<NP, PAD>(Td, c, L2, padmask, P1v, P2mP1v, lane);
+            mbar_wait_tight(xfull + (t & (XR - 1)) * 8, (uint32_t)(t / XR) & 1u, a.err);
+            lds_s<NP>(xslot + (t & (XR - 1)) * CHB, v);
+#pragma unroll
+            for (int i = 0; i < NP; i++) {
+                const uint32_t u = __viaddmin_u16x2(v[i], L2[i], BIG);
+                s[i] = acc ? __viaddmin_u16x2(s[i], u, BIG) : u;
+            }
+            stcg_regs<NP>(sp, s);
+            sp += rs;
+            __syncwarp(); // every lane has its words of ring slot t: the column warp may write row t+XR into it
+            if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(xprog), "r"(t + 1) : "memory");
+            next_row(t);
+        }
+        return;
+    }
+
+    uint32_t T0[NP], T1[NP], L0[NP], L1[NP];
+    if (split) {
+        // ---- boundary column: the two diagonal paths and the hand-over to the neighbour CTA ----------------------------
+        // The diagonal that leaves the CTA (dir_o) is computed FIRST and written to the neighbour's ring, the one that enters
+        // (dir_o ^ 1) is polled for SECOND (its load was issued at the end of the previous row), so that the hand-over latency
+        // overlaps the rest of the row on both sides.
+        const int dir_o = glob_r ? 0 : 1, dir_i = dir_o ^ 1;
+        const int js = up ? 1 : 0;
+        const size_t HJ = (size_t)(G > 1 ? G - 1 : 1) * 2 * HO_DIR;
+        const int b = glob_r ? (int)blockIdx.x : (int)blockIdx.x - 1; // boundary between CTA b and b+1
+        const uint32_t *in_g = a.ho + js * HJ + ((size_t)b * 2 + dir_i) * HO_DIR + lane * NP;
+        uint32_t *out_g = a.ho + js * HJ + ((size_t)b * 2 + dir_o) * HO_DIR + lane * NP;
+        const uint32_t in_sm = in_s[dir_o], out_sm = out_s[dir_i];
+        const uint32_t nb_mb = glob_r ? my_mb - 16 : my_mb + 16; // the one neighbour inside the CTA
+        const bool has_nb = glob_r ? has_l : has_r;              // (n >= 3: always)
+        uint32_t Tpre[NP];
+#pragma unroll
+        for (int i = 0; i < NP; i++) Tpre[i] = padmask[i];
+        auto row = [&](int t, auto par_tag) {
+            constexpr int PAR = decltype(par_tag)::value; // t & 1
+            uint32_t prog;
+            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(prog) : "r"(xprog) : "memory");
+            if (t > 0 && has_nb) mbar_wait_tight(my_mb + (PAR ^ 1) * 8, (uint32_t)((t - 1) >> 1) & 1u, a.err);
+            lds_s<NP>(in_sm + (PAR ^ 1) * PSB, T0);
+            sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
+            ho_write<NP>(out_g + (t & (HO_SLOTS - 1)) * DW, ((t >> 2) & 1) ? 0x80008000u : 0u, T0);
+            if (t == 0) {
+#pragma unroll
+                for (int i = 0; i < NP; i++) T1[i] = padmask[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < NP; i++) T1[i] = Tpre[i]; // loaded at the end of the previous row
+                ho_read<NP>(in_g + ((t - 1) & (HO_SLOTS - 1)) * DW, (((t - 1) >> 2) & 1) ? 0x80008000u : 0u, T1, a.err, true);
+            }
+            sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
+            sts_s<NP>(out_sm + PAR * PSB, T1);
+            __syncwarp();
+            if (lane == 0 && has_nb) mbar_arrive(nb_mb + PAR * 8); // this column's row-t state is in its slot
+            ho_load<NP>(in_g + (t & (HO_SLOTS - 1)) * DW, Tpre);   // the neighbour CTA wrote it early in ITS row t
+            // sat(L0 + L1) to the helper (ring slot t mod XR is free once the helper has finished row t - XR)
+            if (t >= XR && (int)prog < t - XR + 1) {
+                int spins = 0;
+                unsigned long long t0 = 0;
+                do {
+                    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(prog) : "r"(xprog) : "memory");
+                    if (wait_expired(++spins, t0, a.err)) {
+                        *(volatile int *)a.err = 1;
+                        break;
+                    }
+                } while ((int)prog < t - XR + 1);
+            }
+            uint32_t v[NP];
+#pragma unroll
+            for (int i = 0; i < NP; i++) v[i] = __viaddmin_u16x2(L0[i], L1[i], BIG);
+            sts_s<NP>(xslot + (t & (XR - 1)) * CHB, v);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(xfull + (t & (XR - 1)) * 8);
+            next_row(t);
+        };
+#pragma unroll 1
+        for (int t = 0; t < H; t += 2) {
+            row(t, std::integral_constant<int, 0>{});
+            if (t + 1 < H) row(t + 1, std::integral_constant<int, 1>{});
+        }
+        return;
+    }
+
+    // ---- interior column (or a column on the image border): all three paths -----------------------------------------------
+    uint32_t Td[NP], L2[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) Td[i] = padmask[i];
+    const bool waits = has_l || has_r;
+    const bool arrives = (lane == 0 && has_l) || (lane == 1 && has_r);
+    const uint32_t arr_mb = lane == 0 ? my_mb - 16 : my_mb + 16;
+    auto row = [&](int t, auto par_tag) {
+        constexpr int PAR = decltype(par_tag)::value; // t & 1
+        // both neighbours' row t-1 states are in their slots (they arrive on THIS warp's barrier; even rows on the first
+        // barrier, odd rows on the second: a neighbour may run one row ahead)
+        if (t > 0 && waits) mbar_wait_tight(my_mb + (PAR ^ 1) * 8, (uint32_t)((t - 1) >> 1) & 1u, a.err);
+        lds_s<NP>(in_s[0] + (PAR ^ 1) * PSB, T0);
+        lds_s<NP>(in_s[1] + (PAR ^ 1) * PSB, T1);
+        sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
+        sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
+        sts_s<NP>(out_s[0] + PAR * PSB, T0);
+        sts_s<NP>(out_s[1] + PAR * PSB, T1);
+        __syncwarp();
+        if (arrives) mbar_arrive(arr_mb + PAR * 8); // lane 0 on the left neighbour's barrier, lane 1 on the right neighbour's
+        sgm_step<NP, PAD>(Td, c, L2, padmask, P1v, P2mP1v, lane);
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            uint32_t v = __viaddmin_u16x2(L0[i], L1[i], BIG);
+            v = __viaddmin_u16x2(v, L2[i], BIG);
+            s[i] = acc ? __viaddmin_u16x2(s[i], v, BIG) : v;
+        }
+        stcg_regs<NP>(sp, s);
+        sp += rs;
+        next_row(t);
+    };
+#pragma unroll 1
+    for (int t = 0; t < H; t += 2) {
+        row(t, std::integral_constant<int, 0>{});
+        if (t + 1 < H) row(t + 1, std::integral_constant<int, 1>{});
+    }
+}
+
 bool sweep_plain_launch()
 {
     const char *e = getenv("B2S_SWEEP_COOPERATIVE");
@@ -849,14 +1137,22 @@ bool sweep_plain_launch()
     return getenv("CUDA_MPS_PIPE_DIRECTORY") == nullptr; // shared through MPS: other clients' kernels hold SMs we cannot see
 }
 
-template <int NP, bool PAD, int JW, int R> cudaError_t launch_vsweep_t(b2s_ctx *c, const VsArgs &a, int G, size_t smem)
+// launch of a sweep grid (all G strips co-resident): attribute once per kernel and device, occupancy check, plain or cooperative
+template <typename K> cudaError_t launch_sweep_grid(b2s_ctx *c, K kernel, const VsArgs &a, int G, int threads, size_t smem)
 {
-    static std::once_flag once[64]; // per instantiation and device (the attribute belongs to the device's context)
+    static std::mutex mu;
+    static std::set<std::pair<const void *, int>> done; // (kernel, device): the attribute belongs to the device's context
     cudaError_t e = cudaSuccess;
-    std::call_once(once[c->device & 63], [&] { e = cudaFuncSetAttribute(agg_vsweep_kernel<NP, PAD, JW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
-    if (e != cudaSuccess) return e;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        const auto key = std::make_pair((const void *)kernel, c->device);
+        if (!done.count(key)) {
+            if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) != cudaSuccess) return e;
+            done.insert(key);
+        }
+    }
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, agg_vsweep_kernel<NP, PAD, JW, R>, a.n * JW * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1 || G > occ * c->num_sms) return cudaErrorCooperativeLaunchTooLarge; // all strips must be co-resident
     // The strips spin on their neighbours, so every CTA must be resident.  Two ways to get that:
@@ -868,11 +1164,11 @@ template <int NP, bool PAD, int JW, int R> cudaError_t launch_vsweep_t(b2s_ctx *
     //    for device-resident batches (515 pairs/s either way), 5 % end to end (460 against 484 pairs/s): a cooperative grid does
     //    not overlap the other streams' copies and small kernels as freely.
     if (sweep_plain_launch()) {
-        agg_vsweep_kernel<NP, PAD, JW, R><<<G, a.n * JW * 32, smem, c->stream>>>(a);
+        kernel<<<G, threads, smem, c->stream>>>(a);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(G);
-        cfg.blockDim = dim3(a.n * JW * 32);
+        cfg.blockDim = dim3(threads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = c->stream;
         cudaLaunchAttribute attr[1];
@@ -880,10 +1176,24 @@ template <int NP, bool PAD, int JW, int R> cudaError_t launch_vsweep_t(b2s_ctx *
         attr[0].val.cooperative = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if ((e = cudaLaunchKernelEx(&cfg, agg_vsweep_kernel<NP, PAD, JW, R>, a)) != cudaSuccess) return e;
+        if ((e = cudaLaunchKernelEx(&cfg, kernel, a)) != cudaSuccess) return e;
     }
     c->launches++;
     return cudaGetLastError();
+}
+template <int NP, bool PAD, int JW, int R, unsigned WH> cudaError_t launch_vsweep_w(b2s_ctx *c, const VsArgs &a, int G, size_t smem)
+{
+    return launch_sweep_grid(c, agg_vsweep_kernel<NP, PAD, JW, R, WH>, a, G, a.n * JW * 32, smem);
+}
+template <int NP, bool PAD, int JW, int R> cudaError_t launch_vsweep_t(b2s_ctx *c, const VsArgs &a, int G, size_t smem)
+{
+    if constexpr (NP == 2 && !PAD && JW == 2 && R == 8) { // EXPERIMENT: suspend-time hint of the neighbour waits
+        static const int wh = getenv("B2S_VS_WAIT") ? atoi(getenv("B2S_VS_WAIT")) : 0;
+        if (wh == 1) return launch_vsweep_w<NP, PAD, JW, R, 1>(c, a, G, smem);
+        if (wh == 2) return launch_vsweep_w<NP, PAD, JW, R, 2>(c, a, G, smem);
+        if (wh == 3) return launch_vsweep_w<NP, PAD, JW, R, 3>(c, a, G, smem);
+    }
+    return launch_vsweep_w<NP, PAD, JW, R, 0>(c, a, G, smem);
 }
 template <int NP, bool PAD, int JW> cudaError_t launch_vsweep_r(b2s_ctx *c, const VsArgs &a, int G)
 {
@@ -893,8 +1203,25 @@ template <int NP, bool PAD, int JW> cudaError_t launch_vsweep_r(b2s_ctx *c, cons
     return cudaErrorInvalidConfiguration;
 }
 // J sweeps (1 = top-down only, 2 = both): in one CTA when 2n warps fit, else one launch per sweep
+// both sweeps with the boundary columns split between a column warp and a helper warp (agg_vsweep2_kernel); false: not applicable
+template <int NP, bool PAD> bool launch_vsweep2(b2s_ctx *c, const VsArgs &a, int G, cudaError_t *e)
+{
+    if constexpr (NP == 1 || NP == 2 || NP == 4) {
+        static const bool off = getenv("B2S_VSWEEP2") && atoi(getenv("B2S_VSWEEP2")) == 0;
+        const int n = a.n, warps = 2 * n + 4;
+        if (off || n < 3 || warps > 32) return false;
+        const size_t fixed = (size_t)2 * n * 16 + 4 * 8 * 8 + 16 + (size_t)2 * 2 * 2 * (n + 2) * 128 * NP + (size_t)4 * 8 * 128 * NP;
+        const size_t stage = (size_t)warps * 2 * 128 * NP;
+        if (fixed + 8 * stage <= 216 * 1024) *e = launch_sweep_grid(c, agg_vsweep2_kernel<NP, PAD, 8>, a, G, warps * 32, fixed + 8 * stage);
+        else if (fixed + 4 * stage <= 216 * 1024) *e = launch_sweep_grid(c, agg_vsweep2_kernel<NP, PAD, 4>, a, G, warps * 32, fixed + 4 * stage);
+        else return false;
+        return true;
+    } else return false;
+}
 template <int NP, bool PAD> cudaError_t launch_vsweep_j(b2s_ctx *c, VsArgs &a, int G, int J)
 {
+    cudaError_t e2 = cudaSuccess;
+    if (J == 2 && launch_vsweep2<NP, PAD>(c, a, G, &e2)) return e2;
     if (J == 2 && a.n * 2 <= 32) return launch_vsweep_r<NP, PAD, 2>(c, a, G);
     for (int j = 0; j < J; j++) {
         a.up = j;

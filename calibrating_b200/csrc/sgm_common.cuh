@@ -282,6 +282,59 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t addr, uint32_t parity, 
     } while (!ok);
 }
 
+// The same wait with the retry loop written out: a warp that waits for a neighbour re-issues TRYWAIT about every 66 cycles (the
+// hardware's own suspend limit; ptxas drops the suspend-time hint on sm_100a), and every instruction of the retry path takes an
+// issue slot from the warps that are not waiting.  The compiler's loop costs 8 instructions per retry (it rebuilds the operands),
+// this one 2.75: four attempts per trip, the time-out check (wait_expired) only every 1024 attempts.
+__device__ __noinline__ void mbar_wait_retry(uint32_t addr, uint32_t parity, int *err)
+{
+    uint32_t ok;
+    unsigned long long t0 = 0;
+    int spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .u32 n;\n"
+            "mov.u32 n, 256;\n"
+            "B2S_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "@p bra B2S_DONE;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "@p bra B2S_DONE;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "@p bra B2S_DONE;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "@p bra B2S_DONE;\n"
+            "sub.u32 n, n, 1;\n"
+            "setp.ne.u32 p, n, 0;\n"
+            "@p bra B2S_WAIT;\n" // (falls through with p false: no success yet)
+            "B2S_DONE:\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}"
+            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) break;
+        spins += 256;
+        if (wait_expired(spins, t0, err)) {
+            *(volatile int *)err = 1;
+            break;
+        }
+    }
+}
+// fast path inline (one TRYWAIT: the phase has usually completed), everything else out of line
+__device__ __forceinline__ void mbar_wait_tight(uint32_t addr, uint32_t parity, int *err)
+{
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (!ok) mbar_wait_retry(addr, parity, err);
+}
+template <unsigned MODE> __device__ __forceinline__ void mbar_wait_hint(uint32_t addr, uint32_t parity, int *err)
+{
+    if constexpr ((MODE & 1u) == 0) mbar_wait(addr, parity, err);
+    else mbar_wait_tight(addr, parity, err);
+}
+
 // 1-D bulk copy global -> shared (UBLKCP), completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t sdst, const void *gsrc, uint32_t bytes, uint32_t mbar)
 {

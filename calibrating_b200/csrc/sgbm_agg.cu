@@ -576,6 +576,7 @@ struct VsArgs {
     int up;       // JW == 1 only: 0 = top-down sweep, 1 = bottom-up sweep
     uint32_t *ho; // hand-over rings [J][G-1][2][HO_SLOTS][32*NP] u32
     int *err;     // set to 1 if a hand-over wait timed out (never in a correct run)
+    int dbg;      // what-if timing switches (B2S_VS2_FAKE; results are wrong when set): 1 no hand-over polling, 2 no neighbour waits, 4 late prefetch
 };
 template <int NP> __device__ __forceinline__ void lds_regs(const uint32_t *src, uint32_t (&v)[NP])
 {
@@ -651,7 +652,7 @@ template <int NP> __device__ __forceinline__ void ho_write(uint32_t *p, uint32_t
 // writes the sum of its three paths to S2 without reading anything but C, so the two sweeps share no data at all.
 // Warps synchronise only with their two neighbour columns (one mbarrier per warp, phase = row), so the warps of an SM
 // drift apart by up to a row per column and keep the issue slots busy while others wait.
-template <int NP, bool PAD, int JW, int R, unsigned WH = 0>
+template <int NP, bool PAD, int JW, int R>
 __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
 {
     constexpr int DW = 32 * NP;           // 32-bit words of one pixel's d-chunk
@@ -665,21 +666,8 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
     const int lane = threadIdx.x & 31;
     const int wi = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); // warp-uniform by construction
     const int n = a.n, G = gridDim.x, H = a.H, Dp = 64 * NP;
-    int jl = JW == 2 ? (wi >= n ? 1 : 0) : 0; // sweep slot inside the CTA
-    int w = wi - jl * n;                      // column inside the strip
-    if constexpr ((WH & 2u) != 0 && JW == 2) {
-        // the four warps on the strip's boundaries carry the hand-over to the neighbour CTAs and are the slowest of the strip: one per
-        // scheduler (warp id mod 4) instead of two on scheduler 0 and two on scheduler 1
-        if (n >= 3) {
-            if (wi < 4) {
-                jl = wi >> 1;
-                w = (wi & 1) ? n - 1 : 0;
-            } else {
-                jl = (wi - 4) / (n - 2);
-                w = 1 + (wi - 4) % (n - 2);
-            }
-        }
-    }
+    const int jl = JW == 2 ? (wi >= n ? 1 : 0) : 0; // sweep slot inside the CTA
+    const int w = wi - jl * n;                      // column inside the strip
     const bool up = JW == 2 ? jl == 1 : a.up != 0;  // bottom-up sweep?
     const bool acc = !up;                           // top-down: S += paths; bottom-up: S2 = paths
     const int x = blockIdx.x * n + w;
@@ -797,7 +785,7 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
                     for (int i = 0; i < NP; i++) T0[i] = padmask[i];
                 } else ho_read<NP>(in_g[0] + ((t - 1) & (HO_SLOTS - 1)) * DW, (((t - 1) >> 2) & 1) ? 0x80008000u : 0u, T0, a.err);
             } else {
-                if (in_mb[0]) mbar_wait_hint<WH>(in_mb[0] + mb_off, par_in, a.err);
+                if (in_mb[0]) mbar_wait(in_mb[0] + mb_off, par_in, a.err);
                 lds_s<NP>(in_s[0] + pin, T0);
             }
             if (EDGE && polls) {
@@ -814,7 +802,7 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
                 }
                 sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
             } else {
-                if (in_mb[1]) mbar_wait_hint<WH>(in_mb[1] + mb_off, par_in, a.err);
+                if (in_mb[1]) mbar_wait(in_mb[1] + mb_off, par_in, a.err);
                 lds_s<NP>(in_s[1] + pin, T1);
                 sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
                 sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
@@ -871,7 +859,7 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
 //   * the row loop is unrolled by two so that barrier parities and slot parities are immediates, ring stages advance by mask
 //     arithmetic, and the retry path of the waits is the 2.75-instruction loop of mbar_wait_tight.
 // Needs 2n + 4 <= 32 warps and n >= 3 columns per strip; everything else stays with agg_vsweep_kernel.
-template <int NP, bool PAD, int R>
+template <int NP, bool PAD, int R, bool DBG = false>
 __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
 {
     static_assert(NP == 1 || NP == 2 || NP == 4, "ring stages advance by mask arithmetic");
@@ -888,6 +876,7 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
     const int lane = threadIdx.x & 31;
     const int wi = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); // warp-uniform by construction
     const int n = a.n, G = gridDim.x, H = a.H, Dp = 64 * NP;
+    const int dbg = DBG ? a.dbg : 0; // what-if timing switches, compiled out of the production kernel
     int jl, w;
     bool helper = false;
     if (wi < 8) { // the strip's boundary columns and their helpers
@@ -1009,7 +998,7 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
 #pragma unroll 1
         for (int t = 0; t < H; t++) {
             sgm_step<NP, PAD>(Td, c, L2, padmask, P1v, P2mP1v, lane);
-            mbar_wait_tight(xfull + (t & (XR - 1)) * 8, (uint32_t)(t / XR) & 1u, a.err);
+            if (!(dbg & 2)) mbar_wait_tight(xfull + (t & (XR - 1)) * 8, (uint32_t)(t / XR) & 1u, a.err);
             lds_s<NP>(xslot + (t & (XR - 1)) * CHB, v);
 #pragma unroll
             for (int i = 0; i < NP; i++) {
@@ -1047,7 +1036,8 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
             constexpr int PAR = decltype(par_tag)::value; // t & 1
             uint32_t prog;
             asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(prog) : "r"(xprog) : "memory");
-            if (t > 0 && has_nb) mbar_wait_tight(my_mb + (PAR ^ 1) * 8, (uint32_t)((t - 1) >> 1) & 1u, a.err);
+            if ((dbg & 4) && t > 0) ho_load<NP>(in_g + ((t - 1) & (HO_SLOTS - 1)) * DW, Tpre);
+            if (t > 0 && has_nb && !(dbg & 2)) mbar_wait_tight(my_mb + (PAR ^ 1) * 8, (uint32_t)((t - 1) >> 1) & 1u, a.err);
             lds_s<NP>(in_sm + (PAR ^ 1) * PSB, T0);
             sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
             ho_write<NP>(out_g + (t & (HO_SLOTS - 1)) * DW, ((t >> 2) & 1) ? 0x80008000u : 0u, T0);
@@ -1057,13 +1047,13 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
             } else {
 #pragma unroll
                 for (int i = 0; i < NP; i++) T1[i] = Tpre[i]; // loaded at the end of the previous row
-                ho_read<NP>(in_g + ((t - 1) & (HO_SLOTS - 1)) * DW, (((t - 1) >> 2) & 1) ? 0x80008000u : 0u, T1, a.err, true);
+                if (!(dbg & 1)) ho_read<NP>(in_g + ((t - 1) & (HO_SLOTS - 1)) * DW, (((t - 1) >> 2) & 1) ? 0x80008000u : 0u, T1, a.err, true);
             }
             sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
             sts_s<NP>(out_sm + PAR * PSB, T1);
             __syncwarp();
             if (lane == 0 && has_nb) mbar_arrive(nb_mb + PAR * 8); // this column's row-t state is in its slot
-            ho_load<NP>(in_g + (t & (HO_SLOTS - 1)) * DW, Tpre);   // the neighbour CTA wrote it early in ITS row t
+            if (!(dbg & 4)) ho_load<NP>(in_g + (t & (HO_SLOTS - 1)) * DW, Tpre);   // the neighbour CTA wrote it early in ITS row t
             // sat(L0 + L1) to the helper (ring slot t mod XR is free once the helper has finished row t - XR)
             if (t >= XR && (int)prog < t - XR + 1) {
                 int spins = 0;
@@ -1103,7 +1093,7 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
         constexpr int PAR = decltype(par_tag)::value; // t & 1
         // both neighbours' row t-1 states are in their slots (they arrive on THIS warp's barrier; even rows on the first
         // barrier, odd rows on the second: a neighbour may run one row ahead)
-        if (t > 0 && waits) mbar_wait_tight(my_mb + (PAR ^ 1) * 8, (uint32_t)((t - 1) >> 1) & 1u, a.err);
+        if (t > 0 && waits && !(dbg & 2)) mbar_wait_tight(my_mb + (PAR ^ 1) * 8, (uint32_t)((t - 1) >> 1) & 1u, a.err);
         lds_s<NP>(in_s[0] + (PAR ^ 1) * PSB, T0);
         lds_s<NP>(in_s[1] + (PAR ^ 1) * PSB, T1);
         sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
@@ -1181,19 +1171,9 @@ template <typename K> cudaError_t launch_sweep_grid(b2s_ctx *c, K kernel, const 
     c->launches++;
     return cudaGetLastError();
 }
-template <int NP, bool PAD, int JW, int R, unsigned WH> cudaError_t launch_vsweep_w(b2s_ctx *c, const VsArgs &a, int G, size_t smem)
-{
-    return launch_sweep_grid(c, agg_vsweep_kernel<NP, PAD, JW, R, WH>, a, G, a.n * JW * 32, smem);
-}
 template <int NP, bool PAD, int JW, int R> cudaError_t launch_vsweep_t(b2s_ctx *c, const VsArgs &a, int G, size_t smem)
 {
-    if constexpr (NP == 2 && !PAD && JW == 2 && R == 8) { // EXPERIMENT: suspend-time hint of the neighbour waits
-        static const int wh = getenv("B2S_VS_WAIT") ? atoi(getenv("B2S_VS_WAIT")) : 0;
-        if (wh == 1) return launch_vsweep_w<NP, PAD, JW, R, 1>(c, a, G, smem);
-        if (wh == 2) return launch_vsweep_w<NP, PAD, JW, R, 2>(c, a, G, smem);
-        if (wh == 3) return launch_vsweep_w<NP, PAD, JW, R, 3>(c, a, G, smem);
-    }
-    return launch_vsweep_w<NP, PAD, JW, R, 0>(c, a, G, smem);
+    return launch_sweep_grid(c, agg_vsweep_kernel<NP, PAD, JW, R>, a, G, a.n * JW * 32, smem);
 }
 template <int NP, bool PAD, int JW> cudaError_t launch_vsweep_r(b2s_ctx *c, const VsArgs &a, int G)
 {
@@ -1207,11 +1187,17 @@ template <int NP, bool PAD, int JW> cudaError_t launch_vsweep_r(b2s_ctx *c, cons
 template <int NP, bool PAD> bool launch_vsweep2(b2s_ctx *c, const VsArgs &a, int G, cudaError_t *e)
 {
     if constexpr (NP == 1 || NP == 2 || NP == 4) {
-        static const bool off = getenv("B2S_VSWEEP2") && atoi(getenv("B2S_VSWEEP2")) == 0;
+        const bool off = getenv("B2S_VSWEEP2") && atoi(getenv("B2S_VSWEEP2")) == 0; // (tests: the same cases through agg_vsweep_kernel)
         const int n = a.n, warps = 2 * n + 4;
         if (off || n < 3 || warps > 32) return false;
         const size_t fixed = (size_t)2 * n * 16 + 4 * 8 * 8 + 16 + (size_t)2 * 2 * 2 * (n + 2) * 128 * NP + (size_t)4 * 8 * 128 * NP;
         const size_t stage = (size_t)warps * 2 * 128 * NP;
+        if constexpr (NP == 2 && !PAD) { // what-if timings of the benchmark configuration (scripts/vs_variants.sh)
+            if (a.dbg && fixed + 8 * stage <= 216 * 1024) {
+                *e = launch_sweep_grid(c, agg_vsweep2_kernel<NP, PAD, 8, true>, a, G, warps * 32, fixed + 8 * stage);
+                return true;
+            }
+        }
         if (fixed + 8 * stage <= 216 * 1024) *e = launch_sweep_grid(c, agg_vsweep2_kernel<NP, PAD, 8>, a, G, warps * 32, fixed + 8 * stage);
         else if (fixed + 4 * stage <= 216 * 1024) *e = launch_sweep_grid(c, agg_vsweep2_kernel<NP, PAD, 4>, a, G, warps * 32, fixed + 4 * stage);
         else return false;
@@ -1279,6 +1265,7 @@ cudaError_t launch_vsweep(b2s_ctx *c, int n, int J)
     if ((e = cudaMemsetAsync(c->agg_ho.p, 0xFF, ho_bytes, c->stream)) != cudaSuccess) return e;
     a.ho = c->agg_ho.as<uint32_t>();
     a.err = c->agg_err; // (launch_aggregate)
+    a.dbg = getenv("B2S_VS2_FAKE") ? atoi(getenv("B2S_VS2_FAKE")) : 0;
     const bool pad = g.D != g.Dp;
     const bool chained = sweep_plain_launch(); // (cooperative launches need no ordering between handles)
     std::unique_lock<std::mutex> lock(g_chain.mu, std::defer_lock);

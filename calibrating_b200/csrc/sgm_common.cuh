@@ -329,12 +329,6 @@ __device__ __forceinline__ void mbar_wait_tight(uint32_t addr, uint32_t parity, 
                  : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
     if (!ok) mbar_wait_retry(addr, parity, err);
 }
-template <unsigned MODE> __device__ __forceinline__ void mbar_wait_hint(uint32_t addr, uint32_t parity, int *err)
-{
-    if constexpr ((MODE & 1u) == 0) mbar_wait(addr, parity, err);
-    else mbar_wait_tight(addr, parity, err);
-}
-
 // 1-D bulk copy global -> shared (UBLKCP), completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t sdst, const void *gsrc, uint32_t bytes, uint32_t mbar)
 {

@@ -95,13 +95,16 @@ def test_wavefront_schedule(handle, seed, monkeypatch):
         handle.call("b2s_set_option", 3, 0)
 
 
-@pytest.mark.parametrize("cols", ["1", "2", "3", "5", "32", "legacy"])
+@pytest.mark.parametrize("split", ["1", "0"])
+@pytest.mark.parametrize("cols", ["1", "2", "3", "5", "13", "14", "32", "legacy"])
 @pytest.mark.parametrize("seed", [1, 2, 3, 5, 6])
-def test_aggregation_strip_handover(handle, seed, cols, monkeypatch):
+def test_aggregation_strip_handover(handle, seed, cols, split, monkeypatch):
     """The round-1 schedule (B2S_AGG_SCHEDULE=sweep): the fused vertical sweep cut into strips of 1..32 columns (several CTAs
     exchanging diagonal states through the global hand-over rings) and the legacy one-kernel-per-direction path all give the
-    oracle's S volume."""
+    oracle's S volume.  split = 1: MODE_HH strips of 3..14 columns run agg_vsweep2_kernel (boundary columns shared with a helper
+    warp); split = 0: the same cases through agg_vsweep_kernel."""
     monkeypatch.setenv("B2S_AGG_SCHEDULE", "sweep")
+    monkeypatch.setenv("B2S_VSWEEP2", split)
     if cols == "legacy":
         monkeypatch.setenv("B2S_AGG_LEGACY", "1")
     else:

@@ -425,7 +425,7 @@ def main():
         pass
     achieved = AGG_BYTES_PER_PAIR / (agg_ms * 1e-3) / 1e9  # = (bytes per pair / launches) / (group time / launches)
     if n_launch == 3:
-        names = ["agg_hscan_vsum_kernel (+x, forms C from the cost stage's row sums)", "agg_vsweep_kernel (6 of 8 directions)",
+        names = ["agg_hscan_vsum_kernel (+x, forms C from the cost stage's row sums)", "agg_vsweep2_kernel (6 of 8 directions)",
                  "agg_hscan_kernel<ACCUM2, WTA> (-x, folds S2, winner-take-all fused)"]
         dirs = [1, 6, 1]
     elif n_launch == 2:
@@ -443,7 +443,7 @@ def main():
         "e2e": {"value": world * K * P / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": P * 2 * H * W * CN, "d2h_bytes_per_step": P * H * W * 4,
                 "api": "DisparityBatchEngine.compute_batch (host uint8 pairs -> host float32 disparity), wall clock between synchronisations"
                        + ("; N > 1: results stay on the device, NCCL all-gather of every step's disparities and the read of the own shard into pinned host memory, both overlapped with the next step's kernels" if world > 1 else "")},
-        "roofline": {"bound": "hbm", "kernel": "aggregation group: %d launches per pair (dominant: agg_vsweep_kernel)" % n_launch,
+        "roofline": {"bound": "hbm", "kernel": "aggregation group: %d launches per pair (dominant: agg_vsweep2_kernel)" % n_launch,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note,
                      "build_hash": build_hash,
                      "first_launch_plain_scan": {"ms_per_launch": [round(t, 4) for t in alt_parts], "group_ms": round(float(sum(alt_parts)), 4),

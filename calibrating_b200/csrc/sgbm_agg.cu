@@ -25,6 +25,7 @@
 #include <mutex>
 #include <set>
 #include <utility>
+#include <vector>
 #include <type_traits>
 
 #include "b2s_internal.h"
@@ -576,6 +577,7 @@ struct VsArgs {
     int up;       // JW == 1 only: 0 = top-down sweep, 1 = bottom-up sweep
     uint32_t *ho; // hand-over rings [J][G-1][2][HO_SLOTS][32*NP] u32
     int *err;     // set to 1 if a hand-over wait timed out (never in a correct run)
+    long long *trace; // development aid (B2S_VS2_TRACE): clock64 at fixed points of 16 rows of three CTAs, see scripts/vs2_trace.py
     int dbg;      // what-if timing switches (B2S_VS2_FAKE; results are wrong when set): 1 no hand-over polling, 2 no neighbour waits, 4 late prefetch
 };
 template <int NP> __device__ __forceinline__ void lds_regs(const uint32_t *src, uint32_t (&v)[NP])
@@ -859,7 +861,7 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep_kernel(VsArgs a)
 //   * the row loop is unrolled by two so that barrier parities and slot parities are immediates, ring stages advance by mask
 //     arithmetic, and the retry path of the waits is the 2.75-instruction loop of mbar_wait_tight.
 // Needs 2n + 4 <= 32 warps and n >= 3 columns per strip; everything else stays with agg_vsweep_kernel.
-template <int NP, bool PAD, int R, bool DBG = false>
+template <int NP, bool PAD, int R, bool DBG = false, bool TRACE = false>
 __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
 {
     static_assert(NP == 1 || NP == 2 || NP == 4, "ring stages advance by mask arithmetic");
@@ -877,6 +879,14 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
     const int wi = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); // warp-uniform by construction
     const int n = a.n, G = gridDim.x, H = a.H, Dp = 64 * NP;
     const int dbg = DBG ? a.dbg : 0; // what-if timing switches, compiled out of the production kernel
+    // TRACE: lane 0 of every warp of CTAs 60..62 stores clock64 at up to 8 points of rows 512..527 (trace[cta][warp][row][point])
+    const bool tr_cta = TRACE && blockIdx.x >= 60 && blockIdx.x < 63 && lane == 0;
+    long long *const tr_base = TRACE ? a.trace + ((long long)((int)blockIdx.x - 60) * 32 + wi) * 16 * 8 : nullptr;
+    auto mark = [&](int t, int point) {
+        if (TRACE) {
+            if (tr_cta && (unsigned)(t - 512) < 16u) tr_base[(t - 512) * 8 + point] = clock64();
+        }
+    };
     int jl, w;
     bool helper = false;
     if (wi < 8) { // the strip's boundary columns and their helpers
@@ -997,8 +1007,11 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
         for (int i = 0; i < NP; i++) Td[i] = padmask[i];
 #pragma unroll 1
         for (int t = 0; t < H; t++) {
+            mark(t, 0);
             sgm_step<NP, PAD>(Td, c, L2, padmask, P1v, P2mP1v, lane);
+            mark(t, 1);
             if (!(dbg & 2)) mbar_wait_tight(xfull + (t & (XR - 1)) * 8, (uint32_t)(t / XR) & 1u, a.err);
+            mark(t, 2);
             lds_s<NP>(xslot + (t & (XR - 1)) * CHB, v);
 #pragma unroll
             for (int i = 0; i < NP; i++) {
@@ -1009,7 +1022,9 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
             sp += rs;
             __syncwarp(); // every lane has its words of ring slot t: the column warp may write row t+XR into it
             if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(xprog), "r"(t + 1) : "memory");
+            mark(t, 3);
             next_row(t);
+            mark(t, 4);
         }
         return;
     }
@@ -1035,12 +1050,15 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
         auto row = [&](int t, auto par_tag) {
             constexpr int PAR = decltype(par_tag)::value; // t & 1
             uint32_t prog;
+            mark(t, 0);
             asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(prog) : "r"(xprog) : "memory");
             if ((dbg & 4) && t > 0) ho_load<NP>(in_g + ((t - 1) & (HO_SLOTS - 1)) * DW, Tpre);
             if (t > 0 && has_nb && !(dbg & 2)) mbar_wait_tight(my_mb + (PAR ^ 1) * 8, (uint32_t)((t - 1) >> 1) & 1u, a.err);
+            mark(t, 1);
             lds_s<NP>(in_sm + (PAR ^ 1) * PSB, T0);
             sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
             ho_write<NP>(out_g + (t & (HO_SLOTS - 1)) * DW, ((t >> 2) & 1) ? 0x80008000u : 0u, T0);
+            mark(t, 2);
             if (t == 0) {
 #pragma unroll
                 for (int i = 0; i < NP; i++) T1[i] = padmask[i];
@@ -1049,10 +1067,12 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
                 for (int i = 0; i < NP; i++) T1[i] = Tpre[i]; // loaded at the end of the previous row
                 if (!(dbg & 1)) ho_read<NP>(in_g + ((t - 1) & (HO_SLOTS - 1)) * DW, (((t - 1) >> 2) & 1) ? 0x80008000u : 0u, T1, a.err, true);
             }
+            mark(t, 3);
             sgm_step<NP, PAD>(T1, c, L1, padmask, P1v, P2mP1v, lane);
             sts_s<NP>(out_sm + PAR * PSB, T1);
             __syncwarp();
             if (lane == 0 && has_nb) mbar_arrive(nb_mb + PAR * 8); // this column's row-t state is in its slot
+            mark(t, 4);
             if (!(dbg & 4)) ho_load<NP>(in_g + (t & (HO_SLOTS - 1)) * DW, Tpre);   // the neighbour CTA wrote it early in ITS row t
             // sat(L0 + L1) to the helper (ring slot t mod XR is free once the helper has finished row t - XR)
             if (t >= XR && (int)prog < t - XR + 1) {
@@ -1072,7 +1092,9 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
             sts_s<NP>(xslot + (t & (XR - 1)) * CHB, v);
             __syncwarp();
             if (lane == 0) mbar_arrive(xfull + (t & (XR - 1)) * 8);
+            mark(t, 5);
             next_row(t);
+            mark(t, 6);
         };
 #pragma unroll 1
         for (int t = 0; t < H; t += 2) {
@@ -1091,9 +1113,11 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
     const uint32_t arr_mb = lane == 0 ? my_mb - 16 : my_mb + 16;
     auto row = [&](int t, auto par_tag) {
         constexpr int PAR = decltype(par_tag)::value; // t & 1
+        mark(t, 0);
         // both neighbours' row t-1 states are in their slots (they arrive on THIS warp's barrier; even rows on the first
         // barrier, odd rows on the second: a neighbour may run one row ahead)
         if (t > 0 && waits && !(dbg & 2)) mbar_wait_tight(my_mb + (PAR ^ 1) * 8, (uint32_t)((t - 1) >> 1) & 1u, a.err);
+        mark(t, 1);
         lds_s<NP>(in_s[0] + (PAR ^ 1) * PSB, T0);
         lds_s<NP>(in_s[1] + (PAR ^ 1) * PSB, T1);
         sgm_step<NP, PAD>(T0, c, L0, padmask, P1v, P2mP1v, lane);
@@ -1102,6 +1126,7 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
         sts_s<NP>(out_s[1] + PAR * PSB, T1);
         __syncwarp();
         if (arrives) mbar_arrive(arr_mb + PAR * 8); // lane 0 on the left neighbour's barrier, lane 1 on the right neighbour's
+        mark(t, 2);
         sgm_step<NP, PAD>(Td, c, L2, padmask, P1v, P2mP1v, lane);
 #pragma unroll
         for (int i = 0; i < NP; i++) {
@@ -1111,7 +1136,9 @@ __global__ void __launch_bounds__(1024, 1) agg_vsweep2_kernel(VsArgs a)
         }
         stcg_regs<NP>(sp, s);
         sp += rs;
+        mark(t, 3);
         next_row(t);
+        mark(t, 4);
     };
 #pragma unroll 1
     for (int t = 0; t < H; t += 2) {
@@ -1193,6 +1220,10 @@ template <int NP, bool PAD> bool launch_vsweep2(b2s_ctx *c, const VsArgs &a, int
         const size_t fixed = (size_t)2 * n * 16 + 4 * 8 * 8 + 16 + (size_t)2 * 2 * 2 * (n + 2) * 128 * NP + (size_t)4 * 8 * 128 * NP;
         const size_t stage = (size_t)warps * 2 * 128 * NP;
         if constexpr (NP == 2 && !PAD) { // what-if timings of the benchmark configuration (scripts/vs_variants.sh)
+            if (a.trace && fixed + 8 * stage <= 216 * 1024) {
+                *e = launch_sweep_grid(c, agg_vsweep2_kernel<NP, PAD, 8, false, true>, a, G, warps * 32, fixed + 8 * stage);
+                return true;
+            }
             if (a.dbg && fixed + 8 * stage <= 216 * 1024) {
                 *e = launch_sweep_grid(c, agg_vsweep2_kernel<NP, PAD, 8, true>, a, G, warps * 32, fixed + 8 * stage);
                 return true;
@@ -1266,6 +1297,13 @@ cudaError_t launch_vsweep(b2s_ctx *c, int n, int J)
     a.ho = c->agg_ho.as<uint32_t>();
     a.err = c->agg_err; // (launch_aggregate)
     a.dbg = getenv("B2S_VS2_FAKE") ? atoi(getenv("B2S_VS2_FAKE")) : 0;
+    a.trace = nullptr;
+    const char *trace_path = getenv("B2S_VS2_TRACE"); // development aid: dump the row timeline of three CTAs (scripts/vs2_trace.py)
+    const size_t trace_bytes = (size_t)3 * 32 * 16 * 8 * sizeof(long long);
+    if (trace_path) {
+        if ((e = cudaMalloc(&a.trace, trace_bytes)) != cudaSuccess) return e;
+        cudaMemsetAsync(a.trace, 0, trace_bytes, c->stream);
+    }
     const bool pad = g.D != g.Dp;
     const bool chained = sweep_plain_launch(); // (cooperative launches need no ordering between handles)
     std::unique_lock<std::mutex> lock(g_chain.mu, std::defer_lock);
@@ -1287,6 +1325,16 @@ cudaError_t launch_vsweep(b2s_ctx *c, int n, int J)
     default: e = cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;
+    if (a.trace) { // (development aid: synchronous on purpose)
+        std::vector<long long> host(trace_bytes / sizeof(long long));
+        if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;
+        if ((e = cudaMemcpy(host.data(), a.trace, trace_bytes, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+        cudaFree(a.trace);
+        if (FILE *f = fopen(trace_path, "wb")) {
+            fwrite(host.data(), 1, trace_bytes, f);
+            fclose(f);
+        }
+    }
     return chained ? cudaEventRecord(*evp, c->stream) : cudaSuccess;
 }
 

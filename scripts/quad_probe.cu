@@ -6,7 +6,7 @@
 #include <cuda_runtime.h>
 #include "sgm_common.cuh"
 
-template <int MODE> __global__ void __launch_bounds__(1024, 1) probe(uint32_t *out, long long *cyc, int iters, const int16_t *C = nullptr, int16_t *S = nullptr, int width1 = 0)
+template <int MODE> __global__ void __launch_bounds__(1024, 1) probe(uint32_t *out, long long *cyc, int iters, const int16_t *C = nullptr, int16_t *S = nullptr, int width1 = 0, int16_t *S2 = nullptr)
 {
     extern __shared__ __align__(16) uint32_t sm[];
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
@@ -133,15 +133,19 @@ template <int MODE> __global__ void __launch_bounds__(1024, 1) probe(uint32_t *o
         uint32_t T0[2], T1[2], Td[2], c[2], s[2], L0[2], L1[2], L2[2], pm[2] = {0, 0};
         T0[0] = T0[1] = T1[0] = T1[1] = Td[0] = Td[1] = 0;
         const uint32_t ring = (uint32_t)__cvta_generic_to_shared(sm) + wi * 8192, slot = ring + 4096 + lane * 8;
-        const int x = blockIdx.x * (blockDim.x >> 5) + wi;
-        const long long rs = (long long)width1 * 128;
+        const int nw = blockDim.x >> 5, half = nw / 2;
+        const bool upw = MODE == 5 && wi >= half;               // MODE 5: second half of the warps sweeps bottom-up and writes S2
+        const bool readS = MODE == 2 || (MODE == 5 && !upw);
+        const int x = MODE == 5 ? blockIdx.x * half + (upw ? wi - half : wi) : blockIdx.x * nw + wi;
+        const long long rs = (long long)width1 * 128 * (upw ? -1 : 1);
+        const long long o0 = (long long)x * 128 + (upw ? (long long)(iters - 1) * width1 * 128 : 0);
         const int isS = lane >> 4, r = lane & 15;
-        const int16_t *src = (isS ? S : C) + (long long)x * 128 + r * 8;
-        int16_t *sp = S + (long long)x * 128 + lane * 4;
+        const int16_t *src = (isS ? S : C) + o0 + r * 8;
+        int16_t *sp = (upw ? S2 : S) + o0 + lane * 4;
         const uint32_t dst = ring + lane * 16;
         uint32_t o_iss = 0, o_cur = 0;
         for (int p = 0; p < R - 1; p++) {
-            if (MODE == 2 || !isS) cp_async16_s(dst + o_iss, src);
+            if (readS || !isS) cp_async16_s(dst + o_iss, src);
             src += rs; o_iss = (o_iss + 512) & 4095;
             cp_async_commit();
         }
@@ -168,14 +172,14 @@ template <int MODE> __global__ void __launch_bounds__(1024, 1) probe(uint32_t *o
             stcg_regs<2>(sp, s);
             sp += rs;
             __syncwarp();
-            if (MODE == 2 || !isS) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + o_iss), "l"(src), "r"(it + R - 1 < iters ? 16u : 0u) : "memory");
+            if (readS || !isS) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + o_iss), "l"(src), "r"(it + R - 1 < iters ? 16u : 0u) : "memory");
             src += rs; o_iss = (o_iss + 512) & 4095;
             cp_async_commit();
             cp_async_wait<R - 2>();
             __syncwarp();
             o_cur = (o_cur + 512) & 4095;
             lds_s<2>(ring + o_cur + lane * 8, c);
-            if (MODE == 2) lds_s<2>(ring + o_cur + 256 + lane * 8, s);
+            if (readS) lds_s<2>(ring + o_cur + 256 + lane * 8, s);
         }
         out[blockIdx.x * blockDim.x + threadIdx.x] = s[0] ^ s[1] ^ T1[0] ^ Td[1];
     } else { // the pair layout of the shipped sweep: 2 words per lane, one pixel per warp
@@ -221,6 +225,16 @@ int main()
     cudaFuncSetAttribute(probe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 8192);
     cudaFuncSetAttribute(probe<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 8192);
     cudaFuncSetAttribute(probe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * 20480);
+    cudaFuncSetAttribute(probe<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 26 * 8192);
+    int16_t *S2;
+    cudaMalloc(&S2, (size_t)iters * W1 * 256);
+    for (int rep = 0; rep < 3; rep++) {
+        probe<5><<<138, 26 * 32, 26 * 8192>>>(out, cyc, iters, C, S, 138 * 13, S2);
+        cudaDeviceSynchronize();
+    }
+    cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
+    { double avg = 0; for (int i = 0; i < 138; i++) avg += h[i]; avg /= 138;
+      printf("pair, 13 columns x 2 sweeps per CTA on 138 CTAs (the shipped kernel's shape, no synchronisation): %7.1f cycles per row (%s)\n", avg / iters, cudaGetErrorString(cudaGetLastError())); }
     for (int mode = 0; mode < 5; mode++)
         for (int warps : {1, 2, 4, 6, 7, 8, 10, 12, 16, 24}) {
             for (int rep = 0; rep < 2; rep++) {

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from calibrating_b200 import build  # noqa: E402
 
-HOT = ["agg_vsweep_kernelILi2ELb0ELi2ELi8E", "agg_hscan_kernelILi2ELb0ELi2ELi1ELb0E", "agg_hscan_vsum_kernelILi2ELb0ELi5ELb0E", "pixcost_hsum_kernelILi3ELi104ELi0E",
+HOT = ["agg_vsweep2_kernelILi2ELb0ELi8ELb0E", "agg_vsweep_kernelILi2ELb0ELi2ELi8E", "agg_hscan_kernelILi2ELb0ELi2ELi1ELb0E", "agg_hscan_vsum_kernelILi2ELb0ELi5ELb0E", "pixcost_hsum_kernelILi3ELi104ELi0E",
        "agg_wave_kernelILi2ELb0E", "agg_vsweep6_kernelILb0E", "remap_lz4_kernelILi3ELb1E", "wta_kernelILi2ELb1ELi1E", "planes_kernelILi3E", "lr_median_kernel",
        "resize_u8_kernelILi3E", "cloud_emit_kernelILi3E"]
 KEY = ["VIMNMX3", "VIADDMNMX", "VIMNMX", "CREDUX", "UBLKCP", "SYNCS", "LDGSTS", "IDP", "SHFL", "PRMT", "LDS", "STS", "LDG", "STG", "ATOM", "RED", "BAR", "DADD", "DMUL", "DFMA"]

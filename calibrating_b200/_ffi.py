@@ -81,6 +81,7 @@ SIGNATURES = {
     "b2s_set_option": (c_int, [c_void_p, c_int, c_int]),
     "b2s_build_hash": (ctypes.c_char_p, []),
     "b2s_resize_nearest_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float]),
+    "b2s_interpolate_rbf": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "b2s_interpolate_sparse": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.POINTER(c_double), c_void_p, c_int, c_int, c_double, c_void_p]),
     "b2s_depth_to_point_cloud": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, ctypes.POINTER(c_double), c_int, c_void_p, ctypes.c_ulonglong,
                                          ctypes.POINTER(ctypes.c_ulonglong)]),

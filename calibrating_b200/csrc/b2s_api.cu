@@ -500,6 +500,28 @@ int b2s_interpolate_sparse(b2s_handle c, int inter_type, const double *uvz, int 
     return B2S_OK;
 }
 
+int b2s_interpolate_rbf(b2s_handle c, const double *uvw, int n, const uint8_t *mask, int H, int W, double *out)
+{
+    if (!c || !out) return B2S_EINVAL;
+    if (W <= 0 || H <= 0) return fail(c, B2S_EINVAL, "b2s_interpolate_rbf: bad size");
+    if (n < 0 || (n > 0 && !uvw)) return fail(c, B2S_EINVAL, "b2s_interpolate_rbf: the samples are missing");
+    CK(c, cudaSetDevice(c->device));
+    const size_t npx = (size_t)W * H;
+    CK(c, c->pout.ensure(npx * 8));
+    uint8_t *dmask = nullptr;
+    if (mask) {
+        CK(c, c->pin.ensure(npx));
+        CK(c, cudaMemcpyAsync(c->pin.p, mask, npx, cudaMemcpyDefault, c->stream));
+        dmask = c->pin.as<uint8_t>();
+    }
+    CK(c, c->cl_pts.ensure((size_t)(n ? n : 1) * 24));
+    if (n) CK(c, cudaMemcpyAsync(c->cl_pts.p, uvw, (size_t)n * 24, cudaMemcpyDefault, c->stream));
+    CK(c, launch_rbf_fill(c, c->cl_pts.as<double>(), n, dmask, H, W, c->pout.as<double>()));
+    CK(c, cudaMemcpyAsync(out, c->pout.p, npx * 8, cudaMemcpyDefault, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return B2S_OK;
+}
+
 int b2s_set_cam1_model(b2s_handle c, double fx, double fy, double cx, double cy, const double k[12])
 {
     if (!c || !k) return B2S_EINVAL;

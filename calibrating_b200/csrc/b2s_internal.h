@@ -141,6 +141,7 @@ cudaError_t launch_gen_maps(b2s_ctx *c, const b2s_map_params &p, float *mapx, fl
                             uint16_t *fxy16);
 // resize.cu
 cudaError_t launch_resize_u8(b2s_ctx *c, const uint8_t *src, int sH, int sW, int cn, uint8_t *dst, int dH, int dW);
+cudaError_t launch_rbf_fill(b2s_ctx *c, const double *d_uvw, int n, const uint8_t *d_mask, int H, int W, double *d_out);
 cudaError_t launch_resize_nearest_f32(b2s_ctx *c, const float *src, int sH, int sW, float *dst, int dH, int dW, float mul);
 cudaError_t launch_resize_f32(b2s_ctx *c, const float *src, int sH, int sW, float *dst, int dH, int dW, float mul, float div);
 // cloud.cu

@@ -177,8 +177,42 @@ __global__ void __launch_bounds__(256) nearest_fill_kernel(const double *__restr
     out[i] = ((!mask || mask[i]) && sqrt(best) < distance) ? (float)bz : 0.f;
 }
 
+// "rbf" (thin plate): sum_i w_i * r^2 * log(r) = sum_i w_i * 0.5 * r2 * log(r2); float64, samples staged through shared memory
+__global__ void __launch_bounds__(256) rbf_fill_kernel(const double *__restrict__ uvw, int n, const uint8_t *__restrict__ mask, int H, int W,
+                                                       double *__restrict__ out)
+{
+    __shared__ double su[256], sv[256], sw[256];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const double px = (double)x, py = (double)y;
+    double acc = 0.0;
+    for (int base = 0; base < n; base += 256) {
+        const int k = base + threadIdx.x;
+        if (k < n) {
+            su[threadIdx.x] = uvw[3 * k];
+            sv[threadIdx.x] = uvw[3 * k + 1];
+            sw[threadIdx.x] = uvw[3 * k + 2];
+        }
+        __syncthreads();
+        const int m = min(256, n - base);
+        for (int j = 0; j < m; j++) {
+            const double du = su[j] - px, dv = sv[j] - py, r2 = du * du + dv * dv;
+            if (r2 > 0.0) acc += sw[j] * (0.5 * r2 * log(r2));
+        }
+        __syncthreads();
+    }
+    if (x >= W) return;
+    const size_t i = (size_t)y * W + x;
+    out[i] = (!mask || mask[i]) ? acc : 0.0;
+}
+
 } // namespace
 
+cudaError_t launch_rbf_fill(b2s_ctx *c, const double *d_uvw, int n, const uint8_t *d_mask, int H, int W, double *d_out)
+{
+    rbf_fill_kernel<<<dim3((W + 255) / 256, H), 256, 0, c->stream>>>(d_uvw, n, d_mask, H, W, d_out);
+    c->launches++;
+    return cudaGetLastError();
+}
 cudaError_t launch_plane_fill(b2s_ctx *c, const uint8_t *d_mask, int H, int W, double a, double b, double cc, float *d_out)
 {
     plane_fill_kernel<<<dim3((W + 255) / 256, H), 256, 0, c->stream>>>(d_mask, H, W, a, b, cc, d_out);

@@ -63,8 +63,7 @@ def point_cloud_to_depth(points, K, xy, device=0):
 def interpolate_uvzs(uvzs, hw=None, constrained_type=None, inter_type="lstsq", distance=2, device=0):
     """calibrating/utils.py:356-411: densify sparse (u, v, z) samples to an (h, w) float32 image.  The sparse half (a 3-parameter
     least-squares fit on a few hundred points, the convex hull of the samples) stays on the host like the reference's; the dense
-    half -- one value per pixel -- runs on the device.  inter_type "lstsq" or "nearest" ("rbf" needs scipy's thin-plate solver and
-    is not offered)."""
+    half -- one value per pixel -- runs on the device.  inter_type "lstsq", "nearest" (float32 result) or "rbf" (thin plate, float64 result)."""
     import cv2
     uvzs = np.asarray(uvzs)
     if hw is None:
@@ -88,8 +87,21 @@ def interpolate_uvzs(uvzs, hw=None, constrained_type=None, inter_type="lstsq", d
         pts = np.ascontiguousarray(uvzs[:, :3], np.float64)
         h.call("b2s_interpolate_sparse", 1, _ffi.ptr(pts), len(pts), None, None if mask is None else _ffi.ptr(mask), hw[0], hw[1], float(distance),
                _ffi.ptr(out))
+    elif inter_type == "rbf":
+        # scipy.interpolate.Rbf(u, v, z, function="thin_plate", smooth=0.5) (utils.py:373-387; the reference's `episilon=5` is a
+        # misspelt keyword that scipy stores and ignores): the n x n solve on the host, the dense evaluation on the device, float64
+        p = np.float64(uvzs[:, :2])
+        r = np.sqrt(((p[:, None, :] - p[None, :, :]) ** 2).sum(-1))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            A = np.where(r > 0, r ** 2 * np.log(r), 0.0) - np.eye(len(p)) * 0.5
+        uvw = np.ascontiguousarray(np.concatenate([p, np.linalg.solve(A, np.float64(uvzs[:, 2]))[:, None]], 1))
+        z = np.empty(hw, np.float64)
+        h.call("b2s_interpolate_rbf", _ffi.ptr(uvw), len(uvw), None if mask is None else _ffi.ptr(mask), hw[0], hw[1], _ffi.ptr(z))
+        # the reference appends the result to the (u, v, 0) grid rows and hands all of it to uvzs_to_arr2d, which therefore returns TWO
+        # channels (utils.py:383-387, 410): channel 0 is the grid's zero column, channel 1 the interpolated surface.  Kept as it is.
+        out = np.stack([np.zeros(hw, np.float64), z], -1)
     else:
-        raise NotImplementedError("inter_type %r: only 'lstsq' and 'nearest' run on the device" % (inter_type,))
+        raise NotImplementedError("inter_type %r: 'lstsq', 'nearest' and 'rbf'" % (inter_type,))
     return out
 
 

@@ -214,16 +214,20 @@ int b2s_depth_to_point_cloud(b2s_handle h, const double *depth, int H, int W, do
  * rounded half-to-even to the pixel grid of (W,H); of the points landing on a pixel the smallest z survives (the reference
  * writes in the order of descending z), pixels without a point get bg_value. */
 int b2s_point_cloud_to_depth(b2s_handle h, const double *points, unsigned long long n, const double K[9], int W, int H, double bg_value, double *out);
+/* dst (dH,dW) f32 = cv2.resize(src (sH,sW) f32, INTER_NEAREST) * mul: the up-scale of FeatureMatchingAsStereoMatching
+ * (calibrating/stereo_matching.py:133-140: `disparity * hw[1] / resize_shape[1]`, then a nearest-neighbour resize). */
+int b2s_resize_nearest_f32(b2s_handle h, const float *src, int sH, int sW, float *dst, int dH, int dW, float mul);
 /* calibrating/utils.py:347-415 interpolate_uvzs, the dense half (what MatchingByBoard and
  * FeatureMatchingAsStereoMatching densify their sparse disparities with).  out: (H,W) f32.  mask (nullable, (H,W) u8): the pixels to
  * fill (the convex hull the caller rasterised), others are 0.
  *   inter_type 0 ("lstsq"):   out = abc[0]*x + abc[1]*y + abc[2] (the caller fitted the plane; float64, stored float32)
  *   inter_type 1 ("nearest"): out = z of the nearest of the n points uvz (n,3) f64 if it is closer than `distance`, else 0 */
-/* dst (dH,dW) f32 = cv2.resize(src (sH,sW) f32, INTER_NEAREST) * mul: the up-scale of FeatureMatchingAsStereoMatching
- * (calibrating/stereo_matching.py:133-140: `disparity * hw[1] / resize_shape[1]`, then a nearest-neighbour resize). */
-int b2s_resize_nearest_f32(b2s_handle h, const float *src, int sH, int sW, float *dst, int dH, int dW, float mul);
 int b2s_interpolate_sparse(b2s_handle h, int inter_type, const double *uvz, int n, const double abc[3], const uint8_t *mask, int H, int W,
                            double distance, float *out);
+/* inter_type "rbf" of interpolate_uvzs (utils.py:373-387: scipy.interpolate.Rbf, thin plate): out (H,W) f64 =
+ * sum_i w_i * r_i^2 * log(r_i), r_i = distance of the pixel to sample i; uvw (n,3) f64 = (u, v, node weight w): the caller solved the
+ * n x n system (phi(r_ij) - smooth * I) w = z on the host.  mask as above. */
+int b2s_interpolate_rbf(b2s_handle h, const double *uvw, int n, const uint8_t *mask, int H, int W, double *out);
 int b2s_set_option(b2s_handle h, int option, int value);
 /* sha256 (first 16 hex digits) over the CUDA sources this library was built from (calibrating_b200/build.py); ties a
  * profile under profiles/ to the binary it was measured on. */

@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): CPU restatement of the reference's sparse -> dense interpolation,
-calibrating/utils.py:347-411 (`interpolate_sparse2d`, `interpolate_uvzs`; inter_type "lstsq" and "nearest").
+calibrating/utils.py:347-411 (`interpolate_sparse2d`, `interpolate_uvzs`; inter_type "lstsq", "nearest" and "rbf").
 
 Pinned against outputs of the real reference (tests/golden/sparse_small.npz, written by tests/golden/make_golden.py).
 "nearest" is a brute-force search instead of scipy's KDTree: equal to it wherever the nearest sample is unique (of equally near
@@ -38,6 +38,17 @@ def interpolate_uvzs(uvzs, hw=None, constrained_type=None, inter_type="lstsq", d
             k = d2.argmin(1)
             near = np.sqrt(d2[np.arange(hw[1]), k]) < distance
             val[y, near] = np.float32(uvzs[k[near], 2])
+    elif inter_type == "rbf":  # utils.py:373-387: scipy.interpolate.Rbf(u, v, z, function="thin_plate", smooth=0.5), restated with numpy:
+        # nodes = solve(phi(r_ij) - 0.5 I, z), phi(r) = r^2 log r; value(p) = sum_i nodes_i phi(|p - p_i|).  The reference appends the
+        # result to the (u, v, 0) grid rows, so its dense array has two channels: zeros and the surface (float64).
+        p = np.float64(uvzs[:, :2])
+        r = np.sqrt(((p[:, None, :] - p[None, :, :]) ** 2).sum(-1))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            A = np.where(r > 0, r ** 2 * np.log(r), 0.0) - np.eye(len(p)) * 0.5
+            w = np.linalg.solve(A, np.float64(uvzs[:, 2]))
+            d = np.sqrt((xs[..., None] - p[:, 0]) ** 2 + (ys[..., None] - p[:, 1]) ** 2)
+            z = np.where(d > 0, d ** 2 * np.log(d), 0.0) @ w
+        return np.stack([np.zeros(hw), np.where(mask, z, 0.0)], -1)
     else:
         raise NotImplementedError(inter_type)
     return np.where(mask, val, np.float32(0))

@@ -87,7 +87,8 @@ def sparse_case(calibrating):
                         lstsq_nohw=U.interpolate_uvzs(uvzs.copy()),
                         nearest2=U.interpolate_uvzs(uvzs.copy(), hw, None, "nearest"),
                         nearest6_hull=U.interpolate_uvzs(uvzs.copy(), hw, True, "nearest", distance=6),
-                        sparse2d_hull=U.interpolate_sparse2d(sparse.copy(), "convex_hull"), board_dense=board)
+                        sparse2d_hull=U.interpolate_sparse2d(sparse.copy(), "convex_hull"), board_dense=board,
+                        rbf=U.interpolate_uvzs(uvzs[:120].copy(), hw, None, "rbf"), rbf_hull=U.interpolate_uvzs(uvzs[:120].copy(), hw, True, "rbf"))
 
 
 def main():

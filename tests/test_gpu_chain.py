@@ -359,7 +359,11 @@ def test_sparse_interpolation_and_sparse_matchers(golden_dir):
     out = cb.interpolate_uvzs(np.zeros((0, 3)), (4, 5))
     assert out.shape == (4, 5) and not out.any()
     with pytest.raises(NotImplementedError):
-        cb.interpolate_uvzs(g["uvzs"], hw, inter_type="rbf")
+        cb.interpolate_uvzs(g["uvzs"], hw, inter_type="cubic")
+    for key, hull in (("rbf", None), ("rbf_hull", True)):  # thin plate: host solve, dense evaluation on the device, float64
+        got = cb.interpolate_uvzs(g["uvzs"][:120], hw, hull, "rbf")
+        assert got.shape == g[key].shape and got.dtype == np.float64
+        assert np.allclose(got, g[key], rtol=0, atol=1e-9 * np.abs(g[key]).max()), np.abs(got - g[key]).max()
     # 1080p, 2000 samples (more than one shared-memory tile of the nearest search), against the restatement
     rng = np.random.default_rng(4)
     uvz = np.stack([rng.random(2000) * 1900 + 5, rng.random(2000) * 1060 + 5, rng.random(2000) * 50 + 1], 1)

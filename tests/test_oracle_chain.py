@@ -88,3 +88,8 @@ def test_sparse_interpolation_restatement_matches_reference(golden_dir):
     with np.errstate(divide="ignore"):
         assert np.array_equal(1 / sparse.interpolate_sparse2d(1 / g["sparse"], "convex_hull"), g["board_dense"])
     assert sparse.interpolate_uvzs(np.zeros((0, 3)), (4, 5)).shape == (4, 5)
+    # thin-plate "rbf" (scipy.interpolate.Rbf in the reference): float64, two channels (the reference's own output shape)
+    for key, hull in (("rbf", None), ("rbf_hull", True)):
+        got = sparse.interpolate_uvzs(g["uvzs"][:120], hw, hull, "rbf")
+        assert got.shape == g[key].shape == hw + (2,) and got.dtype == np.float64
+        assert np.allclose(got, g[key], rtol=0, atol=1e-9 * np.abs(g[key]).max())

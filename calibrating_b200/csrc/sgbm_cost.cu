@@ -71,8 +71,8 @@ constexpr int NRP_WIDE = (TX + 2 * 5 + 512) / 2 + 3; // ... and for D <= 512
 
 // LAYOUT 1 (block layout of the wavefront kernel: a word = disparities (d, d+8)): the right-pixel table holds ONE entry per
 // reversed index m = (pixel m, pixel m+8) instead of the two alignment copies of neighbouring pairs; 2*NRP entries per plane.
-template <int CN, int NRP, int LAYOUT>
-__global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4 *__restrict__ PL, const uchar4 *__restrict__ PR,
+template <int CN, int NRP, int LAYOUT, bool GROUPED = false>
+__global__ void __launch_bounds__(COST_THREADS, 4) pixcost_hsum_kernel(const uchar4 *__restrict__ PL, const uchar4 *__restrict__ PR,
                                                                     int16_t *__restrict__ hs, SgbmGeom g)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -114,13 +114,75 @@ __global__ void __launch_bounds__(COST_THREADS) pixcost_hsum_kernel(const uchar4
         }
         uchar4 a = prow[clampi(xrmax - m0, 0, g.W - 1)];
         uchar4 b = prow[clampi(xrmax - m1, 0, g.W - 1)];
-        sR[i] = make_uint4(a.x | ((uint32_t)b.x << 16), a.y | ((uint32_t)b.y << 16), a.z | ((uint32_t)b.z << 16), 0u);
+        // GROUPED: a lane reads entries 2*lane + const, so the entries of a copy are stored de-interleaved (even ones, then odd ones):
+        // the lanes of a quarter-warp then hit eight different 16-byte bank groups
+        const int pos = (GROUPED && LAYOUT == 0) ? pc * NRP + (wd >> 1) + (wd & 1) * ((NRP + 1) / 2) : i;
+        sR[pos] = make_uint4(a.x | ((uint32_t)b.x << 16), a.y | ((uint32_t)b.y << 16), a.z | ((uint32_t)b.z << 16), 0u);
     }
     __syncthreads();
 
-    // phase 1: warp -> column j, lane -> disparity pairs d0 = 2*(lane + 32*i)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t Bp = BT_BIAS * 0x10001u, unbias = (uint32_t)(CN * (BT_BIAS + BT_BIAS / 4)) * 0x10001u;
+    if constexpr (GROUPED && LAYOUT == 0) {
+        // phase 1, grouped (round 2): the kernel is bound by the shared-memory data pipe (89 % busy, profiles/r02_pixcost_a_raw.csv), and
+        // most of its wavefronts are the LDS.128 of the right-pixel pairs, one per plane and voxel pair.  The pair that column j needs for
+        // word q is the pair that column j+2 needs for word q+1 (same right pixels, same alignment copy), so a warp takes GC = 4 columns of
+        // one parity and a lane two adjacent words of each: 5 table loads per plane serve 8 voxel pairs instead of 8.  The loop over the
+        // planes is outermost (the left constants of four columns for one plane at a time), eight accumulators stay in registers.
+        constexpr int GC = 4;
+        const int ngi = ((TXH + 1) / 2 + GC - 1) / GC; // groups per parity
+        for (int gidx = wid; gidx < 2 * ngi; gidx += COST_THREADS / 32) {
+            const int par = gidx & 1, j0 = par + 2 * GC * (gidx >> 1);
+            if (j0 >= TXH) continue;
+            const int mj0 = TXH - 1 - j0; // reversed right index of d = 0 for column j0; column j0 + 2c: mj0 - 2c
+            const uint4 *rb = sR + (mj0 & 1) * NRP; // the alignment copy of this parity; entry index = (mj0 >> 1) + word - column offset
+            for (int w2 = lane; w2 < DW / 2; w2 += 32) { // words 2*w2, 2*w2+1 = disparities 4*w2 .. 4*w2+3
+                const int q0 = 2 * w2;
+                uint32_t acc[GC][2];
+#pragma unroll
+                for (int c = 0; c < GC; c++) acc[c][0] = acc[c][1] = 0;
+#pragma unroll
+                for (int p = 0; p < NPL; p++) {
+                    uint4 E[GC + 1]; // entry e - (GC-1): voxel (column c, word k) uses entry k - c
+#pragma unroll
+                    for (int e = 0; e < GC + 1; e++) {
+                        const int idx = max((mj0 >> 1) + q0 + e - (GC - 1), 0); // (negative only for columns past the tile)
+                        E[e] = rb[p * 2 * NRP + (idx >> 1) + (idx & 1) * ((NRP + 1) / 2)];
+                    }
+#pragma unroll
+                    for (int c = 0; c < GC; c++) {
+                        const uint4 L4 = sL[min(j0 + 2 * c, TXH - 1) * NPL + p];
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const uint4 R4 = E[k - c + (GC - 1)];
+                            const uint32_t V = R4.x, V0 = R4.y, V1 = R4.z;
+                            uint32_t c0 = __vimax3_s16x2(L4.x - V1, V0 + L4.y, Bp);
+                            uint32_t c1 = __vimax3_s16x2(V + L4.z, L4.w - V, Bp);
+                            uint32_t cc = __vmins2(c0, c1);
+                            if (p >= CN) cc = (cc >> 2) & 0x007F007Fu;
+                            acc[c][k] += cc;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < GC; c++) {
+                    const int j = j0 + 2 * c, x1 = xlo + j;
+                    if (j >= TXH) continue;
+                    const bool inside = x1 >= 0 && x1 < g.width1;
+                    uint32_t o[2];
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const int d0 = 2 * (q0 + k);
+                        uint32_t v = acc[c][k] - unbias;
+                        if (d0 + 1 >= g.D) v &= 0x0000FFFFu;
+                        o[k] = (inside && d0 < g.D) ? v : 0u; // padded d-lanes and columns outside the cost volume are zero
+                    }
+                    *(uint2 *)(pixw + j * DW + q0) = make_uint2(o[0], o[1]);
+                }
+            }
+        }
+    } else
+    // phase 1: warp -> column j, lane -> disparity pairs d0 = 2*(lane + 32*i)
     for (int j = wid; j < TXH; j += COST_THREADS / 32) {
         const int x1 = xlo + j;
         uint32_t *out = pixw + j * DW;
@@ -323,7 +385,10 @@ cudaError_t launch_cost_volume(b2s_ctx *c, const uint8_t *d_left, const uint8_t 
     cudaError_t e;
     if (g.layout == 0) {
         if (nrp == NRP_WIDE) e = g.cn == 3 ? launch(pixcost_hsum_kernel<3, NRP_WIDE, 0>) : launch(pixcost_hsum_kernel<1, NRP_WIDE, 0>);
-        else if (g.cn == 3) e = nrp == 104 ? launch(pixcost_hsum_kernel<3, 104, 0>) : launch(pixcost_hsum_kernel<3, NRP_MAX, 0>);
+        else if (g.NP >= 2 && !(getenv("B2S_COST_GROUPED") && atoi(getenv("B2S_COST_GROUPED")) == 0)) { // two words per lane need Dp >= 128
+            if (g.cn == 3) e = nrp == 104 ? launch(pixcost_hsum_kernel<3, 104, 0, true>) : launch(pixcost_hsum_kernel<3, NRP_MAX, 0, true>);
+            else e = nrp == 104 ? launch(pixcost_hsum_kernel<1, 104, 0, true>) : launch(pixcost_hsum_kernel<1, NRP_MAX, 0, true>);
+        } else if (g.cn == 3) e = nrp == 104 ? launch(pixcost_hsum_kernel<3, 104, 0>) : launch(pixcost_hsum_kernel<3, NRP_MAX, 0>);
         else e = nrp == 104 ? launch(pixcost_hsum_kernel<1, 104, 0>) : launch(pixcost_hsum_kernel<1, NRP_MAX, 0>);
     } else {
         if (g.cn == 3) e = nrp == 104 ? launch(pixcost_hsum_kernel<3, 104, 1>) : launch(pixcost_hsum_kernel<3, NRP_MAX, 1>);

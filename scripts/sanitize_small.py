@@ -40,3 +40,13 @@ cam1, cam2 = cb.Cam.load(rig["cam1"]), cb.Cam.load(rig["cam2"])
 T = np.eye(4); T[:3, 3] = [0.05, 0, 0.01]
 print("project", (cam1.project_cam2_depth(cam2, res["unrectify_depth"], T=T) > 0).mean())
 print("batch", len(st.get_depth_batch([(img1, img2)] * 3, streams=2)))
+# round 2: device-side max_size (resize kernels), point clouds, sparse interpolation
+st3 = cb.Stereo.load(rig).set_stereo_matching(cb.SemiGlobalBlockMatching({"max_size": 200, "num_disparities": 48}), max_depth=3.5)
+print("max_size chain", st3.get_depth(img1, img2)["unrectify_depth"].shape)
+K = np.float64([[210.0, 0, 81.5], [0, 209.0, 58.25], [0, 0, 1]])
+dm = np.random.default_rng(0).random((60, 80)) * 2 + 0.5
+pc = cb.depth_to_point_cloud(dm, K, interpolation_rate=1.5)
+print("cloud", pc.shape, cb.point_cloud_to_depth(pc, K, (80, 60)).shape)
+uvz = np.random.default_rng(1).random((300, 3)) * [70, 50, 3] + [5, 5, 1]
+for it in ("lstsq", "nearest", "rbf"):
+    print("interpolate", it, cb.interpolate_uvzs(uvz[:100], (60, 80), True, it).shape)

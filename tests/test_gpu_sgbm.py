@@ -95,6 +95,24 @@ def test_wavefront_schedule(handle, seed, monkeypatch):
         handle.call("b2s_set_option", 3, 0)
 
 
+@pytest.mark.parametrize("grouped", ["1", "0"])
+@pytest.mark.parametrize("seed", range(8))
+def test_cost_kernel_lane_mappings(handle, seed, grouped, monkeypatch):
+    """pixcost_hsum_kernel with the grouped lane mapping (four columns of one parity per warp, two adjacent words per lane; the default
+    from 65 disparities on) and with the round-1 mapping (B2S_COST_GROUPED=0): both give the oracle's cost volume, for 65..256
+    disparities incl. padded ranges, 1 and 3 channels, blocks 1..11, tiles cut by the image border."""
+    monkeypatch.setenv("B2S_COST_GROUPED", grouped)
+    rng = np.random.default_rng(4200 + seed)
+    D = [65, 96, 128, 130, 192, 218, 250, 256][seed]
+    c = _case(rng, D=D, mode=seed % 2)
+    c["w"] = D + c["p"]["min_disparity"] + [12, 70, 129, 64, 200, 131, 66, 90][seed]
+    l, r, _ = synth.rectified_pair(c["h"], c["w"], D, seed, c["cn"])
+    ref = osgbm.sgbm_compute(l, r, want_volumes=True, **c["p"])
+    got = cb.StereoSGBM(handle=handle, **c["p"]).compute(l, r)
+    assert np.array_equal(handle.fetch_volume(0), ref["C"]), "cost volume"
+    assert np.array_equal(got, ref["disp"])
+
+
 @pytest.mark.parametrize("split", ["1", "0"])
 @pytest.mark.parametrize("cols", ["1", "2", "3", "5", "13", "14", "32", "legacy"])
 @pytest.mark.parametrize("seed", [1, 2, 3, 5, 6])

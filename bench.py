@@ -448,7 +448,7 @@ def main():
                      "build_hash": build_hash,
                      "first_launch_plain_scan": {"ms_per_launch": [round(t, 4) for t in alt_parts], "group_ms": round(float(sum(alt_parts)), 4),
                                                  "frac": AGG_BYTES_PER_PAIR / (float(sum(alt_parts)) * 1e-3) / 1e9 / peak,
-                                                 "note": "round-1 convention: C finished by the cost stage (vsum_kernel), first launch = agg_hscan_kernel<INIT>"},
+                                                 "note": "round-1 convention: C finished by the cost stage (vsum_kernel), first launch = agg_hscan_kernel<INIT>; the round-1 bench line (frac 0.237) used this form, so this is the figure to compare it with"},
                      "batched": {"handles_in_flight": S, "ms_per_pair": round(agg_batched_ms, 4), "achieved": AGG_BYTES_PER_PAIR / (agg_batched_ms * 1e-3) / 1e9,
                                  "frac": AGG_BYTES_PER_PAIR / (agg_batched_ms * 1e-3) / 1e9 / peak,
                                  "note": "the group of %d handles enqueued round-robin on their streams (on the finished C), wall = first start to last end" % S},
